@@ -1,0 +1,482 @@
+// Implicit-GEMM convolution / GEMM on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA operand loads).
+//
+//   forward / data-gradient / plain GEMM :  igemm_kernel   (A = activations, K-major via 4-D TMA boxes with zero fill
+//                                                            doing the conv padding; B = packed weights, K-major)
+//   weight gradient                      :  wgrad_kernel   (A = dY^T, B = X^T: both MN-major straight from NHWC)
+//
+// Replaces aten::convolution / convolution_backward (cuDNN) and addmm at the call sites listed in include/cdae.h.
+// Warp roles per CTA (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> global), one TMEM lane quarter each.
+#include <mutex>
+
+#include "sm100.cuh"
+
+namespace cdae {
+using namespace sm100;
+
+// ------------------------------------------------------------------------------------------------ host: tensor maps
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, const uint32_t* elem_strides) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return CDAE_ERR_CUDA; }
+  cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = elem_strides ? elem_strides[i] : 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu] box [%u %u %u %u]", (int)r, rank,
+              (unsigned long long)gd[0], (unsigned long long)(rank > 1 ? gd[1] : 0),
+              (unsigned long long)(rank > 2 ? gd[2] : 0), (unsigned long long)(rank > 3 ? gd[3] : 0), bx[0],
+              rank > 1 ? bx[1] : 0, rank > 2 ? bx[2] : 0, rank > 3 ? bx[3] : 0);
+    return CDAE_ERR_CUDA;
+  }
+  return CDAE_OK;
+}
+
+static inline int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// pixel-tile geometry: BW*BH*BNI == pixels, every factor a power of two
+static void tile_geometry(int pixels, int OHt, int OWt, int* BW, int* BH, int* BNI) {
+  int bw = pow2_ceil(OWt); if (bw > pixels) bw = pixels;
+  int bh = pow2_ceil(OHt); if (bh > pixels / bw) bh = pixels / bw;
+  *BW = bw; *BH = bh; *BNI = pixels / (bw * bh);
+}
+
+// ------------------------------------------------------------------------------------------------ forward kernel
+struct alignas(64) IgemmKParams {
+  CUtensorMap tmA[4];
+  CUtensorMap tmB;
+  cdae_seg seg[CDAE_MAX_SEG];
+  int nseg, nkb;
+  int BW, BH, BNI, tilesW, tilesH;
+  int in_stride;
+  int Nimg, OHt, OWt;
+  int OH, OW, ldo, cout, sps, ooh, oow, out_mode;
+  void* out;
+  const float* bias;
+  const float* bias2;
+  const __nv_bfloat16* resid;
+  int ldr;
+};
+
+constexpr int kATileBytes = 128 * 128;  // 128 pixels x 64 bf16
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ IgemmKParams p) {
+  constexpr int kBTileBytes = BN * 128;
+  constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  constexpr uint32_t kIdesc = make_idesc_bf16(128, BN, 0, 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+  // bars[0..S) full, [S..2S) empty, [2S] tmem_full ; then tmem base address
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile coordinates
+  const int mt = blockIdx.x;
+  const int tw = mt % p.tilesW, th = (mt / p.tilesW) % p.tilesH, tn = mt / (p.tilesW * p.tilesH);
+  const int n0 = blockIdx.y * BN;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int cw = tw * p.BW * p.in_stride, chh = th * p.BH * p.in_stride, cn = tn * p.BNI;
+      int kb = 0;
+      for (int sg = 0; sg < p.nseg; ++sg) {
+        const cdae_seg g = p.seg[sg];
+        const CUtensorMap* tma = &p.tmA[g.src];
+        for (int ch = 0; ch < g.nchunk; ++ch, ++kb) {
+          const int s = kb % STAGES;
+          const uint32_t ph = (kb / STAGES) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_expect_tx(full_bar(s), kStageBytes);
+          const uint32_t a_dst = smem_base + s * kStageBytes;
+          tma_load_4d(a_dst, tma, full_bar(s), g.c0 + ch * 64, cw + g.dw, chh + g.dh, cn);
+          tma_load_2d(a_dst + kATileBytes, &p.tmB, full_bar(s), g.wk + ch * 64, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    for (int kb = 0; kb < p.nkb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = smem_base + s * kStageBytes;
+        const uint64_t adesc = smem_desc_kmajor_sw128(a_addr);
+        const uint64_t bdesc = smem_desc_kmajor_sw128(a_addr + kATileBytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // 4 x (K = 16 bf16 = 32 B) inside the 128 B swizzle row: +2 in the >>4 address field
+          umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0);
+        umma_commit(empty_bar(s));
+        if (kb == p.nkb - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    // epilogue: warp q owns TMEM lanes [32q, 32q+32)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int bw = r % p.BW, bh = (r / p.BW) % p.BH, bn = r / (p.BW * p.BH);
+    const int n = tn * p.BNI + bn, ty = th * p.BH + bh, tx = tw * p.BW + bw;
+    const bool row_ok = (n < p.Nimg) && (ty < p.OHt) && (tx < p.OWt);
+    const int oy = ty * p.sps + p.ooh, ox = tx * p.sps + p.oow;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    constexpr int CH = BN < 32 ? 16 : 32;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += CH) {
+      uint32_t acc[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c;
+      __syncwarp();  // tcgen05.ld is warp-collective (.sync.aligned): keep the warp converged around it
+      if (CH == 32) tmem_ld32(taddr, acc); else tmem_ld16(taddr, acc);
+      tmem_ld_wait();
+      const int co0 = n0 + c;
+      if (!row_ok || co0 >= p.cout) {
+        // nothing to write for this lane / column chunk
+      } else if (p.out_mode == 0) {
+        const size_t pix = ((size_t)n * p.OH + oy) * p.OW + ox;
+        __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + co0;
+        const __nv_bfloat16* rrow = p.resid ? p.resid + pix * p.ldr + co0 : nullptr;
+#pragma unroll
+        for (int j = 0; j < CH; j += 8) {
+          if (co0 + j >= p.cout) break;
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[j + e]);
+          if (p.bias) {
+            const float4 b0 = *reinterpret_cast<const float4*>(p.bias + co0 + j);
+            const float4 b1 = *reinterpret_cast<const float4*>(p.bias + co0 + j + 4);
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+          }
+          if (p.bias2) {
+            const float4 b0 = *reinterpret_cast<const float4*>(p.bias2 + co0 + j);
+            const float4 b1 = *reinterpret_cast<const float4*>(p.bias2 + co0 + j + 4);
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+          }
+          if (rrow) {
+            float rv[8]; unpack8(ld8(rrow + j), rv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] += rv[e];
+          }
+          st8(orow + j, pack8(v));
+        }
+      } else {
+        // NCHW fp32 (final eps conv): consecutive lanes are consecutive pixels -> coalesced per channel
+        float* o = reinterpret_cast<float*>(p.out);
+        for (int j = 0; j < CH; ++j) {
+          const int co = co0 + j;
+          if (co >= p.cout) break;
+          float v = __uint_as_float(acc[j]);
+          if (p.bias) v += p.bias[co];
+          o[(((size_t)n * p.cout + co) * p.OH + oy) * p.OW + ox] = v;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+}
+
+template <int BN, int STAGES>
+static int launch_igemm(const IgemmKParams& kp, dim3 grid, cudaStream_t st) {
+  constexpr int smem = STAGES * (kATileBytes + BN * 128) + 1024 + 256;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  });
+  if (attr_err != cudaSuccess) { set_error("igemm smem attribute: %s", cudaGetErrorString(attr_err)); return CDAE_ERR_CUDA; }
+  igemm_kernel<BN, STAGES><<<grid, 192, smem, st>>>(kp);
+  CDAE_CHECK_LAUNCH("igemm_kernel");
+  return CDAE_OK;
+}
+
+}  // namespace cdae
+
+using namespace cdae;
+
+extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
+  CDAE_CHECK_ARG(d && d->out && d->wgt && d->nsrc >= 1 && d->nsrc <= 4, "igemm: bad descriptor");
+  CDAE_CHECK_ARG(d->nseg >= 1 && d->nseg <= CDAE_MAX_SEG, "igemm: nseg %d out of range", d->nseg);
+  CDAE_CHECK_SHAPE(d->in_stride == 1 || d->in_stride == 2, "igemm: in_stride %d", d->in_stride);
+  CDAE_CHECK_SHAPE(d->wk % 8 == 0, "igemm: weight K %d must be a multiple of 8", d->wk);
+  IgemmKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  const int es = d->in_stride;
+  const int OHt = (d->H + es - 1) / es, OWt = (d->W + es - 1) / es;
+  tile_geometry(128, OHt, OWt, &kp.BW, &kp.BH, &kp.BNI);
+  kp.tilesW = (OWt + kp.BW - 1) / kp.BW;
+  kp.tilesH = (OHt + kp.BH - 1) / kp.BH;
+  const int tilesN = (d->N + kp.BNI - 1) / kp.BNI;
+  kp.in_stride = es; kp.Nimg = d->N; kp.OHt = OHt; kp.OWt = OWt;
+  kp.OH = d->OH; kp.OW = d->OW; kp.ldo = d->ldo; kp.cout = d->cout;
+  kp.sps = d->sps > 0 ? d->sps : 1; kp.ooh = d->ooh; kp.oow = d->oow; kp.out_mode = d->out_mode;
+  kp.out = d->out; kp.bias = d->bias; kp.bias2 = d->bias2; kp.resid = reinterpret_cast<const __nv_bfloat16*>(d->resid); kp.ldr = d->ldr;
+  CDAE_CHECK_SHAPE(kp.out_mode == 1 || (d->cout % 8 == 0 && d->ldo % 8 == 0), "igemm: NHWC output needs cout, ldo %% 8 == 0");
+  CDAE_CHECK_SHAPE(!d->resid || d->ldr % 8 == 0, "igemm: residual pitch %% 8");
+  for (int i = 0; i < d->nsrc; ++i) {
+    CDAE_CHECK_ARG(d->src[i], "igemm: null source %d", i);
+    CDAE_CHECK_SHAPE(d->src_c[i] % 8 == 0, "igemm: source %d channels %d must be a multiple of 8", i, d->src_c[i]);
+    const uint64_t C = d->src_c[i];
+    uint64_t dims[4] = {C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
+    uint64_t str[3] = {C * 2, C * 2 * d->W, C * 2 * (uint64_t)d->W * d->H};
+    uint32_t box[4] = {64, (uint32_t)(kp.BW * es), (uint32_t)(kp.BH * es), (uint32_t)kp.BNI};
+    uint32_t est[4] = {1, (uint32_t)es, (uint32_t)es, 1};
+    int rc = make_tmap_bf16(&kp.tmA[i], d->src[i], 4, dims, str, box, est);
+    if (rc) return rc;
+  }
+  int bn = d->bn;
+  if (bn == 0) bn = d->cout >= 128 ? 128 : d->cout >= 64 ? 64 : d->cout > 16 ? 32 : 16;
+  {
+    uint64_t dims[2] = {(uint64_t)d->wk, (uint64_t)d->wrows};
+    uint64_t str[1] = {(uint64_t)d->wk * 2};
+    uint32_t box[2] = {64, (uint32_t)bn};
+    int rc = make_tmap_bf16(&kp.tmB, d->wgt, 2, dims, str, box, nullptr);
+    if (rc) return rc;
+  }
+  int nkb = 0;
+  for (int i = 0; i < d->nseg; ++i) {
+    const cdae_seg& g = d->seg[i];
+    CDAE_CHECK_ARG(g.src >= 0 && g.src < d->nsrc && g.nchunk >= 1, "igemm: bad segment %d", i);
+    CDAE_CHECK_SHAPE(g.wk + g.nchunk * 64 <= d->wk + 56, "igemm: segment %d overruns weight K", i);
+    kp.seg[i] = g;
+    nkb += g.nchunk;
+  }
+  kp.nseg = d->nseg; kp.nkb = nkb;
+  dim3 grid(kp.tilesW * kp.tilesH * tilesN, (d->cout + bn - 1) / bn);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
+  switch (bn) {
+    case 16: return launch_igemm<16, 4>(kp, grid, st);
+    case 32: return launch_igemm<32, 4>(kp, grid, st);
+    case 64: return launch_igemm<64, 4>(kp, grid, st);
+    case 128: return launch_igemm<128, 3>(kp, grid, st);
+    case 256: return launch_igemm<256, 4>(kp, grid, st);
+    default: set_error("igemm: unsupported bn %d", bn); return CDAE_ERR_SHAPE;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ weight gradient
+namespace cdae {
+
+struct alignas(64) WgradKParams {
+  CUtensorMap tmDy;   // dY  [N, OH, OW, ldy]   box {64, bw, bh, bni}
+  CUtensorMap tmX;    // src [N, H, W, src_c]   box {64, bw*es, bh*es, bni}
+  int bw, bh, bni, tilesW, tilesH, ntiles;   // 64-pixel K tiles over the dY pixel grid
+  int es, ksize, c0;
+  int tiles_per_split;
+  float* dw; int dw_ld, taps, ci_off, cin_real, cout;
+};
+
+constexpr int kWgBoxBytes = 64 * 128;  // 64 pixels x 64 channels bf16
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ WgradKParams p) {
+  constexpr int kABytes = 2 * kWgBoxBytes;            // 128 output channels
+  constexpr int kBBytes = (BN / 64) * kWgBoxBytes;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr uint32_t kTmemCols = BN;
+  constexpr uint32_t kIdesc = make_idesc_bf16(128, BN, 1, 1);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int co0 = blockIdx.x * 128;
+  const int ci_tiles = gridDim.y / p.taps;
+  const int tap = blockIdx.y / ci_tiles, ci0 = (blockIdx.y % ci_tiles) * BN;
+  const int dh = p.ksize == 3 ? tap / 3 - 1 : 0, dw = p.ksize == 3 ? tap % 3 - 1 : 0;
+  const int t_begin = blockIdx.z * p.tiles_per_split;
+  int t_end = t_begin + p.tiles_per_split; if (t_end > p.ntiles) t_end = p.ntiles;
+  const int nkb = t_end - t_begin;
+
+  if (nkb > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int t = t_begin + kb;
+          const int tw = t % p.tilesW, th = (t / p.tilesW) % p.tilesH, tn = t / (p.tilesW * p.tilesH);
+          const int s = kb % STAGES;
+          const uint32_t ph = (kb / STAGES) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_expect_tx(full_bar(s), kStageBytes);
+          const uint32_t a_dst = smem_base + s * kStageBytes;
+          const int ow = tw * p.bw, oh = th * p.bh, nn = tn * p.bni;
+          tma_load_4d(a_dst, &p.tmDy, full_bar(s), co0, ow, oh, nn);
+          tma_load_4d(a_dst + kWgBoxBytes, &p.tmDy, full_bar(s), co0 + 64, ow, oh, nn);
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_4d(a_dst + kABytes + j * kWgBoxBytes, &p.tmX, full_bar(s), p.c0 + ci0 + j * 64, ow * p.es + dw,
+                        oh * p.es + dh, nn);
+        }
+      }
+    } else if (warp == 1) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_base + s * kStageBytes;
+          // MN-major: 64-channel blocks kWgBoxBytes apart (LBO), 8-pixel K groups 1024 B apart (SBO)
+          const uint64_t adesc = smem_desc_mnmajor_sw128(a_addr, kWgBoxBytes, 1024);
+          const uint64_t bdesc = smem_desc_mnmajor_sw128(a_addr + kABytes, kWgBoxBytes, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // K = 16 pixels = two 1024 B atoms = +128 in the >>4 address field
+            umma_f16(tmem_base, adesc + 128 * k, bdesc + 128 * k, kIdesc, (kb | k) != 0);
+          umma_commit(empty_bar(s));
+          if (kb == nkb - 1) umma_commit(tmem_full_bar);
+        }
+        __syncwarp();
+      }
+    } else {
+      const int q = warp & 3;
+      const int co = co0 + q * 32 + lane;
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t acc[32];
+        __syncwarp();
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, acc);
+        tmem_ld_wait();
+        float* row = p.dw + ((size_t)co * p.taps + tap) * p.dw_ld + p.ci_off + ci0 + c;
+        const int lim = p.cin_real - (ci0 + c);
+        if (co >= p.cout) {
+          // padded output-channel row: nothing to accumulate
+        } else if (lim >= 32 && (p.dw_ld % 4 == 0) && ((p.ci_off & 3) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            atomicAdd(reinterpret_cast<float4*>(row + j),
+                      make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]),
+                                  __uint_as_float(acc[j + 3])));
+        } else {
+          for (int j = 0; j < 32 && j < lim; ++j) atomicAdd(row + j, __uint_as_float(acc[j]));
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+}
+
+template <int BN, int STAGES>
+static int launch_wgrad(const WgradKParams& kp, dim3 grid, cudaStream_t st) {
+  constexpr int smem = STAGES * (2 * kWgBoxBytes + (BN / 64) * kWgBoxBytes) + 1024 + 256;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  });
+  if (attr_err != cudaSuccess) { set_error("wgrad smem attribute: %s", cudaGetErrorString(attr_err)); return CDAE_ERR_CUDA; }
+  wgrad_kernel<BN, STAGES><<<grid, 192, smem, st>>>(kp);
+  CDAE_CHECK_LAUNCH("wgrad_kernel");
+  return CDAE_OK;
+}
+
+}  // namespace cdae
+
+extern "C" int cdae_wgrad(const cdae_wgrad_desc* d, cdae_stream s) {
+  CDAE_CHECK_ARG(d && d->dy && d->src && d->dw, "wgrad: bad descriptor");
+  CDAE_CHECK_SHAPE(d->ksize == 1 || d->ksize == 3, "wgrad: ksize %d", d->ksize);
+  CDAE_CHECK_SHAPE(d->in_stride == 1 || d->in_stride == 2, "wgrad: in_stride %d", d->in_stride);
+  CDAE_CHECK_SHAPE(d->ldy % 8 == 0 && d->src_c % 8 == 0, "wgrad: pitches must be multiples of 8");
+  WgradKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  tile_geometry(64, d->OH, d->OW, &kp.bw, &kp.bh, &kp.bni);
+  kp.tilesW = (d->OW + kp.bw - 1) / kp.bw;
+  kp.tilesH = (d->OH + kp.bh - 1) / kp.bh;
+  const int tilesN = (d->N + kp.bni - 1) / kp.bni;
+  kp.ntiles = kp.tilesW * kp.tilesH * tilesN;
+  kp.es = d->in_stride; kp.ksize = d->ksize; kp.c0 = d->c0;
+  kp.dw = d->dw; kp.dw_ld = d->dw_ld; kp.taps = d->ksize * d->ksize; kp.ci_off = d->ci_off;
+  kp.cin_real = d->cin_real > 0 ? d->cin_real : d->cin; kp.cout = d->cout;
+  {
+    const uint64_t C = d->ldy;
+    uint64_t dims[4] = {C, (uint64_t)d->OW, (uint64_t)d->OH, (uint64_t)d->N};
+    uint64_t str[3] = {C * 2, C * 2 * d->OW, C * 2 * (uint64_t)d->OW * d->OH};
+    uint32_t box[4] = {64, (uint32_t)kp.bw, (uint32_t)kp.bh, (uint32_t)kp.bni};
+    int rc = make_tmap_bf16(&kp.tmDy, d->dy, 4, dims, str, box, nullptr);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t C = d->src_c;
+    const int es = d->in_stride;
+    uint64_t dims[4] = {C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
+    uint64_t str[3] = {C * 2, C * 2 * d->W, C * 2 * (uint64_t)d->W * d->H};
+    uint32_t box[4] = {64, (uint32_t)(kp.bw * es), (uint32_t)(kp.bh * es), (uint32_t)kp.bni};
+    uint32_t est[4] = {1, (uint32_t)es, (uint32_t)es, 1};
+    int rc = make_tmap_bf16(&kp.tmX, d->src, 4, dims, str, box, est);
+    if (rc) return rc;
+  }
+  const int bn = d->cin > 64 ? 128 : 64;
+  const int co_tiles = (d->cout + 127) / 128, ci_tiles = (d->cin + bn - 1) / bn;
+  int splits = d->splits;
+  if (splits <= 0) {
+    const int base = co_tiles * ci_tiles * kp.taps;
+    splits = (2 * kNumSMs + base - 1) / base;
+    if (splits > kp.ntiles) splits = kp.ntiles;
+    if (splits < 1) splits = 1;
+  }
+  kp.tiles_per_split = (kp.ntiles + splits - 1) / splits;
+  splits = (kp.ntiles + kp.tiles_per_split - 1) / kp.tiles_per_split;
+  dim3 grid(co_tiles, ci_tiles * kp.taps, splits);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
+  if (bn == 128) return launch_wgrad<128, 6>(kp, grid, st);
+  return launch_wgrad<64, 6>(kp, grid, st);
+}

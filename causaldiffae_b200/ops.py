@@ -1,0 +1,269 @@
+"""Tensor-level wrappers over the C ABI (one function per libcdae entry point).
+
+These are thin: they check dtype/layout, allocate outputs with torch (device memory is PyTorch's job) and launch on
+the current stream.  Everything numerical happens in the hand-written kernels; there is no torch fallback.
+Activations are NHWC bf16 tensors [N, H, W, C] (or [rows, C] for plain GEMMs)."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import IgemmDesc, WgradDesc, Seg, ptr, stream, check
+
+bf16 = torch.bfloat16
+
+
+def _f32c(t):
+    assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), "expected contiguous fp32 CUDA tensor"
+    return t
+
+
+def _bf16c(t):
+    assert t.is_cuda and t.dtype == bf16 and t.is_contiguous(), "expected contiguous bf16 CUDA tensor"
+    return t
+
+
+# ------------------------------------------------------------------ diffusion elementwise
+def q_sample(x0, noise, t, sqrt_ac, sqrt_1mac, out=None):
+    """ref gaussian_diffusion.py:201-222"""
+    _f32c(x0); _f32c(noise); _f32c(sqrt_ac); _f32c(sqrt_1mac)
+    assert t.dtype == torch.int64 and t.is_cuda and x0.shape == noise.shape
+    out = torch.empty_like(x0) if out is None else out
+    B = x0.shape[0]
+    if x0.numel() == 0:
+        return out
+    check(_lib.lib().cdae_q_sample(ptr(x0), ptr(noise), ptr(t), ptr(sqrt_ac), ptr(sqrt_1mac), ptr(out), B,
+                                   x0.numel() // max(B, 1), stream()))
+    return out
+
+
+def mse_loss(pred, target, gscale=None, want_grad=False):
+    """per-sample mean((target-pred)^2) and, optionally, d(sum_b gscale[b]*mse[b])/dpred (ref gaussian_diffusion.py:847)."""
+    _f32c(pred); _f32c(target)
+    B = pred.shape[0]
+    mse = torch.empty(B, device=pred.device, dtype=torch.float32)
+    dpred = torch.empty_like(pred) if want_grad else None
+    if want_grad:
+        _f32c(gscale)
+    check(_lib.lib().cdae_mse_loss(ptr(pred), ptr(target), ptr(mse), ptr(gscale), ptr(dpred), B,
+                                   pred.numel() // max(B, 1), stream()))
+    return mse, dpred
+
+
+def ddim_step(x, eps_c, coef_table, t_idx, eps_u=None, w=None, noise=None, want_xstart=False, out=None):
+    """ref gaussian_diffusion.py:277-285, 320-341, 506-558 (coef_table rows built by SpacedDiffusion.ddim_coef_table)."""
+    _f32c(x); _f32c(eps_c); _f32c(coef_table)
+    assert t_idx.dtype == torch.int32 and t_idx.is_cuda
+    B = x.shape[0]
+    stride = 0 if t_idx.numel() == 1 else 1
+    assert stride == 0 or t_idx.numel() == B
+    out = torch.empty_like(x) if out is None else out
+    x0 = torch.empty_like(x) if want_xstart else None
+    check(_lib.lib().cdae_ddim_step(ptr(x), ptr(eps_c), ptr(eps_u), float(w if w is not None else 0.0),
+                                    int(w is not None), ptr(coef_table), ptr(t_idx), stride, ptr(noise), ptr(out),
+                                    ptr(x0), B, x.numel() // max(B, 1), stream()))
+    return out, x0
+
+
+def adam_ema(p, g, m, v, ema, hyper, gsq_out=None):
+    """ref train_util.py:292-303 + nn.py:503-513; flat fp32 arenas, hyper = device fp32[9]."""
+    n = p.numel()
+    check(_lib.lib().cdae_adam_ema(ptr(p), ptr(g), ptr(m), ptr(v), ptr(ema), ptr(hyper), ptr(gsq_out), n, stream()))
+
+
+def ema_update(ema, p, rate):
+    check(_lib.lib().cdae_ema_update(ptr(ema), ptr(p), float(rate), p.numel(), stream()))
+
+
+def zero_(t):
+    check(_lib.lib().cdae_zero(ptr(t), t.numel() * t.element_size(), stream()))
+    return t
+
+
+# ------------------------------------------------------------------ layout
+def nchw_to_nhwc_pad(x, cpad=64, out=None):
+    _f32c(x)
+    N, Cc, H, W = x.shape
+    out = torch.empty(N, H, W, cpad, device=x.device, dtype=bf16) if out is None else out
+    check(_lib.lib().cdae_nchw_to_nhwc_pad(ptr(x), ptr(out), N, Cc, H, W, cpad, stream()))
+    return out
+
+
+def nhwc_to_nchw(x, c):
+    _bf16c(x)
+    N, H, W, ld = x.shape
+    out = torch.empty(N, c, H, W, device=x.device, dtype=torch.float32)
+    check(_lib.lib().cdae_nhwc_to_nchw(ptr(x), ptr(out), N, c, H, W, ld, stream()))
+    return out
+
+
+def upsample2x(x, out=None):
+    _bf16c(x)
+    N, H, W, Cc = x.shape
+    out = torch.empty(N, 2 * H, 2 * W, Cc, device=x.device, dtype=bf16) if out is None else out
+    check(_lib.lib().cdae_upsample2x(ptr(x), ptr(out), N, H, W, Cc, stream()))
+    return out
+
+
+def sumpool2x(dy, out=None, accumulate=False):
+    _bf16c(dy)
+    N, H2, W2, Cc = dy.shape
+    out = torch.empty(N, H2 // 2, W2 // 2, Cc, device=dy.device, dtype=bf16) if out is None else out
+    check(_lib.lib().cdae_sumpool2x(ptr(dy), ptr(out), N, H2 // 2, W2 // 2, Cc, int(accumulate), stream()))
+    return out
+
+
+def zero_insert2x(x, out=None):
+    _bf16c(x)
+    N, H, W, Cc = x.shape
+    out = torch.empty(N, 2 * H, 2 * W, Cc, device=x.device, dtype=bf16) if out is None else out
+    check(_lib.lib().cdae_zero_insert2x(ptr(x), ptr(out), N, H, W, Cc, stream()))
+    return out
+
+
+def colsum_(x2d, out, c=None):
+    """out[c] += sum_rows x2d[:, c]  (bias gradients)."""
+    _bf16c(x2d)
+    rows, ld = x2d.reshape(-1, x2d.shape[-1]).shape
+    check(_lib.lib().cdae_colsum(ptr(x2d), ptr(out), rows, c if c is not None else ld, ld, stream()))
+    return out
+
+
+# ------------------------------------------------------------------ GroupNorm32 (+FiLM)(+SiLU)
+def gn_fwd(x0, gamma, beta, x1=None, film=None, film_off=0, silu=True, out=None, mean=None, rstd=None):
+    """ref nn.py:430-437 / unet.py:185-198.  x0 [B,H,W,C0] (+ x1 [B,H,W,C1] concatenated on channels)."""
+    _bf16c(x0)
+    B = x0.shape[0]
+    C0 = x0.shape[-1]
+    HW = x0.numel() // (B * C0)
+    C1 = 0
+    if x1 is not None:
+        _bf16c(x1); C1 = x1.shape[-1]
+    Ct = C0 + C1
+    out = torch.empty(*x0.shape[:-1], Ct, device=x0.device, dtype=bf16) if out is None else out
+    mean = torch.empty(B, 32, device=x0.device, dtype=torch.float32) if mean is None else mean
+    rstd = torch.empty(B, 32, device=x0.device, dtype=torch.float32) if rstd is None else rstd
+    check(_lib.lib().cdae_gn_fwd(ptr(x0), C0, ptr(x1), C1, B, HW, ptr(gamma), ptr(beta), ptr(film),
+                                 film.shape[1] if film is not None else 0, film_off, int(silu), ptr(out), ptr(mean),
+                                 ptr(rstd), stream()))
+    return out, mean, rstd
+
+
+def gn_bwd(dy, x0, gamma, beta, mean, rstd, x1=None, film=None, film_off=0, silu=True, dx0=None, dx1=None,
+           accumulate_dx=0, dgamma=None, dbeta=None, dfilm=None, dadd=None):
+    """accumulate_dx: bit0 -> add into dx0, bit1 -> add into dx1 (True == both); dadd: extra bf16 [B,HW,C] gradient."""
+    if accumulate_dx is True:
+        accumulate_dx = 3
+    _bf16c(dy); _bf16c(x0)
+    B = x0.shape[0]
+    C0 = x0.shape[-1]
+    HW = x0.numel() // (B * C0)
+    C1 = 0
+    if x1 is not None:
+        _bf16c(x1); C1 = x1.shape[-1]
+        dx1 = torch.empty_like(x1) if dx1 is None else dx1
+    dx0 = torch.empty_like(x0) if dx0 is None else dx0
+    check(_lib.lib().cdae_gn_bwd(ptr(dy), ptr(x0), C0, ptr(x1), C1, B, HW, ptr(gamma), ptr(beta), ptr(film),
+                                 film.shape[1] if film is not None else 0, film_off, int(silu), ptr(mean), ptr(rstd),
+                                 ptr(dadd), ptr(dx0), ptr(dx1), int(accumulate_dx), ptr(dgamma), ptr(dbeta), ptr(dfilm), stream()))
+    return dx0, dx1
+
+
+# ------------------------------------------------------------------ implicit GEMM (tcgen05)
+def conv_segments(chans, ksize=3, transposed=False, wk0=0, src0=0):
+    """K segments of a ksize x ksize conv whose input is the channel concat of sources with `chans` channels.
+    Weight K index = tap * sum(chans) + channel (OHWI packing).  transposed=True gives the data-gradient taps."""
+    ctot = sum(chans)
+    segs = []
+    taps = [(kh, kw) for kh in range(ksize) for kw in range(ksize)]
+    for ti, (kh, kw) in enumerate(taps):
+        dh, dw = (kh - ksize // 2, kw - ksize // 2)
+        if transposed:
+            dh, dw = -dh, -dw
+        off = 0
+        for si, c in enumerate(chans):
+            assert c % 64 == 0, "source channels must be multiples of 64"
+            segs.append((src0 + si, dh, dw, 0, c // 64, wk0 + ti * ctot + off))
+            off += c
+    return segs, wk0 + len(taps) * ctot
+
+
+def make_igemm_desc(srcs, segs, wgt, out, cout, in_stride=1, bias=None, resid=None, out_mode=0, sps=1, ooh=0, oow=0,
+                    bn=0, out_hw=None, bias2=None):
+    """Fill a cdae_igemm_desc.  srcs: bf16 [N,H,W,C]; wgt: bf16 [rows, K]; out: bf16 NHWC or fp32 NCHW (out_mode 1)."""
+    d = IgemmDesc()
+    N, H, W = srcs[0].shape[:3]
+    for i, s in enumerate(srcs):
+        _bf16c(s)
+        assert tuple(s.shape[:3]) == (N, H, W)
+        d.src[i] = s.data_ptr()
+        d.src_c[i] = s.shape[3]
+    d.nsrc, d.N, d.H, d.W, d.in_stride = len(srcs), N, H, W, in_stride
+    assert len(segs) <= _lib.MAX_SEG
+    d.nseg = len(segs)
+    for i, sg in enumerate(segs):
+        d.seg[i] = Seg(*sg)
+    _bf16c(wgt)
+    d.wgt, d.wrows, d.wk = wgt.data_ptr(), wgt.shape[0], wgt.shape[1]
+    d.out, d.out_mode = out.data_ptr(), out_mode
+    if out_mode == 0:
+        OH, OW = (out.shape[1], out.shape[2]) if out_hw is None else out_hw
+        d.ldo = out.shape[-1]
+    else:
+        OH, OW = out.shape[2], out.shape[3]
+        d.ldo = 0
+    d.OH, d.OW, d.cout = OH, OW, cout
+    d.sps, d.ooh, d.oow = sps, ooh, oow
+    d.bias = ptr(bias)
+    d.bias2 = ptr(bias2)
+    d.resid = ptr(resid)
+    d.ldr = resid.shape[-1] if resid is not None else 0
+    d.bn = bn
+    d._keep = (srcs, wgt, out, bias, bias2, resid)   # keep tensors alive as long as the descriptor
+    return d
+
+
+def igemm(desc):
+    check(_lib.lib().cdae_igemm(C.byref(desc), stream()))
+
+
+def make_wgrad_desc(dy, src, dw, cout, cin, ksize=3, in_stride=1, c0=0, ci_off=0, cin_real=None, dw_ld=None, splits=0):
+    """dw (fp32 [cout, taps, dw_ld]) += dy^T * shifted(src).  dy: bf16 [N,OH,OW,ldy]; src: bf16 [N,H,W,C]."""
+    _bf16c(dy); _bf16c(src)
+    d = WgradDesc()
+    d.dy, d.ldy, d.cout = dy.data_ptr(), dy.shape[-1], cout
+    d.src, d.src_c, d.c0, d.cin = src.data_ptr(), src.shape[-1], c0, cin
+    d.N, d.H, d.W = src.shape[0], src.shape[1], src.shape[2]
+    d.OH, d.OW = dy.shape[1], dy.shape[2]
+    d.in_stride, d.ksize = in_stride, ksize
+    d.dw = dw.data_ptr()
+    d.dw_ld = dw_ld if dw_ld is not None else cin
+    d.ci_off, d.cin_real, d.splits = ci_off, (cin_real if cin_real is not None else cin), splits
+    d._keep = (dy, src, dw)
+    return d
+
+
+def wgrad(desc):
+    check(_lib.lib().cdae_wgrad(C.byref(desc), stream()))
+
+
+# ------------------------------------------------------------------ attention
+def attn_fwd(qkv, heads, out=None, lse=None):
+    """ref unet.py:239-253. qkv bf16 [B, T, 3C] with per-head [q|k|v] interleave; returns out bf16 [B,T,C], lse fp32 [B,heads,T]."""
+    _bf16c(qkv)
+    B, T, C3 = qkv.shape
+    Cc = C3 // 3
+    ch = Cc // heads
+    out = torch.empty(B, T, Cc, device=qkv.device, dtype=bf16) if out is None else out
+    lse = torch.empty(B, heads, T, device=qkv.device, dtype=torch.float32) if lse is None else lse
+    check(_lib.lib().cdae_attn_fwd(ptr(qkv), ptr(out), ptr(lse), B, T, heads, ch, stream()))
+    return out, lse
+
+
+def attn_bwd(qkv, out, dout, lse, heads, dqkv=None):
+    _bf16c(qkv); _bf16c(out); _bf16c(dout)
+    B, T, C3 = qkv.shape
+    ch = C3 // 3 // heads
+    dqkv = torch.empty_like(qkv) if dqkv is None else dqkv
+    check(_lib.lib().cdae_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), B, T, heads, ch, stream()))
+    return dqkv

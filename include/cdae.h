@@ -1,0 +1,140 @@
+/*
+ * cdae.h — C ABI of libcdae.so, the sm_100a kernel library behind causaldiffae_b200.
+ *
+ * The reference (Akomand/CausalDiffAE) is pure Python/PyTorch: it has no FFI, its arithmetic is
+ * whatever ATen/cuDNN/cuBLAS does underneath `improved_diffusion/*.py`.  Each entry point below
+ * replaces the ATen call sequence of one reference call site (cited file:line, paths relative to
+ * the reference root).  Conventions:
+ *   - plain pointers and sizes only; every buffer (incl. workspaces) is owned by the caller;
+ *   - asynchronous launch on the given stream; no allocation, no host sync, graph-capturable;
+ *   - returns 0 on success, a negative cdae_status otherwise; cdae_last_error() gives the text;
+ *   - re-entrant / thread-safe (called from Python main and autograd worker threads);
+ *   - sm_100a only: cdae_init() fails on any other device.  There is no CPU path.
+ * Activations inside the UNet torso are NHWC bf16 ("pixels x channels"); fp32 accumulation.
+ */
+#ifndef CDAE_H_
+#define CDAE_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* cdae_stream;   /* cudaStream_t */
+
+enum cdae_status {
+  CDAE_OK = 0, CDAE_ERR_ARG = -1, CDAE_ERR_SHAPE = -2, CDAE_ERR_CUDA = -3, CDAE_ERR_ARCH = -4
+};
+
+int cdae_version(void);
+const char* cdae_last_error(void);
+/* checks the current device is compute capability 10.x, resolves cuTensorMapEncodeTiled, sets func attributes */
+int cdae_init(void);
+
+/* ------------------------------------------------------------------ fused elementwise (HBM bound) */
+/* q_sample: x_t = sqrt_ac[t[b]] * x0 + sqrt_1mac[t[b]] * noise      (gaussian_diffusion.py:201-222)
+ * tables are device fp32 arrays of length T (fp32(round(float64)), cf. _extract_into_tensor :938-951). */
+int cdae_q_sample(const float* x0, const float* noise, const int64_t* t, const float* sqrt_ac,
+                  const float* sqrt_1mac, float* x_t, int64_t B, int64_t per_sample, cdae_stream s);
+/* per-sample MSE of (target - pred) and its gradient scale            (gaussian_diffusion.py:847, train_util.py:266)
+ * mse[b] = mean_chw (target-pred)^2 ; if dpred != NULL: dpred = 2*(pred-target)*gscale[b]/per_sample */
+int cdae_mse_loss(const float* pred, const float* target, float* mse, const float* gscale, float* dpred,
+                  int64_t B, int64_t per_sample, cdae_stream s);
+/* DDIM x_{t-1} update with optional classifier-free guidance combine   (gaussian_diffusion.py:277-285,320-341,506-558)
+ * coef_table: device fp32 [T'][8] rows {sqrt_recip_ac, sqrt_recipm1_ac, sqrt(ac_prev), sqrt(1-ac_prev-sigma^2),
+ * sigma*[t!=0], clip_denoised, predict_xstart, 0}; the row is chosen on the device by t_idx[b*t_idx_stride]
+ * (stride 0: one index for the whole batch, so a captured CUDA graph can be replayed for every step). */
+int cdae_ddim_step(const float* x, const float* eps_c, const float* eps_u, float w, int use_w,
+                   const float* coef_table, const int32_t* t_idx, int t_idx_stride, const float* noise,
+                   float* x_prev, float* pred_xstart, int64_t B, int64_t per_sample, cdae_stream s);
+/* fused AdamW + EMA + grad-norm + bf16 weight copy over the flat parameter arena
+ * (train_util.py:292-303 optimize_normal, nn.py:503-513 update_ema, torch.optim.AdamW defaults)
+ * hyper: device floats {lr, beta1, beta2, eps, weight_decay, bias_corr1, bias_corr2, ema_rate, grad_scale} */
+int cdae_adam_ema(float* p, const float* g, float* m, float* v, float* ema, const float* hyper,
+                  float* gsq_out, int64_t n, cdae_stream s);
+/* extra EMA rates (train_util.py:296-297): ema = rate*ema + (1-rate)*p */
+int cdae_ema_update(float* ema, const float* p, float rate, int64_t n, cdae_stream s);
+int cdae_zero(void* p, int64_t bytes, cdae_stream s);
+
+/* ------------------------------------------------------------------ layout / packing */
+/* NCHW fp32 image -> NHWC bf16 padded to Cpad channels (zeros)          (feeds unet.py:392 stem conv) */
+int cdae_nchw_to_nhwc_pad(const float* x, void* out_bf16, int N, int C, int H, int W, int Cpad, cdae_stream s);
+/* NHWC bf16 [N,H,W,ld] first C channels -> NCHW fp32 (gradient of the above / debugging) */
+int cdae_nhwc_to_nchw(const void* x_bf16, float* out, int N, int C, int H, int W, int ld, cdae_stream s);
+/* table-driven weight pack: fp32 master (OHWI physical) -> bf16 forward [Cout_pad][taps][Cin_pad] and
+ * bf16 transposed [Cin_pad][taps][Cout_pad] copies used by the implicit-GEMM kernels. One launch for all layers. */
+typedef struct {
+  int64_t src_off;      /* element offset into fp32 arena */
+  int64_t dst_fwd_off;  /* element offset into bf16 arena, -1: skip */
+  int64_t dst_tr_off;   /* element offset into bf16 arena, -1: skip */
+  int32_t cout, cin, taps, cout_pad, cin_pad;
+  int32_t fwd_ld, tr_ld;  /* destination row pitch in elements (0: dense = taps*cin_pad / taps*cout_pad) */
+  int32_t _pad;
+} cdae_pack_entry;
+int cdae_pack_weights(const float* arena, void* bf16_arena, const cdae_pack_entry* entries_dev, int n_entries,
+                      int64_t max_elems, cdae_stream s);
+/* nearest x2 upsample NHWC bf16 (unet.py:69-79 F.interpolate) and its adjoint (2x2 sum pool) */
+int cdae_upsample2x(const void* x, void* out, int N, int H, int W, int C, cdae_stream s);
+int cdae_sumpool2x(const void* dy, void* dx, int N, int H, int W, int C, int accumulate, cdae_stream s);
+/* zero-insertion (adjoint gather of a stride-2 conv): out[n,2h,2w,:] = x[n,h,w,:], zeros elsewhere */
+int cdae_zero_insert2x(const void* x, void* out, int N, int H, int W, int C, cdae_stream s);
+/* column sums of a [rows, C] bf16 matrix accumulated into fp32 (bias gradients) */
+int cdae_colsum(const void* x_bf16, float* out, int64_t rows, int C, int ld, cdae_stream s);
+
+/* ------------------------------------------------------------------ GroupNorm32 (+FiLM) (+SiLU)   nn.py:430-437, unet.py:185-198 */
+/* x = concat(x0[C0], x1[C1]) NHWC bf16 per sample (x1 may be NULL). y = act(GN(x)*gamma+beta)*(1+scale)+shift ...
+ * precisely: u = (xhat*gamma+beta)*(1+scale[b,c]) + shift[b,c]; y = silu ? u*sigmoid(u) : u.  stats -> mean/rstd [B,32].
+ * film: fp32 [B, film_ld] with scale at col film_off + c and shift at film_off + C + c (NULL: no FiLM). */
+int cdae_gn_fwd(const void* x0, int C0, const void* x1, int C1, int B, int HW,
+                const float* gamma, const float* beta, const float* film, int film_ld, int film_off,
+                int silu, void* y, float* mean, float* rstd, cdae_stream s);
+/* backward: dx split into dx0/dx1; accumulate_dx bit0/bit1: add to the existing contents of dx0/dx1;
+ * dadd: optional bf16 [B,HW,C] tensor added to dx (identity-skip gradient of a ResBlock, unet.py:198);
+ * dgamma/dbeta (+=, fp32), dfilm (+= into [B, film_ld] at the same columns) */
+int cdae_gn_bwd(const void* dy, const void* x0, int C0, const void* x1, int C1, int B, int HW,
+                const float* gamma, const float* beta, const float* film, int film_ld, int film_off, int silu,
+                const float* mean, const float* rstd, const void* dadd, void* dx0, void* dx1, int accumulate_dx,
+                float* dgamma, float* dbeta, float* dfilm, cdae_stream s);
+
+/* ------------------------------------------------------------------ implicit-GEMM convolution on tcgen05/TMEM/TMA
+ * Replaces aten::convolution (cuDNN) at unet.py:143-171 (ResBlock convs + 1x1 skip), :69-79, :97-105 (up/down),
+ * :216-218 (attention qkv/proj Conv1d), :392, :498 and every nn.Linear that is GEMM shaped.
+ *   out[pixel, co] = sum_seg sum_c src[seg.src][pixel shifted by (dh,dw), seg.c0 + c] * wgt[co, seg.wk + c]
+ * Sources are NHWC bf16 with identical (N,H,W); a K "segment" is one filter tap of one source (64-channel chunks).
+ * The same kernel does forward, data-gradient (transposed weights, negated taps) and plain GEMMs (1 tap).      */
+#define CDAE_MAX_SEG 48
+typedef struct { int32_t src, dh, dw, c0, nchunk, wk; } cdae_seg;
+typedef struct {
+  const void* src[4]; int32_t src_c[4];    /* source tensors and their channel counts (row pitch) */
+  int32_t nsrc, N, H, W;                   /* source spatial dims */
+  int32_t in_stride;                       /* 1, or 2: output pixel p reads input pixel 2p+tap (TMA element stride) */
+  int32_t nseg; cdae_seg seg[CDAE_MAX_SEG];
+  const void* wgt; int32_t wrows, wk;      /* bf16 [wrows][wk] */
+  void* out; int32_t out_mode;             /* 0: NHWC bf16, 1: NCHW fp32 */
+  int32_t OH, OW, ldo, cout;               /* full output dims, row pitch (NHWC), number of real output channels */
+  int32_t sps, ooh, oow;                   /* output pixel = (tile_y*sps + ooh, tile_x*sps + oow) */
+  const float* bias;                       /* fp32 [cout] or NULL */
+  const float* bias2;                      /* second fp32 [cout] bias (fused 1x1 skip conv) or NULL */
+  const void* resid; int32_t ldr;          /* bf16 tensor added in the epilogue (same pixel indexing as out) or NULL */
+  int32_t bn;                              /* N tile: 16, 32, 64, 128 or 256 (0: auto) */
+} cdae_igemm_desc;
+int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s);
+
+/* weight gradient:  dW[co, tap, ci] += sum_pixels dy[pixel, co] * src[pixel*in_stride + tap, c0 + ci]
+ * (aten::convolution_backward wgrad). dy NHWC bf16 [N,OH,OW,ldy]; fp32 accumulation with red.add into dw. */
+typedef struct {
+  const void* dy; int32_t ldy, cout;       /* cout real rows (<= padded rows present in dy pitch) */
+  const void* src; int32_t src_c;          /* source tensor, row pitch */
+  int32_t c0, cin;                         /* channel window of the source that maps to dW columns [ci_off, ci_off+cin) */
+  int32_t N, H, W, OH, OW, in_stride;
+  int32_t ksize;                           /* 1 or 3 */
+  float* dw; int32_t dw_ld;                /* fp32 dW[co][tap][dw_ld] ; columns start at ci_off */
+  int32_t ci_off, cin_real;                /* only ci < cin_real written */
+  int32_t splits;                          /* split-K factor over pixel tiles (0: auto) */
+} cdae_wgrad_desc;
+int cdae_wgrad(const cdae_wgrad_desc* d, cdae_stream s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

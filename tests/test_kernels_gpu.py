@@ -1,0 +1,285 @@
+"""Kernel-level parity: every libcdae entry point (through the C ABI) against plain fp32 torch / the oracle."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+bf16 = torch.bfloat16
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def relerr(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+def pack_ohwi(w):
+    """OIHW fp32 -> bf16 [Cout, taps*Cin] (tap-major, channel-minor)"""
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous().to(bf16)
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous().to(bf16)
+
+
+def nchw(x):
+    return x.float().permute(0, 3, 1, 2).contiguous()
+
+
+# ------------------------------------------------------------------ diffusion elementwise
+def test_q_sample_bit_exact_vs_oracle():
+    from causaldiffae_b200 import ops
+    from oracle import diffusion as od
+    d = od.Diffusion(steps=1000)
+    g = torch.Generator().manual_seed(0)
+    B = 37
+    x0, nz = torch.rand(B, 3, 64, 64, generator=g), torch.randn(B, 3, 64, 64, generator=g)
+    t = torch.randint(0, 1000, (B,), generator=g)
+    ref = d.q_sample(x0, t, nz)
+    ta = torch.from_numpy(d.tables["sqrt_alphas_cumprod"]).float().to(dev())
+    tb = torch.from_numpy(d.tables["sqrt_one_minus_alphas_cumprod"]).float().to(dev())
+    out = ops.q_sample(x0.to(dev()), nz.to(dev()), t.to(dev()), ta, tb)
+    assert torch.equal(out.cpu(), ref)
+    # empty batch is a no-op
+    e = ops.q_sample(x0[:0].to(dev()), nz[:0].to(dev()), t[:0].to(dev()), ta, tb)
+    assert e.shape[0] == 0
+
+
+def test_mse_loss_and_grad():
+    from causaldiffae_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    B = 9
+    pred, tgt = torch.randn(B, 3, 32, 32, generator=g), torch.randn(B, 3, 32, 32, generator=g)
+    w = torch.rand(B, generator=g)
+    p = pred.clone().requires_grad_(True)
+    mse_ref = ((tgt - p) ** 2).mean(dim=(1, 2, 3))
+    (mse_ref * w).sum().backward()
+    mse, dp = ops.mse_loss(pred.to(dev()), tgt.to(dev()), w.to(dev()), want_grad=True)
+    np.testing.assert_allclose(mse.cpu().numpy(), mse_ref.detach().numpy(), rtol=2e-6)
+    np.testing.assert_allclose(dp.cpu().numpy(), p.grad.numpy(), rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("eta,w", [(0.0, None), (0.0, 2.0), (0.7, 1.5)])
+def test_ddim_step_vs_oracle(eta, w):
+    from causaldiffae_b200 import ops
+    from causaldiffae_b200.respace import ddim_coef_table
+    from oracle import diffusion as od
+    d = od.Diffusion(steps=1000, timestep_respacing="ddim50")
+    g = torch.Generator().manual_seed(2)
+    B = 5
+    x, ec, eu, nz = (torch.randn(B, 3, 64, 64, generator=g) for _ in range(4))
+    tab = torch.from_numpy(ddim_coef_table(d.tables, eta=eta, clip_denoised=True)).to(dev())
+    for ti in (49, 17, 0):
+        t = torch.full((B,), ti, dtype=torch.long)
+        ref, x0ref = d.ddim_step(x, t, ec, eu if w is not None else None, w, eta, nz)
+        out, x0 = ops.ddim_step(x.to(dev()), ec.to(dev()), tab, torch.tensor([ti], dtype=torch.int32, device=dev()),
+                                eps_u=eu.to(dev()) if w is not None else None, w=w, noise=nz.to(dev()), want_xstart=True)
+        np.testing.assert_allclose(x0.cpu().numpy(), x0ref.numpy(), rtol=0, atol=0)
+        np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=2e-6, atol=2e-6)
+    # per-sample timestep indices
+    tt = torch.tensor([0, 3, 49, 20, 7])
+    ref, _ = d.ddim_step(x, tt, ec, None, None, eta, nz)
+    out, _ = ops.ddim_step(x.to(dev()), ec.to(dev()), tab, tt.to(torch.int32).to(dev()), noise=nz.to(dev()))
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=2e-6, atol=2e-6)
+
+
+def test_adam_ema_vs_torch_adamw():
+    from causaldiffae_b200 import ops
+    from causaldiffae_b200.train_util import adam_hyper
+    g = torch.Generator().manual_seed(3)
+    n = 4096 * 3 + 4
+    p0 = torch.randn(n, generator=g)
+    pr = p0.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([pr], lr=1e-3, weight_decay=0.01)
+    ema_ref = p0.clone()
+    p, m, v, ema = p0.clone().to(dev()), torch.zeros(n, device=dev()), torch.zeros(n, device=dev()), p0.clone().to(dev())
+    gsq = torch.zeros(1, device=dev())
+    for step in range(1, 6):
+        grad = torch.randn(n, generator=g)
+        pr.grad = grad.clone()
+        opt.step()
+        ema_ref.mul_(0.99).add_(pr.detach(), alpha=0.01)
+        hyper = torch.tensor(adam_hyper(1e-3, step, weight_decay=0.01, ema_rate=0.99), device=dev())
+        gsq.zero_()
+        ops.adam_ema(p, grad.to(dev()), m, v, ema, hyper, gsq)
+        np.testing.assert_allclose(float(gsq), float((grad ** 2).sum()), rtol=1e-5)
+    np.testing.assert_allclose(p.cpu().numpy(), pr.detach().numpy(), rtol=2e-5, atol=2e-7)
+    np.testing.assert_allclose(ema.cpu().numpy(), ema_ref.numpy(), rtol=2e-5, atol=2e-7)
+
+
+# ------------------------------------------------------------------ layout kernels
+def test_layout_kernels():
+    from causaldiffae_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(3, 3, 16, 16, generator=g).to(dev())
+    y = ops.nchw_to_nhwc_pad(x, 64)
+    assert y.shape == (3, 16, 16, 64)
+    assert torch.equal(y[..., :3].float(), x.permute(0, 2, 3, 1).to(bf16).float()) and float(y[..., 3:].abs().max()) == 0
+    assert torch.equal(ops.nhwc_to_nchw(y, 3), x.to(bf16).float())
+    a = torch.randn(2, 8, 8, 64, generator=g).to(dev()).to(bf16)
+    up = ops.upsample2x(a)
+    assert torch.equal(nchw(up), F.interpolate(nchw(a), scale_factor=2, mode="nearest"))
+    sp = ops.sumpool2x(up)
+    assert relerr(sp, 4 * a.float()) < 1e-2
+    zi = ops.zero_insert2x(a)
+    assert torch.equal(zi[:, ::2, ::2], a) and float(zi[:, 1::2].abs().max()) == 0 and float(zi[:, :, 1::2].abs().max()) == 0
+    cs = torch.zeros(64, device=dev())
+    ops.colsum_(a, cs)
+    np.testing.assert_allclose(cs.cpu().numpy(), a.float().sum(dim=(0, 1, 2)).cpu().numpy(), rtol=1e-4, atol=1e-3)
+
+
+# ------------------------------------------------------------------ GroupNorm
+@pytest.mark.parametrize("C0,C1,HW,film,silu", [(128, 0, 64 * 64, True, True), (64, 0, 16 * 16, False, True),
+                                                (512, 384, 8 * 8, False, True), (256, 128, 32 * 32, True, True),
+                                                (384, 0, 16 * 16, False, False), (64, 64, 4 * 4, True, True)])
+def test_groupnorm_fwd_bwd(C0, C1, HW, film, silu):
+    from causaldiffae_b200 import ops
+    g = torch.Generator().manual_seed(C0 + C1 + HW)
+    B, Ct = 3, C0 + C1
+    S = int(HW ** 0.5)
+    x = (torch.randn(B, Ct, S, S, generator=g) * 1.5 + 0.3).to(dev()).to(bf16).float()
+    gamma = (1 + 0.2 * torch.randn(Ct, generator=g)).to(dev())
+    beta = (0.2 * torch.randn(Ct, generator=g)).to(dev())
+    film_t = (0.3 * torch.randn(B, 2 * Ct + 32, generator=g)).to(dev()) if film else None
+    foff = 16
+    dy = torch.randn(B, Ct, S, S, generator=g).to(dev()).to(bf16).float()
+    xr, gr, br = x.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    fr = film_t.clone().requires_grad_(True) if film else None
+    u = F.group_norm(xr, 32, gr, br, eps=1e-5)
+    if film:
+        u = u * (1 + fr[:, foff:foff + Ct, None, None]) + fr[:, foff + Ct:foff + 2 * Ct, None, None]
+    yref = u * torch.sigmoid(u) if silu else u
+    yref.backward(dy)
+    x_nhwc = nhwc(x)
+    x0 = x_nhwc[..., :C0].contiguous()
+    x1 = x_nhwc[..., C0:].contiguous() if C1 else None
+    y, mean, rstd = ops.gn_fwd(x0, gamma, beta, x1=x1, film=film_t, film_off=foff, silu=silu)
+    assert relerr(nchw(y), yref) < 6e-3
+    dgamma, dbeta = torch.zeros(Ct, device=dev()), torch.zeros(Ct, device=dev())
+    dfilm = torch.zeros_like(film_t) if film else None
+    dx0, dx1 = ops.gn_bwd(nhwc(dy), x0, gamma, beta, mean, rstd, x1=x1, film=film_t, film_off=foff, silu=silu,
+                          dgamma=dgamma, dbeta=dbeta, dfilm=dfilm)
+    dx = torch.cat([dx0, dx1], dim=-1) if C1 else dx0
+    assert relerr(nchw(dx), xr.grad) < 8e-3
+    assert relerr(dgamma, gr.grad) < 3e-3 and relerr(dbeta, br.grad) < 3e-3
+    if film:
+        assert relerr(dfilm, fr.grad) < 3e-3
+    # accumulate mode adds to what is already in dx
+    base = torch.randn_like(dx0.float()).to(bf16)
+    acc0 = base.clone()
+    acc1 = torch.zeros_like(dx1) if C1 else None
+    ops.gn_bwd(nhwc(dy), x0, gamma, beta, mean, rstd, x1=x1, film=film_t, film_off=foff, silu=silu, dx0=acc0, dx1=acc1,
+               accumulate_dx=True)
+    assert relerr(acc0.float(), base.float() + dx0.float()) < 1e-2
+
+
+# ------------------------------------------------------------------ implicit GEMM (tcgen05)
+def _conv_case(N, H, chans, cout, ksize=3, stride=1, bias=True, resid=False, seed=0, bn=0):
+    from causaldiffae_b200 import ops
+    g = torch.Generator().manual_seed(seed)
+    cin = sum(chans)
+    x = torch.randn(N, cin, H, H, generator=g).to(dev()).to(bf16).float()
+    w = (torch.randn(cout, cin, ksize, ksize, generator=g) * (cin * ksize * ksize) ** -0.5).to(dev()).to(bf16).float()
+    b = torch.randn(cout, generator=g).to(dev()) if bias else None
+    ref = F.conv2d(x, w, b, stride=stride, padding=ksize // 2)
+    OH = ref.shape[2]
+    r = torch.randn(N, cout, OH, OH, generator=g).to(dev()).to(bf16).float() if resid else None
+    if resid:
+        ref = ref + r
+    xs, off = [], 0
+    xn = nhwc(x)
+    for c in chans:
+        xs.append(xn[..., off:off + c].contiguous()); off += c
+    segs, K = ops.conv_segments(chans, ksize)
+    out = torch.full((N, OH, OH, cout), float("nan"), device=dev(), dtype=bf16)
+    d = ops.make_igemm_desc(xs, segs, pack_ohwi(w), out, cout, in_stride=stride, bias=b,
+                            resid=nhwc(r) if resid else None, bn=bn)
+    ops.igemm(d)
+    torch.cuda.synchronize()
+    return relerr(nchw(out), ref)
+
+
+@pytest.mark.parametrize("N,H,chans,cout,ksize,stride,resid", [
+    (2, 64, [64], 128, 3, 1, False),          # BW=64,BH=2
+    (2, 32, [128], 128, 3, 1, True),          # residual epilogue
+    (3, 16, [128, 64], 128, 3, 1, False),     # concat (split-K over two tensors)
+    (5, 8, [256], 256, 3, 1, False),          # 8x8: two images per 128-pixel tile, ragged batch (5)
+    (9, 4, [128], 128, 3, 1, False),          # 4x4: eight images per tile, ragged
+    (2, 32, [128], 128, 3, 2, False),         # stride-2 (Downsample) via TMA element strides
+    (2, 16, [192], 64, 1, 1, True),           # 1x1 skip conv, cout 64
+    (1, 64, [64], 64, 3, 1, False),
+])
+def test_igemm_conv_forward(N, H, chans, cout, ksize, stride, resid):
+    err = _conv_case(N, H, chans, cout, ksize, stride, True, resid, seed=H + cout)
+    assert err < 5e-3, err
+
+
+@pytest.mark.parametrize("bn", [64, 128, 256])
+def test_igemm_tile_widths(bn):
+    assert _conv_case(2, 16, [128], 256, 3, 1, True, False, seed=bn, bn=bn) < 5e-3
+
+
+def test_igemm_plain_gemm_and_small_cout():
+    from causaldiffae_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    rows, K, Nn = 1000, 512, 384
+    a = torch.randn(rows, K, generator=g).to(dev()).to(bf16)
+    w = (torch.randn(Nn, K, generator=g) * K ** -0.5).to(dev()).to(bf16)
+    bias = torch.randn(Nn, generator=g).to(dev())
+    out = torch.empty(1, 1, rows, Nn, device=dev(), dtype=bf16)
+    d = ops.make_igemm_desc([a.view(1, 1, rows, K)], [(0, 0, 0, 0, K // 64, 0)], w, out, Nn, bias=bias)
+    ops.igemm(d)
+    assert relerr(out.view(rows, Nn), a.float() @ w.float().t() + bias) < 5e-3
+    # final eps conv: 128 -> 3 channels, NCHW fp32 output, weight rows padded to 16
+    x = torch.randn(2, 128, 32, 32, generator=g).to(dev()).to(bf16).float()
+    w3 = (torch.randn(3, 128, 3, 3, generator=g) * 0.03).to(dev()).to(bf16).float()
+    b3 = torch.randn(3, generator=g).to(dev())
+    wp = torch.zeros(16, 9 * 128, device=dev(), dtype=bf16)
+    wp[:3] = pack_ohwi(w3)
+    out3 = torch.empty(2, 3, 32, 32, device=dev())
+    segs, _ = ops.conv_segments([128], 3)
+    ops.igemm(ops.make_igemm_desc([nhwc(x)], segs, wp, out3, 3, bias=b3, out_mode=1))
+    assert relerr(out3, F.conv2d(x, w3, b3, padding=1)) < 5e-3
+
+
+def test_igemm_dgrad_matches_autograd():
+    from causaldiffae_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    N, H, cin, cout = 2, 16, 128, 192
+    x = torch.randn(N, cin, H, H, generator=g).to(dev()).requires_grad_(True)
+    w = (torch.randn(cout, cin, 3, 3, generator=g) * 0.03).to(dev()).to(bf16).float()
+    dy = torch.randn(N, cout, H, H, generator=g).to(dev()).to(bf16).float()
+    F.conv2d(x, w, padding=1).backward(dy)
+    wt = w.permute(1, 2, 3, 0).reshape(cin, 9 * cout).contiguous().to(bf16)     # [Cin][tap][Cout]
+    segs, _ = ops.conv_segments([cout], 3, transposed=True)
+    dx = torch.empty(N, H, H, cin, device=dev(), dtype=bf16)
+    ops.igemm(ops.make_igemm_desc([nhwc(dy)], segs, wt, dx, cin))
+    assert relerr(nchw(dx), x.grad) < 5e-3
+
+
+@pytest.mark.parametrize("N,H,cin,cout,ksize,stride", [(2, 32, 128, 128, 3, 1), (4, 8, 256, 128, 3, 1), (2, 16, 64, 64, 3, 1),
+                                                       (3, 16, 192, 256, 1, 1), (2, 32, 128, 128, 3, 2), (8, 4, 128, 128, 3, 1),
+                                                       (2, 64, 64, 128, 3, 1)])
+def test_wgrad_matches_autograd(N, H, cin, cout, ksize, stride):
+    from causaldiffae_b200 import ops
+    g = torch.Generator().manual_seed(H + cin)
+    x = torch.randn(N, cin, H, H, generator=g).to(dev()).to(bf16).float()
+    w = torch.zeros(cout, cin, ksize, ksize, device=dev(), requires_grad=True)
+    y = F.conv2d(x, w, stride=stride, padding=ksize // 2)
+    dy = torch.randn(y.shape, generator=g).to(dev()).to(bf16).float()
+    y.backward(dy)
+    dw = torch.zeros(cout, ksize * ksize, cin, device=dev())
+    ops.wgrad(ops.make_wgrad_desc(nhwc(dy), nhwc(x), dw, cout, cin, ksize=ksize, in_stride=stride))
+    ref = w.grad.permute(0, 2, 3, 1).reshape(cout, ksize * ksize, cin)
+    assert relerr(dw, ref) < 5e-3
+    # accumulation semantics (+=) and a channel window of a wider source (concat operand)
+    if cin >= 128 and ksize == 3 and stride == 1:
+        dw2 = torch.ones(cout, 9, cin, device=dev())
+        ops.wgrad(ops.make_wgrad_desc(nhwc(dy), nhwc(x), dw2, cout, 64, ksize=3, c0=64, ci_off=64, dw_ld=cin))
+        assert relerr(dw2[:, :, 64:128] - 1, ref[:, :, 64:128]) < 5e-3
+        assert float((dw2[:, :, :64] - 1).abs().max()) == 0
