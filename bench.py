@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py — CausalDiffAE denoising hot path on B200 (contract: see the task statement / DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path (libcdae via the C ABI)
+    python bench.py --impl reference [--steps K] [--warmup W]      # the reference algorithm on the host CPU cores
+
+Workload (BASELINE.json configs[1]): Pendulum-shaped synthetic 3x64x64, 4-variable causal DAG, CausalDiffAE training
+(num_channels 128, 2 res blocks, attention at 16x16 / 8x8, rep_cond + causal_modeling), per-GPU batch 64, bf16 tensor-core
+compute with fp32 master weights; one "step" = TrainLoop.run_step (forward + backward + fused AdamW/EMA) on one batch.
+N > 1: one process per GPU under torchrun, NCCL gradient all-reduce, weak scaling (per-GPU batch fixed).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+PENDULUM = [[0, 0, 1, 1], [0, 0, 1, 1], [0, 0, 0, 0], [0, 0, 0, 0]]
+FLAGS = dict(image_size=64, num_channels=128, num_res_blocks=2, num_heads=4, attention_resolutions="16,8",
+             class_cond=False, rep_cond=True, n_vars=4, causal_modeling=True, in_channels=3, learn_sigma=False,
+             rescale_timesteps=False, rescale_learned_sigmas=False, diffusion_steps=1000, noise_schedule="linear")
+FWD_GFLOP_PER_IMG = 60.62          # SURVEY.md 8d (2*MAC, forward, cfg2/3); train = 3x forward
+WORKLOAD = "pendulum64-train: 3x64x64, 4-var DAG, nc128 x2 res blocks, attn@16,8, per-GPU batch %d"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sus=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+def synth_batch(B, seed, device=None, pinned=False):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(B, 3, 64, 64, generator=g)
+    c = torch.rand(B, 4, generator=g)
+    if pinned:
+        x, c = x.pin_memory(), c.pin_memory()
+    if device is not None:
+        x, c = x.to(device), c.to(device)
+    return x, {"c": c}
+
+
+# ---------------------------------------------------------------------------------------------- reference arm (CPU)
+def run_reference(args):
+    """The reference algorithm (oracle/ = restatement pinned against the real reference) on the host cores, same
+    config/metric; each step is a bounded sample of the workload (small batch) so the run ends within minutes."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import model as om, diffusion as od, schedules
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    Bs = args.ref_batch
+    cfg = om.config_from_flags(**FLAGS, A=PENDULUM)
+    sd = om.seeded_state_dict(cfg, seed=0)
+    diff = od.Diffusion(steps=1000)
+    tr = od.RefTrainer(sd, cfg, diff, lr=1e-4, ema_rate=0.9999)
+    x, cond = synth_batch(Bs, 0)
+    np.random.seed(0); torch.manual_seed(0)
+
+    def step():
+        t, w = schedules.uniform_sample_t(1000, Bs)
+        tr.run_step(x, torch.from_numpy(t), torch.randn_like(x), torch.from_numpy(w), c=cond["c"])
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = Bs * args.steps / dt
+    sample = f"{args.steps} optimisation steps at batch {Bs} (of the per-GPU batch {args.batch}), fp32, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "train_img_per_s", "value": val, "unit": "img/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD % args.batch, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def cpu_baseline_sample(batch):
+    """oracle timed on the host cores for ~10-30 s (rank 0, N=1 only)"""
+    from oracle import model as om, diffusion as od, schedules
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    Bs, n = 4, 3
+    cfg = om.config_from_flags(**FLAGS, A=PENDULUM)
+    sd = om.seeded_state_dict(cfg, seed=0)
+    diff = od.Diffusion(steps=1000)
+    tr = od.RefTrainer(sd, cfg, diff, lr=1e-4)
+    x, cond = synth_batch(Bs, 0)
+    np.random.seed(0); torch.manual_seed(0)
+
+    def step():
+        t, w = schedules.uniform_sample_t(1000, Bs)
+        tr.run_step(x, torch.from_numpy(t), torch.randn_like(x), torch.from_numpy(w), c=cond["c"])
+
+    step()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        step()
+    dt = time.perf_counter() - t0
+    return {"value": Bs * n / dt, "unit": "img/s", "cores": cores, "kind": "port",
+            "sample": f"{n} oracle optimisation steps at batch {Bs} (workload batch {batch}), fp32 torch CPU"}
+
+
+# ---------------------------------------------------------------------------------------------- dominant-kernel roofline
+def conv_roofline(peaks, B):
+    """Live CUDA-event timing of the dominant kernel class: the 3x3 implicit-GEMM conv (tcgen05), at the layer shape
+    that carries the most FLOPs in cfg2 (res.out 128->128 @ 64x64 and 256->256 @ 32x32, 10 % each).
+    Inputs are rotated over buffers totalling more than L2 (126 MB) so that every launch streams from HBM."""
+    from causaldiffae_b200 import ops
+    dev = torch.device("cuda")
+    out = {}
+    for name, (C, S) in {"conv3x3_128c_64px": (128, 64), "conv3x3_256c_32px": (256, 32)}.items():
+        nbuf = max(2, int(200e6 // (B * S * S * C * 2)) + 1)
+        xs = [torch.randn(B, S, S, C, device=dev).to(torch.bfloat16) for _ in range(nbuf)]
+        ys = [torch.empty(B, S, S, C, device=dev, dtype=torch.bfloat16) for _ in range(nbuf)]
+        w = (torch.randn(C, 9 * C, device=dev) * 0.02).to(torch.bfloat16)
+        bias = torch.zeros(C, device=dev)
+        segs, _ = ops.conv_segments([C], 3)
+        descs = [ops.make_igemm_desc([x], segs, w, y, C, bias=bias) for x, y in zip(xs, ys)]
+        for d in descs:
+            ops.igemm(d)
+        torch.cuda.synchronize()
+        reps = 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            for d in descs:
+                ops.igemm(d)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / (reps * nbuf)
+        flops = 2.0 * B * S * S * C * 9 * C
+        out[name] = dict(ms=ms, tflops=flops / ms / 1e9, flops=flops)
+    top = out["conv3x3_128c_64px"]
+    return {"bound": "tensor", "kernel": "igemm_kernel<128,3> (3x3 conv 128->128 @64x64, batch %d)" % B,
+            "achieved": top["tflops"], "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": top["tflops"] / peaks["tf_burst"],
+            "traffic": None, "peak_source": peaks["src"] + " bf16 burst", "flops_per_launch": top["flops"],
+            "other_shapes": {k: round(v["tflops"], 1) for k, v in out.items()}}
+
+
+# ---------------------------------------------------------------------------------------------- CUDA arm
+def run_cuda(args):
+    import torch.distributed as dist
+    from causaldiffae_b200 import script_util as su, dist_util, logger, engine as eng_mod
+    from causaldiffae_b200.train_util import TrainLoop
+    import causaldiffae_b200.nn as cnn
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist_util.setup_dist()
+    logger.configure(dir=os.path.join("/tmp", f"cdae_bench_{os.getpid()}"), format_strs=[])
+    cnn.RNG_MODE = "device"        # throughput runs draw xi / masks on the device generator (no per-step H2D)
+    peaks = load_peaks()
+    B = args.batch
+    torch.manual_seed(0)
+    model, diff = su.create_model_and_diffusion(**{**su.model_and_diffusion_defaults(), **FLAGS}, A=PENDULUM)
+    # de-zero the zero_module tensors (reference init makes eps == 0) so that the timed math is generic
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if float(p.abs().sum()) == 0.0 and p.dim() > 1:
+                fan_in = p[0].numel()
+                p.copy_(torch.randn(p.shape, generator=g) * fan_in ** -0.5)
+    model.to(dev)
+    loop = TrainLoop(model=model, diffusion=diff, data=None, batch_size=B, microbatch=-1, lr=1e-4, ema_rate="0.9999",
+                     log_interval=10 ** 9, save_interval=10 ** 9, resume_checkpoint="", rep_cond=True, n_vars=4,
+                     causal_modeling=True, in_channels=3)
+    loop.log_quartiles = False
+    np.random.seed(1234 + rank)
+    dev_batches = [synth_batch(B, 100 + rank * 10 + i, device=dev) for i in range(2)]
+    host_batches = [synth_batch(B, 200 + rank * 10 + i, pinned=True) for i in range(3)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    def step_dev(i):
+        x, cond = dev_batches[i % len(dev_batches)]
+        loop.run_step(x, dict(cond))
+
+    last = {}
+
+    def step_host(i):
+        x, cond = host_batches[i % len(host_batches)]
+        loop.run_step(x, dict(cond))
+        last["loss"] = float(loop.last_loss)       # D2H read of the step's result
+
+    for i in range(max(args.warmup, 3)):
+        step_dev(i)
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms_step = timed(step_dev, args.steps)
+    clk = clocks.stop()
+    for i in range(3):
+        step_host(i)
+    ms_e2e = timed(step_host, args.steps)
+
+    pl = model.engine.plan(B, True)
+    launches_per_step = pl.n_fwd_launch + pl.n_bwd_launch + 6     # + q_sample, mse fwd/bwd, zero, pack, adam
+    value = B * world / (ms_step / 1000)
+    e2e = B * world / (ms_e2e / 1000)
+    train_flops = 3 * FWD_GFLOP_PER_IMG * 1e9 * B
+    res = {
+        "metric": "train_img_per_s", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD % B, "global_batch": B * world, "parallelism": f"dp{world}",
+                   "l2": "per-step working set (activations + 93.5M-param arenas, several GB) exceeds the 126 MB L2; no flush",
+                   "graphs": eng_mod.USE_GRAPHS},
+        "e2e": {"value": e2e, "unit": "img/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(B * (3 * 64 * 64 + 4) * 4 + B * 12), "d2h_bytes_per_step": 4,
+                "loss": last.get("loss")},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "clocks": clk,
+        "step_roofline": {"bound": "tensor", "achieved": train_flops / ms_step / 1e9, "peak": peaks["tf_sus"],
+                          "unit": "TFLOP/s", "frac": train_flops / ms_step / 1e9 / peaks["tf_sus"],
+                          "note": "algorithmic 3 x 60.62 GFLOP/img over the whole step vs " + peaks["src"] + " sustained bf16"},
+    }
+    if rank == 0:
+        try:
+            res["roofline"] = conv_roofline(peaks, B)
+        except Exception as ex:   # never lose the headline number to the auxiliary measurement
+            res["roofline"] = {"error": repr(ex)}
+        if world == 1 and not args.no_cpu:
+            res["cpu_baseline"] = cpu_baseline_sample(B)
+        if not args.no_ddim:
+            try:
+                res["ddim"] = ddim_bench(model, world, dev, args)
+            except Exception as ex:
+                res["ddim"] = {"error": repr(ex)}
+    elif not args.no_ddim:
+        try:
+            ddim_bench(model, world, dev, args)
+        except Exception:
+            pass
+    if rank == 0:
+        print(json.dumps(res))
+    barrier()
+
+
+def ddim_bench(model, world, dev, args):
+    """Secondary workload (BASELINE configs[3]): counterfactual encode -> do() -> DDIM decode, batch of interventions
+    sharded over ranks with no communication until a final gather."""
+    import torch.distributed as dist
+    from causaldiffae_b200 import script_util as su
+    from causaldiffae_b200.sampling import counterfactual
+    steps = args.ddim_steps
+    _, diff = su.create_model_and_diffusion(**{**su.model_and_diffusion_defaults(), **FLAGS,
+                                               "timestep_respacing": f"ddim{steps}"}, A=PENDULUM)
+    Bd = args.ddim_batch
+    g = torch.Generator().manual_seed(7)
+    x = torch.rand(Bd, 3, 64, 64, generator=g).to(dev)
+    model.eval()
+    out = counterfactual(model, diff, x, do_var=0, do_value=0.2)        # warm-up (plan build + graph capture)
+    out = counterfactual(model, diff, x, do_var=0, do_value=0.2)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = counterfactual(model, diff, x, do_var=0, do_value=-0.35)
+    if world > 1:
+        gathered = [torch.empty_like(out) for _ in range(world)]
+        dist.all_gather(gathered, out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    model.train()
+    peaks = load_peaks()
+    tf = steps * FWD_GFLOP_PER_IMG * 1e9 * Bd / float(ms) / 1e9
+    return {"metric": f"ddim{steps}_counterfactual_img_per_s", "value": Bd * world / (float(ms) / 1000), "unit": "img/s",
+            "batch_per_gpu": Bd, "ms": float(ms), "tflops_per_gpu": tf, "frac_of_sustained_peak": tf / peaks["tf_sus"]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="per-GPU batch")
+    ap.add_argument("--ref-batch", type=int, default=4, help="bounded per-step sample of the reference arm")
+    ap.add_argument("--ddim-steps", type=int, default=50)
+    ap.add_argument("--ddim-batch", type=int, default=128)
+    ap.add_argument("--no-ddim", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 6:
+            args.steps = 6          # bounded: the CPU arm runs ~2-4 s per step
+        args.warmup = min(args.warmup, 1)
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -75,7 +75,7 @@ _SIGS = {
     "cdae_attn_bwd": ([P, P, P, P, P, I32, I32, I32, I32, P], C.c_int),
 }
 # entry points that later files add; absent symbols are only an error when called
-_OPTIONAL = {"cdae_attn_fwd", "cdae_attn_bwd"}
+_OPTIONAL = set()
 
 
 class CdaeError(RuntimeError):

@@ -1,0 +1,653 @@
+"""Kernel engine for the UNet torso: a static execution plan of libcdae launches over NHWC bf16 activations.
+
+Design (B200-first, not a translation of the eager reference):
+  * all parameters live in ONE flat fp32 arena (and their gradients in a second one): the optimizer is a single
+    fused kernel over the arena, the DDP all-reduce is one contiguous NCCL call, EMA is a flat copy;
+    conv weights are stored OHWI (channels-last) so that the bf16 operand copies are a cast (+pad) and the
+    tensor-core weight-gradient kernel writes coalesced rows;
+  * the torso (stem -> input/middle/output blocks -> out conv, ref unet.py:622-632) is compiled per batch size into a
+    list of kernel launches with preallocated buffers and prebuilt descriptors; forward and backward are each
+    replayed as one CUDA graph;
+  * concat skip connections are never materialised: GroupNorm and the implicit GEMM read two sources (split-K);
+  * the ResBlock 1x1 skip conv is extra K segments of the second 3x3 implicit GEMM; bias/residual adds are epilogues.
+The per-ResBlock FiLM vectors `emb_layers(SiLU(emb))` (ref unet.py:148-154,186-192) are ONE batched GEMM because the
+22 emb_layers weights are adjacent in the arena.
+"""
+import ctypes as C
+import os
+
+import torch as th
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib, ops
+from ._lib import PackEntry
+
+bf16 = th.bfloat16
+USE_GRAPHS = os.environ.get("CDAE_GRAPHS", "1") != "0"
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+class _ConvW:
+    """bf16 operand copies of one conv/linear weight inside the bf16 arena."""
+
+    def __init__(self, param, bias, cout, cin, taps, cin_pad=None, cout_pad=None):
+        self.param, self.bias = param, bias
+        self.cout, self.cin, self.taps = cout, cin, taps
+        self.cin_pad = cin_pad or _round_up(cin, 64)
+        self.cout_pad = cout_pad or (_round_up(cout, 64) if cout >= 64 else 16)
+        self.fwd = None      # bf16 [cout_pad, K]
+        self.tr = None       # bf16 [cin_pad, taps*cout_tr_pad]
+        self.cout_tr_pad = _round_up(cout, 64)
+
+
+class T:
+    """A planned activation: bf16 NHWC buffer + lazily allocated gradient buffer."""
+
+    def __init__(self, plan, shape, name=""):
+        self.plan, self.shape, self.name = plan, tuple(shape), name
+        self.t = plan.alloc(shape)
+        self.g = None
+        self.g_written = False
+
+    def grad(self):
+        if self.g is None:
+            self.g = self.plan.alloc(self.shape)
+        return self.g
+
+    def grad_acc(self):
+        """False for the first producer of this gradient (write), True for later ones (accumulate)."""
+        acc = self.g_written
+        self.g_written = True
+        return acc
+
+
+class Plan:
+    def __init__(self, engine, B, train):
+        self.e, self.B, self.train = engine, B, train
+        self.dev = engine.device
+        self.fwd, self.bwd = [], []        # lists of zero-arg callables; bwd is executed in reverse build order
+        self.bufs = []
+        self.fwd_graph = self.bwd_graph = None
+        self.runs = 0
+        self.n_fwd_launch = self.n_bwd_launch = 0
+
+    def alloc(self, shape, dtype=bf16):
+        t = th.empty(shape, device=self.dev, dtype=dtype)
+        self.bufs.append(t)
+        return t
+
+    def add_fwd(self, fn, n=1):
+        self.fwd.append(fn); self.n_fwd_launch += n
+
+    def add_bwd(self, fns):
+        """fns: callables of ONE layer in execution order; layers are replayed last-to-first."""
+        self.bwd.append(list(fns)); self.n_bwd_launch += len(fns)
+
+    # ---- execution
+    def _run_fwd_eager(self):
+        for f in self.fwd:
+            f()
+
+    def _run_bwd_eager(self):
+        for layer in reversed(self.bwd):
+            for f in layer:
+                f()
+
+    def forward(self):
+        if USE_GRAPHS and self.runs >= 1:
+            if self.fwd_graph is None:
+                self.fwd_graph = _capture(self._run_fwd_eager)
+            self.fwd_graph.replay()
+        else:
+            self._run_fwd_eager()
+        self.runs += 1
+
+    def backward(self):
+        if USE_GRAPHS and self.runs >= 2:
+            if self.bwd_graph is None:
+                self.bwd_graph = _capture(self._run_bwd_eager)
+            self.bwd_graph.replay()
+        else:
+            self._run_bwd_eager()
+
+
+def _capture(fn):
+    g = th.cuda.CUDAGraph()
+    th.cuda.synchronize()
+    s = th.cuda.Stream()
+    s.wait_stream(th.cuda.current_stream())
+    with th.cuda.stream(s):
+        with th.cuda.graph(g, stream=s):
+            fn()
+    th.cuda.current_stream().wait_stream(s)
+    return g
+
+
+class Engine:
+    def __init__(self, model):
+        self.model = model
+        p0 = next(model.parameters())
+        if not p0.is_cuda:
+            raise _lib.CdaeError("the UNet engine needs the model on a CUDA (sm_100a) device; there is no CPU path")
+        self.device = p0.device
+        _lib.lib()
+        self.plans = {}
+        self._layer_plans = {}
+        self._build_arena()
+        self._build_weight_pack()
+        self._packed_version = None
+        self.dirty = True
+        for mod in model.modules():
+            object.__setattr__(mod, "_cdae_root", model)
+
+    # ------------------------------------------------------------------ flat parameter arena
+    def _torso_conv_params(self):
+        m = self.model
+        out = set()
+        from .unet import ResBlock, AttentionBlock, Upsample, Downsample
+        for mod in list(m.input_blocks.modules()) + list(m.middle_block.modules()) + list(m.output_blocks.modules()):
+            if isinstance(mod, (nn.Conv2d, nn.Conv1d)):
+                out.add(id(mod.weight))
+        out.add(id(m.out[2].weight))
+        return out
+
+    def resblocks(self):
+        from .unet import ResBlock
+        m = self.model
+        return [mod for blk in list(m.input_blocks) + [m.middle_block] + list(m.output_blocks) for mod in blk
+                if isinstance(mod, ResBlock)]
+
+    def _build_arena(self):
+        m = self.model
+        ohwi = self._torso_conv_params()
+        rbs = self.resblocks()
+        order, seen = [], set()
+        for rb in rbs:
+            order.append(rb.emb_layers[1].weight)
+        for rb in rbs:
+            order.append(rb.emb_layers[1].bias)
+        seen = {id(p) for p in order}
+        for p in m.parameters():
+            if id(p) not in seen:
+                order.append(p); seen.add(id(p))
+        offs, off = {}, 0
+        for p in order:
+            offs[id(p)] = off
+            off += _round_up(p.numel(), 4)
+        self.n_params = off
+        self.arena = th.zeros(off, device=self.device, dtype=th.float32)
+        self.grad_arena = th.zeros(off, device=self.device, dtype=th.float32)
+        self.param_offsets = offs
+        self._views = []     # (param, offset, numel, ohwi?) for state export from other arenas (EMA)
+        with th.no_grad():
+            for p in order:
+                o, n = offs[id(p)], p.numel()
+                is_ohwi = id(p) in ohwi and p.dim() == 4
+                flat, gflat = self.arena[o:o + n], self.grad_arena[o:o + n]
+                if is_ohwi:
+                    O, I, H, W = p.shape
+                    flat.view(O, H, W, I).copy_(p.detach().permute(0, 2, 3, 1))
+                    p.data = flat.view(O, H, W, I).permute(0, 3, 1, 2)
+                    p.grad = gflat.view(O, H, W, I).permute(0, 3, 1, 2)
+                else:
+                    flat.view(p.shape).copy_(p.detach())
+                    p.data = flat.view(p.shape)
+                    p.grad = gflat.view(p.shape)
+                self._views.append((p, o, n, is_ohwi))
+        ted = m.model_channels * 4
+        self.film_width = sum(rb.emb_layers[1].weight.shape[0] for rb in rbs)
+        self.film_w = nn.Parameter(self.arena[:self.film_width * ted].view(self.film_width, ted))
+        self.film_w.grad = self.grad_arena[:self.film_width * ted].view(self.film_width, ted)
+        b0 = offs[id(rbs[0].emb_layers[1].bias)]
+        self.film_b = nn.Parameter(self.arena[b0:b0 + self.film_width])
+        self.film_b.grad = self.grad_arena[b0:b0 + self.film_width]
+        self.film_off, o = {}, 0
+        for rb in rbs:
+            self.film_off[id(rb)] = o
+            o += rb.emb_layers[1].weight.shape[0]
+
+    def owns(self, p):
+        a0 = self.arena.data_ptr()
+        return a0 <= p.data_ptr() < a0 + self.arena.numel() * 4
+
+    def grad_of(self, p):
+        o, n = self.param_offsets[id(p)], p.numel()
+        return self.grad_arena[o:o + n]
+
+    def export_state(self, flat):
+        """{name: tensor} views of another flat arena (e.g. EMA) with the model's names/shapes."""
+        by_id = {id(p): (o, n, oh) for p, o, n, oh in self._views}
+        out = {}
+        for name, p in self.model.named_parameters():
+            o, n, oh = by_id[id(p)]
+            if oh:
+                O, I, H, W = p.shape
+                out[name] = flat[o:o + n].view(O, H, W, I).permute(0, 3, 1, 2)
+            else:
+                out[name] = flat[o:o + n].view(p.shape)
+        return out
+
+    # ------------------------------------------------------------------ bf16 operand copies
+    def _build_weight_pack(self):
+        from .unet import ResBlock, AttentionBlock, Upsample, Downsample
+        m = self.model
+        self.convs = {}
+        entries, off = [], 0
+
+        def reg(key, w, b, cout, cin, taps, cin_pad=None, cout_pad=None, fuse_skip=None):
+            nonlocal off
+            cw = _ConvW(w, b, cout, cin, taps, cin_pad, cout_pad)
+            K = taps * cw.cin_pad
+            Ktot = K + (fuse_skip.cin_pad if fuse_skip is not None else 0)
+            cw.K, cw.Ktot = K, Ktot
+            cw.fwd_off, cw.fwd_shape = off, (cw.cout_pad, Ktot)
+            off += _round_up(cw.cout_pad * Ktot, 64)
+            cw.tr_off, cw.tr_shape = off, (cw.cin_pad, taps * cw.cout_tr_pad)
+            off += _round_up(cw.cin_pad * taps * cw.cout_tr_pad, 64)
+            e = PackEntry(self.param_offsets[id(w)], cw.fwd_off, cw.tr_off, cout, cin, taps, cw.cout_pad, cw.cin_pad,
+                          Ktot, 0, 0)
+            entries.append(e)
+            if fuse_skip is not None:
+                # the 1x1 skip weight lives in the trailing columns of the same forward matrix
+                sk = fuse_skip
+                sk.fwd_in = cw
+                entries.append(PackEntry(self.param_offsets[id(sk.param)], cw.fwd_off + K, -1, sk.cout, sk.cin, 1,
+                                         cw.cout_pad, sk.cin_pad, Ktot, 0, 0))
+            self.convs[key] = cw
+            # transposed copy must use cout_tr_pad columns: separate entry when it differs from cout_pad
+            if cw.cout_tr_pad != cw.cout_pad:
+                e.dst_tr_off = -1
+                entries.append(PackEntry(self.param_offsets[id(w)], -1, cw.tr_off, cout, cin, taps, cw.cout_tr_pad,
+                                         cw.cin_pad, 0, 0, 0))
+            return cw
+
+        stem = m.input_blocks[0][0]
+        reg(id(stem), stem.weight, stem.bias, stem.out_channels, stem.in_channels, 9)
+        for blk in list(m.input_blocks)[1:] + [m.middle_block] + list(m.output_blocks):
+            for mod in blk:
+                if isinstance(mod, ResBlock):
+                    c1, c2 = mod.in_layers[2], mod.out_layers[3]
+                    reg(id(c1), c1.weight, c1.bias, c1.out_channels, c1.in_channels, 9)
+                    sk = None
+                    if not isinstance(mod.skip_connection, nn.Identity):
+                        s = mod.skip_connection
+                        sk = _ConvW(s.weight, s.bias, s.out_channels, s.in_channels, 1)
+                        sk.tr_off, sk.tr_shape = off, (sk.cin_pad, sk.cout_tr_pad)
+                        off += _round_up(sk.cin_pad * sk.cout_tr_pad, 64)
+                        entries.append(PackEntry(self.param_offsets[id(s.weight)], -1, sk.tr_off, sk.cout, sk.cin, 1,
+                                                 sk.cout_tr_pad, sk.cin_pad, 0, 0, 0))
+                        self.convs[id(s)] = sk
+                    reg(id(c2), c2.weight, c2.bias, c2.out_channels, c2.in_channels, 9, fuse_skip=sk)
+                elif isinstance(mod, AttentionBlock):
+                    reg(id(mod.qkv), mod.qkv.weight, mod.qkv.bias, mod.qkv.out_channels, mod.qkv.in_channels, 1)
+                    reg(id(mod.proj_out), mod.proj_out.weight, mod.proj_out.bias, mod.proj_out.out_channels,
+                        mod.proj_out.in_channels, 1)
+                elif isinstance(mod, Downsample):
+                    reg(id(mod.op), mod.op.weight, mod.op.bias, mod.op.out_channels, mod.op.in_channels, 9)
+                elif isinstance(mod, Upsample):
+                    reg(id(mod.conv), mod.conv.weight, mod.conv.bias, mod.conv.out_channels, mod.conv.in_channels, 9)
+        oc = m.out[2]
+        reg(id(oc), oc.weight, oc.bias, oc.out_channels, oc.in_channels, 9)
+        self.bf16_arena = th.zeros(off, device=self.device, dtype=bf16)
+        for cw in self.convs.values():
+            if getattr(cw, "fwd_off", None) is not None and cw.fwd is None and hasattr(cw, "fwd_shape"):
+                n = cw.fwd_shape[0] * cw.fwd_shape[1]
+                cw.fwd = self.bf16_arena[cw.fwd_off:cw.fwd_off + n].view(cw.fwd_shape)
+            n = cw.tr_shape[0] * cw.tr_shape[1]
+            cw.tr = self.bf16_arena[cw.tr_off:cw.tr_off + n].view(cw.tr_shape)
+        arr = (PackEntry * len(entries))(*entries)
+        host = th.frombuffer(bytearray(bytes(arr)), dtype=th.uint8)
+        self.pack_entries = host.to(self.device)
+        self.n_pack = len(entries)
+        self.pack_max = max(max(e.cout_pad, 1) * e.taps * e.cin_pad for e in entries)
+
+    def pack(self, force=False):
+        """fp32 master arena -> bf16 operand copies (one launch). Re-run whenever the arena changed."""
+        ver = self.arena._version
+        if not (force or self.dirty or ver != self._packed_version):
+            return
+        ops.check(_lib.lib().cdae_pack_weights(self.arena.data_ptr(), self.bf16_arena.data_ptr(),
+                                               self.pack_entries.data_ptr(), self.n_pack, self.pack_max, ops.stream()))
+        self._packed_version, self.dirty = ver, False
+
+    # ------------------------------------------------------------------ planning helpers
+    def _gparam(self, p):
+        """fp32 gradient view of a (non-OHWI) parameter inside the grad arena"""
+        return self.grad_of(p)
+
+    def plan_conv(self, pl, cw, srcs, out, ksize, stride=1, resid=None, skip=None, skip_srcs=None, out_mode=0,
+                  need_dgrad=True):
+        """out = conv_ksize(concat(srcs)) + bias [+ resid] [+ conv1x1_skip(concat(skip_srcs)) + bias_skip]"""
+        chans = [s.shape[3] for s in srcs]
+        segs, K = ops.conv_segments(chans, ksize)
+        all_srcs = list(srcs)
+        bias2 = None
+        if skip is not None:
+            ssegs, _ = ops.conv_segments([s.shape[3] for s in skip_srcs], 1, wk0=K, src0=len(all_srcs))
+            segs += ssegs
+            all_srcs += list(skip_srcs)
+            bias2 = skip.bias
+        d = ops.make_igemm_desc([s.t for s in all_srcs], segs, cw.fwd, out if out_mode == 1 else out.t, cw.cout,
+                                in_stride=stride, bias=cw.bias, bias2=bias2, resid=resid.t if resid is not None else None,
+                                out_mode=out_mode)
+        pl.add_fwd(lambda: ops.igemm(d))
+        return chans
+
+    def plan_conv_bwd(self, pl, cw, srcs, dy, ksize, stride=1, need_dgrad=True):
+        """gradients of out = conv(concat(srcs)): bias, weight, and data (into srcs[i].grad()). dy: bf16 NHWC tensor."""
+        fns = []
+        gb, gw = self._gparam(cw.bias), self._gparam(cw.param)
+        if cw.cout % 8 == 0:
+            fns.append(lambda: ops.colsum_(dy, gb, c=cw.cout))
+        else:   # final eps conv: 3 real channels inside a 64-wide padded gradient
+            tmp = pl.alloc((dy.shape[-1],), th.float32)
+            fns.append(lambda: ops.zero_(tmp))
+            fns.append(lambda: ops.colsum_(dy, tmp))
+            fns.append(lambda: gb.add_(tmp[:cw.cout]))
+        off = 0
+        for s in srcs:
+            c = s.shape[3]
+            real = max(0, min(c, cw.cin - off))
+            wd = ops.make_wgrad_desc(dy, s.t, gw, cw.cout, c, ksize=ksize, in_stride=stride, ci_off=off, cin_real=real,
+                                     dw_ld=cw.cin)
+            fns.append(lambda wd=wd: ops.wgrad(wd))
+            off += c
+        if need_dgrad:
+            dyz = dy
+            if stride == 2:
+                dyz = pl.alloc((dy.shape[0], dy.shape[1] * 2, dy.shape[2] * 2, dy.shape[3]))
+                fns.append(lambda: ops.zero_insert2x(dy, out=dyz))
+            nco = dy.shape[-1]
+            if nco != cw.cout_tr_pad:
+                raise _lib.CdaeError("internal: dy pitch does not match the transposed weight packing")
+            segs, _ = ops.conv_segments([nco], ksize, transposed=True)
+            off = 0
+            for s in srcs:
+                c = s.shape[3]
+                acc, g = s.grad_acc(), s.grad()
+                d = ops.make_igemm_desc([dyz], segs, cw.tr[off:off + c], g, c, resid=g if acc else None)
+                fns.append(lambda d=d: ops.igemm(d))
+                off += c
+        return fns
+
+    # ------------------------------------------------------------------ layer planners
+    def plan_resblock(self, pl, rb, x0, x1, film, dfilm):
+        B, H, W = x0.shape[:3]
+        cin = x0.shape[3] + (x1.shape[3] if x1 is not None else 0)
+        cout = rb.out_channels
+        gn1, c1, gn2, c2 = rb.in_layers[0], rb.in_layers[2], rb.out_layers[0], rb.out_layers[3]
+        cw1, cw2 = self.convs[id(c1)], self.convs[id(c2)]
+        has_skip = not isinstance(rb.skip_connection, nn.Identity)
+        sk = self.convs[id(rb.skip_connection)] if has_skip else None
+        foff = self.film_off[id(rb)]
+        a1, h1, a2, out = T(pl, (B, H, W, cin)), T(pl, (B, H, W, cout)), T(pl, (B, H, W, cout)), T(pl, (B, H, W, cout))
+        st1 = (pl.alloc((B, 32), th.float32), pl.alloc((B, 32), th.float32))
+        st2 = (pl.alloc((B, 32), th.float32), pl.alloc((B, 32), th.float32))
+        x1t = x1.t if x1 is not None else None
+        pl.add_fwd(lambda: ops.gn_fwd(x0.t, gn1.weight, gn1.bias, x1=x1t, silu=True, out=a1.t, mean=st1[0], rstd=st1[1]))
+        self.plan_conv(pl, cw1, [a1], h1, 3)
+        pl.add_fwd(lambda: ops.gn_fwd(h1.t, gn2.weight, gn2.bias, film=film, film_off=foff, silu=True, out=a2.t,
+                                      mean=st2[0], rstd=st2[1]))
+        srcs_x = [x0] + ([x1] if x1 is not None else [])
+        if has_skip:
+            self.plan_conv(pl, cw2, [a2], out, 3, skip=sk, skip_srcs=srcs_x)
+        else:
+            self.plan_conv(pl, cw2, [a2], out, 3, resid=x0)
+        if pl.train:
+            def build_bwd():
+                fns = []
+                dout = out.grad()
+                # conv2 (+ fused skip): bias, weights, data
+                fns += self.plan_conv_bwd(pl, cw2, [a2], dout, 3)
+                if has_skip:
+                    gsk_b, gsk_w = self._gparam(sk.bias), self._gparam(sk.param)
+                    fns.append(lambda: ops.colsum_(dout, gsk_b))
+                    off = 0
+                    for s in srcs_x:
+                        c = s.shape[3]
+                        wd = ops.make_wgrad_desc(dout, s.t, gsk_w, cout, c, ksize=1, ci_off=off, dw_ld=cin)
+                        fns.append(lambda wd=wd: ops.wgrad(wd))
+                        acc, g = s.grad_acc(), s.grad()
+                        segs, _ = ops.conv_segments([cout], 1)
+                        d = ops.make_igemm_desc([dout], segs, sk.tr[off:off + c], g, c, resid=g if acc else None)
+                        fns.append(lambda d=d: ops.igemm(d))
+                        off += c
+                # GN2 (+FiLM) backward -> dh1
+                ggn2w, ggn2b = self._gparam(gn2.weight), self._gparam(gn2.bias)
+                da2, dh1 = a2.grad(), h1.grad()
+                fns.append(lambda: ops.gn_bwd(da2, h1.t, gn2.weight, gn2.bias, st2[0], st2[1], film=film, film_off=foff,
+                                              silu=True, dx0=dh1, dgamma=ggn2w, dbeta=ggn2b, dfilm=dfilm))
+                h1.g_written = True
+                # conv1
+                fns += self.plan_conv_bwd(pl, cw1, [a1], dh1, 3)
+                # GN1 backward -> dx (+ identity-skip gradient)
+                ggn1w, ggn1b = self._gparam(gn1.weight), self._gparam(gn1.bias)
+                da1 = a1.grad()
+                acc0 = x0.grad_acc()
+                acc1 = x1.grad_acc() if x1 is not None else False
+                dx0 = x0.grad()
+                dx1 = x1.grad() if x1 is not None else None
+                accmask = (1 if acc0 else 0) | (2 if acc1 else 0)
+                dadd = None if has_skip else dout
+                fns.append(lambda: ops.gn_bwd(da1, x0.t, gn1.weight, gn1.bias, st1[0], st1[1], x1=x1t, silu=True,
+                                              dx0=dx0, dx1=dx1, accumulate_dx=accmask, dgamma=ggn1w, dbeta=ggn1b,
+                                              dadd=dadd))
+                return fns
+            pl.bwd_builders.append(build_bwd)
+        return out
+
+    def plan_attention(self, pl, ab, x):
+        B, H, W, Cc = x.shape
+        Tn = H * W
+        heads = ab.num_heads
+        cwq, cwp = self.convs[id(ab.qkv)], self.convs[id(ab.proj_out)]
+        n, qkv, o, out = T(pl, (B, H, W, Cc)), T(pl, (B, H, W, 3 * Cc)), T(pl, (B, H, W, Cc)), T(pl, (B, H, W, Cc))
+        st = (pl.alloc((B, 32), th.float32), pl.alloc((B, 32), th.float32))
+        lse = pl.alloc((B, heads, Tn), th.float32)
+        pl.add_fwd(lambda: ops.gn_fwd(x.t, ab.norm.weight, ab.norm.bias, silu=False, out=n.t, mean=st[0], rstd=st[1]))
+        self.plan_conv(pl, cwq, [n], qkv, 1)
+        qv, ov = qkv.t.view(B, Tn, 3 * Cc), o.t.view(B, Tn, Cc)
+        pl.add_fwd(lambda: ops.attn_fwd(qv, heads, out=ov, lse=lse))
+        self.plan_conv(pl, cwp, [o], out, 1, resid=x)
+        if pl.train:
+            def build_bwd():
+                fns = []
+                dout = out.grad()
+                fns += self.plan_conv_bwd(pl, cwp, [o], dout, 1)
+                dqkv = qkv.grad()
+                do = o.grad()
+                fns.append(lambda: ops.attn_bwd(qv, ov, do.view(B, Tn, Cc), lse, heads, dqkv=dqkv.view(B, Tn, 3 * Cc)))
+                qkv.g_written = True
+                fns += self.plan_conv_bwd(pl, cwq, [n], dqkv, 1)
+                gw, gb = self._gparam(ab.norm.weight), self._gparam(ab.norm.bias)
+                dn = n.grad()
+                acc = x.grad_acc()
+                dx = x.grad()
+                fns.append(lambda: ops.gn_bwd(dn, x.t, ab.norm.weight, ab.norm.bias, st[0], st[1], silu=False, dx0=dx,
+                                              accumulate_dx=1 if acc else 0, dgamma=gw, dbeta=gb, dadd=dout))
+                return fns
+            pl.bwd_builders.append(build_bwd)
+        return out
+
+    def plan_downsample(self, pl, ds, x):
+        B, H, W, Cc = x.shape
+        cw = self.convs[id(ds.op)]
+        out = T(pl, (B, H // 2, W // 2, Cc))
+        self.plan_conv(pl, cw, [x], out, 3, stride=2)
+        if pl.train:
+            pl.bwd_builders.append(lambda: self.plan_conv_bwd(pl, cw, [x], out.grad(), 3, stride=2))
+        return out
+
+    def plan_upsample(self, pl, up, x):
+        B, H, W, Cc = x.shape
+        cw = self.convs[id(up.conv)]
+        u, out = T(pl, (B, 2 * H, 2 * W, Cc)), T(pl, (B, 2 * H, 2 * W, Cc))
+        pl.add_fwd(lambda: ops.upsample2x(x.t, out=u.t))
+        self.plan_conv(pl, cw, [u], out, 3)
+        if pl.train:
+            def build_bwd():
+                fns = self.plan_conv_bwd(pl, cw, [u], out.grad(), 3)
+                du = u.grad()
+                acc, dx = x.grad_acc(), x.grad()
+                fns.append(lambda: ops.sumpool2x(du, out=dx, accumulate=acc))
+                return fns
+            pl.bwd_builders.append(build_bwd)
+        return out
+
+    # ------------------------------------------------------------------ whole torso
+    def build_plan(self, B, train):
+        from .unet import ResBlock, AttentionBlock, Upsample, Downsample
+        m = self.model
+        S = m.image_size
+        pl = Plan(self, B, train)
+        pl.bwd_builders = []
+        if S is None:
+            raise _lib.CdaeError("UNetModel needs image_size (create_model passes it)")
+        pl.x_in = pl.alloc((B, m.in_channels, S, S), th.float32)
+        pl.film_in = pl.alloc((B, self.film_width), th.float32)
+        pl.dfilm = pl.alloc((B, self.film_width), th.float32) if train else None
+        pl.eps = pl.alloc((B, m.out_channels, S, S), th.float32)
+        xin = T(pl, (B, S, S, 64))
+        pl.add_fwd(lambda: ops.nchw_to_nhwc_pad(pl.x_in, 64, out=xin.t))
+        stem = m.input_blocks[0][0]
+        cws = self.convs[id(stem)]
+        h = T(pl, (B, S, S, stem.out_channels))
+        self.plan_conv(pl, cws, [xin], h, 3)
+        if train:
+            pl.bwd_builders.append(lambda h0=h: self.plan_conv_bwd(pl, cws, [xin], h0.grad(), 3, need_dgrad=False))
+        hs = [h]
+
+        def run_block(blk, h, skip=None):
+            for mod in blk:
+                if isinstance(mod, ResBlock):
+                    h = self.plan_resblock(pl, mod, h, skip, pl.film_in, pl.dfilm)
+                    skip = None
+                elif isinstance(mod, AttentionBlock):
+                    h = self.plan_attention(pl, mod, h)
+                elif isinstance(mod, Downsample):
+                    h = self.plan_downsample(pl, mod, h)
+                elif isinstance(mod, Upsample):
+                    h = self.plan_upsample(pl, mod, h)
+                else:
+                    raise _lib.CdaeError(f"unplanned module {type(mod)}")
+            return h
+
+        for blk in list(m.input_blocks)[1:]:
+            h = run_block(blk, h)
+            hs.append(h)
+        h = run_block(m.middle_block, h)
+        for blk in m.output_blocks:
+            h = run_block(blk, h, skip=hs.pop())
+        gno, co = m.out[0], m.out[2]
+        cwo = self.convs[id(co)]
+        a = T(pl, h.shape)
+        sto = (pl.alloc((B, 32), th.float32), pl.alloc((B, 32), th.float32))
+        pl.add_fwd(lambda: ops.gn_fwd(h.t, gno.weight, gno.bias, silu=True, out=a.t, mean=sto[0], rstd=sto[1]))
+        self.plan_conv(pl, cwo, [a], pl.eps, 3, out_mode=1)
+        if train:
+            pl.deps_in = pl.alloc((B, m.out_channels, S, S), th.float32)
+            dyo = pl.alloc((B, S, S, 64))
+            hfin = h
+
+            def build_out_bwd():
+                fns = [lambda: ops.nchw_to_nhwc_pad(pl.deps_in, 64, out=dyo)]
+                fns += self.plan_conv_bwd(pl, cwo, [a], dyo, 3)
+                gw, gb = self._gparam(gno.weight), self._gparam(gno.bias)
+                da = a.grad()
+                acc, dx = hfin.grad_acc(), hfin.grad()
+                fns.append(lambda: ops.gn_bwd(da, hfin.t, gno.weight, gno.bias, sto[0], sto[1], silu=True, dx0=dx,
+                                              accumulate_dx=1 if acc else 0, dgamma=gw, dbeta=gb))
+                return fns
+            pl.bwd_builders.append(build_out_bwd)
+            # backward ops are built in REVERSE layer order so that "first producer writes, later ones accumulate"
+            # is decided in true execution order
+            built = [b() for b in reversed(pl.bwd_builders)]
+            for fns in reversed(built):
+                pl.add_bwd(fns)
+        return pl
+
+    def plan(self, B, train):
+        key = (B, bool(train))
+        pl = self.plans.get(key)
+        if pl is None:
+            pl = self.build_plan(B, train)
+            self.plans[key] = pl
+        return pl
+
+    # ------------------------------------------------------------------ public entry: the torso as one autograd node
+    def film(self, emb):
+        """all 22 emb_layers(SiLU(emb)) as one GEMM (ref unet.py:148-154,186) -> [B, sum 2*Cout] fp32"""
+        return F.linear(F.silu(emb.float()), self.film_w, self.film_b)
+
+    def torso(self, x, emb):
+        if not self.owns(next(self.model.parameters())):
+            raise _lib.CdaeError("model parameters were re-homed after the engine was built; access model.engine again")
+        film = self.film(emb)
+        train = th.is_grad_enabled() and film.requires_grad
+        return _Torso.apply(self, x, film, train)
+
+
+class _Torso(th.autograd.Function):
+    @staticmethod
+    def forward(ctx, eng, x, film, train):
+        B = x.shape[0]
+        pl = eng.plan(B, train)
+        eng.pack()
+        pl.x_in.copy_(x)
+        pl.film_in.copy_(film)
+        pl.forward()
+        ctx.pl = pl
+        return pl.eps.clone()
+
+    @staticmethod
+    def backward(ctx, deps):
+        pl = ctx.pl
+        if not pl.train:
+            raise _lib.CdaeError("backward through a torso forward that ran in inference mode")
+        pl.deps_in.copy_(deps)
+        pl.dfilm.zero_()
+        pl.backward()
+        return None, None, pl.dfilm.clone(), None
+
+
+# ---------------------------------------------------------------------- standalone layers (per-layer parity, API users)
+def groupnorm_nchw(x, weight, bias, silu=False):
+    xs = x.float()
+    shp = xs.shape
+    x4 = xs.reshape(shp[0], shp[1], -1, 1)
+    xn = x4.permute(0, 2, 3, 1).contiguous().to(bf16)
+    y, _, _ = ops.gn_fwd(xn, weight.detach().float().contiguous(), bias.detach().float().contiguous(), silu=silu)
+    return y.float().permute(0, 3, 1, 2).reshape(shp).to(x.dtype)
+
+
+def run_layer(mod, x, emb=None):
+    """Inference-only execution of ONE torso layer (ResBlock / AttentionBlock / Upsample / Downsample) on NCHW fp32
+    input through the same planned kernels the full torso uses."""
+    from .unet import ResBlock, AttentionBlock, Upsample, Downsample
+    root = getattr(mod, "_cdae_root", None)
+    if root is None:
+        raise _lib.CdaeError("standalone layer calls need model.engine to have been built (layers are bound to it)")
+    eng = root.engine
+    eng.pack()
+    B, Cc, H, W = x.shape
+    pl = Plan(eng, B, False)
+    pl.bwd_builders = []
+    xin = T(pl, (B, H, W, Cc))
+    xin.t.copy_(x.float().permute(0, 2, 3, 1))
+    if isinstance(mod, ResBlock):
+        film = eng.film(emb)
+        out = eng.plan_resblock(pl, mod, xin, None, film.contiguous(), None)
+    elif isinstance(mod, AttentionBlock):
+        out = eng.plan_attention(pl, mod, xin)
+    elif isinstance(mod, Upsample):
+        out = eng.plan_upsample(pl, mod, xin)
+    elif isinstance(mod, Downsample):
+        out = eng.plan_downsample(pl, mod, xin)
+    else:
+        raise _lib.CdaeError(f"run_layer: unsupported module {type(mod)}")
+    pl._run_fwd_eager()
+    return out.t.float().permute(0, 3, 1, 2).contiguous()

@@ -283,3 +283,24 @@ def test_wgrad_matches_autograd(N, H, cin, cout, ksize, stride):
         ops.wgrad(ops.make_wgrad_desc(nhwc(dy), nhwc(x), dw2, cout, 64, ksize=3, c0=64, ci_off=64, dw_ld=cin))
         assert relerr(dw2[:, :, 64:128] - 1, ref[:, :, 64:128]) < 5e-3
         assert float((dw2[:, :, :64] - 1).abs().max()) == 0
+
+
+# ------------------------------------------------------------------ attention
+@pytest.mark.parametrize("B,T,heads,ch", [(2, 256, 4, 96), (3, 64, 4, 128), (2, 16, 4, 32), (1, 784, 2, 64), (2, 100, 1, 48)])
+def test_attention_fwd_bwd(B, T, heads, ch):
+    from causaldiffae_b200 import ops
+    from oracle.model import qkv_attention
+    g = torch.Generator().manual_seed(T + ch)
+    C = heads * ch
+    qkv = torch.randn(B, T, 3 * C, generator=g).to(dev()).to(bf16)
+    dout = torch.randn(B, T, C, generator=g).to(dev()).to(bf16)
+    # oracle layout: [B*heads, 3*ch, T]
+    ref_in = qkv.float().permute(0, 2, 1).reshape(B * heads, 3 * ch, T).clone().requires_grad_(True)
+    ref = qkv_attention(ref_in)                                        # [B*heads, ch, T]
+    ref.backward(dout.float().permute(0, 2, 1).reshape(B * heads, ch, T))
+    out, lse = ops.attn_fwd(qkv, heads)
+    assert relerr(out.float().permute(0, 2, 1).reshape(B * heads, ch, T), ref) < 1e-2
+    dqkv = ops.attn_bwd(qkv, out, dout, lse, heads)
+    got = dqkv.float().permute(0, 2, 1).reshape(B * heads, 3 * ch, T)
+    for name, sl in (("dq", slice(0, ch)), ("dk", slice(ch, 2 * ch)), ("dv", slice(2 * ch, 3 * ch))):
+        assert relerr(got[:, sl], ref_in.grad[:, sl]) < 2e-2, name

@@ -1,0 +1,146 @@
+"""Model-level parity on the GPU: causaldiffae_b200 (CUDA path through the C ABI) against the CPU oracle on identical
+seeded weights (reference state_dict format), inputs and noise.  Tolerances (BASELINE.json north_star): bf16 path,
+per-layer teacher-forced relative L2 <= 1e-2; end-to-end eps reported and bounded at 3e-2 (PyTorch's own bf16 autocast
+of the reference sits at 1.6e-2); integer work bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+CFG1 = dict(image_size=32, num_channels=64, num_res_blocks=2, class_cond=True, rep_cond=True, n_vars=2,
+            causal_modeling=True, in_channels=1, learn_sigma=False, rescale_timesteps=False,
+            rescale_learned_sigmas=False, diffusion_steps=1000)
+CFG2S = dict(image_size=64, num_channels=64, num_res_blocks=1, class_cond=False, rep_cond=True, n_vars=4,
+             causal_modeling=True, in_channels=3, learn_sigma=False, rescale_timesteps=False,
+             rescale_learned_sigmas=False, diffusion_steps=1000)
+PENDULUM = [[0, 0, 1, 1], [0, 0, 1, 1], [0, 0, 0, 0], [0, 0, 0, 0]]
+
+
+def relerr(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+def build(flags, A=None, seed=0):
+    from causaldiffae_b200 import script_util as su
+    from oracle import model as om, diffusion as od
+    full = {**su.model_and_diffusion_defaults(), **flags}
+    model, diff = su.create_model_and_diffusion(**full, A=A)
+    cfg = om.config_from_flags(**full, A=A)
+    sd = om.seeded_state_dict(cfg, seed=seed)
+    model.load_state_dict(sd, strict=True)
+    model.cuda()
+    odiff = od.Diffusion(steps=full["diffusion_steps"], timestep_respacing=full["timestep_respacing"])
+    return model, diff, cfg, sd, odiff
+
+
+def inputs(flags, B, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    C, S = flags["in_channels"], flags["image_size"]
+    return dict(x0=torch.rand(B, C, S, S, generator=g), noise=torch.randn(B, C, S, S, generator=g),
+                t=torch.randint(0, flags["diffusion_steps"], (B,), generator=g), y=torch.randint(0, 10, (B,), generator=g),
+                c=torch.rand(B, flags["n_vars"], generator=g), z=torch.randn(B, 512, generator=g),
+                w=torch.rand(B, generator=g) + 0.5)
+
+
+@pytest.mark.parametrize("flags,A", [(CFG1, None), (CFG2S, PENDULUM)])
+def test_eps_forward_given_z(flags, A):
+    from oracle import model as om
+    model, diff, cfg, sd, odiff = build(flags, A)
+    inp = inputs(flags, 4)
+    model.eval()
+    with torch.no_grad():
+        x_t = odiff.q_sample(inp["x0"], inp["t"], inp["noise"])
+        kw = dict(y=inp["y"]) if cfg.num_classes else {}
+        ref = om.unet_forward(sd, cfg, x_t, inp["t"], z=inp["z"], training=False, **kw)[0]
+        for rep in range(3):   # eager, then graph capture, then graph replay
+            got = model(x_t.cuda(), inp["t"].cuda(), z=inp["z"].cuda(), **{k: v.cuda() for k, v in kw.items()})[0]
+            err = relerr(got, ref)
+            assert err < 3e-2, (rep, err)
+
+
+def test_per_layer_teacher_forced():
+    from oracle import model as om
+    model, diff, cfg, sd, odiff = build(CFG1)
+    model.eval(); model.engine
+    g = torch.Generator().manual_seed(9)
+    emb = torch.randn(3, 256, generator=g)
+    with torch.no_grad():
+        cases = [("input_blocks.1.0.", model.input_blocks[1][0], (3, 64, 32, 32), "res"),
+                 ("input_blocks.4.0.", model.input_blocks[4][0], (3, 64, 16, 16), "res"),     # 64 -> 128 with 1x1 skip
+                 ("input_blocks.4.1.", model.input_blocks[4][1], (3, 128, 16, 16), "attn"),
+                 ("middle_block.1.", model.middle_block[1], (3, 128, 4, 4), "attn"),
+                 ("input_blocks.3.0.", model.input_blocks[3][0], (3, 64, 32, 32), "down"),
+                 ("output_blocks.2.1.", model.output_blocks[2][1], (3, 128, 4, 4), "up")]
+        for prefix, mod, shape, kind in cases:
+            x = torch.randn(shape, generator=g)
+            if kind == "res":
+                ref = om.resblock(sd, prefix, x, emb)
+                got = mod(x.cuda(), emb.cuda())
+            elif kind == "attn":
+                ref = om.attention_block(sd, prefix, x, mod.num_heads)
+                got = mod(x.cuda())
+            elif kind == "down":
+                ref = om.downsample(sd, prefix, x)
+                got = mod(x.cuda())
+            else:
+                ref = om.upsample(sd, prefix, x)
+                got = mod(x.cuda())
+            err = relerr(got, ref)
+            assert err <= 1e-2, (prefix, err)
+
+
+@pytest.mark.parametrize("flags,A,masking", [(CFG1, None, False), (CFG2S, PENDULUM, True)])
+def test_training_losses_and_gradients(flags, A, masking):
+    from oracle import model as om, diffusion as od
+    flags = {**flags, "masking": masking}
+    model, diff, cfg, sd, odiff = build(flags, A)
+    inp = inputs(flags, 4)
+    diff.kl_weight = odiff.kl_weight = 0.3
+    # oracle (CPU fp32 autograd)
+    for n in om.trainable_names(cfg):
+        sd[n].requires_grad_(True)
+    torch.manual_seed(21)
+    ref = od.training_losses(odiff, sd, cfg, inp["x0"], inp["t"], inp["noise"], y=inp["y"] if cfg.num_classes else None,
+                             c=inp["c"])
+    (ref["loss"] * inp["w"]).mean().backward()
+    # CUDA path; compat RNG mode draws xi / mask on the CPU generator in the reference's order
+    model.train()
+    kw = dict(c=inp["c"].cuda())
+    if cfg.num_classes:
+        kw["y"] = inp["y"].cuda()
+    eng = model.engine
+    for rep in range(3):           # eager, capture, replay: gradients must be identical in all three modes
+        eng.grad_arena.zero_()
+        for b in model.buffers():  # BatchNorm running stats would otherwise drift between repetitions
+            pass
+        torch.manual_seed(21)
+        terms = diff.training_losses(model, inp["x0"].cuda(), inp["t"].cuda(), model_kwargs=dict(kw),
+                                     noise=inp["noise"].cuda(), rep_cond=True, causal_modeling=True)
+        (terms["loss"] * inp["w"].cuda()).mean().backward()
+        assert relerr(terms["mse"], ref["mse"]) < 2e-2, rep
+        assert relerr(terms["kld_rep"], ref["kld_rep"]) < 1e-3, rep
+        named = dict(model.named_parameters())
+        gsq = sum(float((p.grad.float() ** 2).sum()) for p in named.values())
+        gsq_ref = sum(float((sd[n].grad ** 2).sum()) for n in om.trainable_names(cfg))
+        assert abs(np.sqrt(gsq) / np.sqrt(gsq_ref) - 1) < 3e-2, (rep, gsq, gsq_ref)
+        worst = 0.0
+        for n in om.trainable_names(cfg):
+            gr = sd[n].grad
+            if float(gr.norm()) < 1e-6 * np.sqrt(gsq_ref):
+                continue
+            worst = max(worst, relerr(named[n].grad, gr))
+        assert worst < 8e-2, (rep, worst)
+
+
+def test_zero_init_identity():
+    """reference init zeroes every out conv (Q5): eps == 0 and mse == mean(noise^2) exactly"""
+    from causaldiffae_b200 import script_util as su
+    torch.manual_seed(0)
+    model, diff = su.create_model_and_diffusion(**{**su.model_and_diffusion_defaults(), **CFG1})
+    model.cuda()
+    inp = inputs(CFG1, 2)
+    terms = diff.training_losses(model, inp["x0"].cuda(), inp["t"].cuda(), model_kwargs=dict(y=inp["y"].cuda(), c=inp["c"].cuda()),
+                                 noise=inp["noise"].cuda(), rep_cond=True, causal_modeling=True)
+    np.testing.assert_allclose(terms["mse"].detach().cpu().numpy(), (inp["noise"] ** 2).mean(dim=(1, 2, 3)).numpy(), rtol=1e-6)
