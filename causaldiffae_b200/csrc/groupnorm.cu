@@ -2,9 +2,11 @@
 // Replaces native_group_norm + casts + sigmoid/mul + FiLM mul/add (ref nn.py:430-437, unet.py:185-198, 223-231).
 //
 // One thread-block CLUSTER per sample: each CTA owns a slab of pixels, accumulates per-channel partial sums with
-// 128-bit loads, the cluster combines them through distributed shared memory, then every CTA normalises its slab
-// (the second read of the slab hits L2: the slab was just streamed by the same CTA).  Inputs may be a channel
-// concatenation of two tensors (UNet skip connections, unet.py:629) - groups may straddle the boundary.
+// vector loads (several independent requests in flight per thread), the cluster combines them through distributed
+// shared memory, then every CTA normalises its slab (the second read of the slab hits L2: it was just streamed by the
+// same CTA).  Inputs may be a channel concatenation of two tensors (UNet skip connections, unet.py:629) - groups may
+// straddle the boundary.  CTAs are 256 threads with bounded registers so that 3-4 CTAs share an SM and the reduction /
+// cluster-barrier phases of one CTA overlap the streaming phases of the others.
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -14,30 +16,51 @@ namespace cg = cooperative_groups;
 namespace cdae {
 
 constexpr int kGroups = 32;
+constexpr int kGnThreads = 256;
 
 struct GnParams {
   const __nv_bfloat16* x0; const __nv_bfloat16* x1;
   int C0, C1, C, HW, S;          // S = CTAs per sample (cluster size)
-  int nvec, R;                   // 8-channel vectors per pixel, pixel rows per pass
+  int nvec, R;                   // channel vectors per pixel, pixel rows per pass
   const float* gamma; const float* beta;
   const float* film; int film_ld, film_off;
   int silu;
   float* mean; float* rstd;
-  // forward
-  __nv_bfloat16* y;
-  // backward
-  const __nv_bfloat16* dy;
+  __nv_bfloat16* y;              // forward
+  const __nv_bfloat16* dy;       // backward
   const __nv_bfloat16* dadd;
   __nv_bfloat16* dx0; __nv_bfloat16* dx1; int accumulate_dx;
   float* dgamma; float* dbeta; float* dfilm;
 };
 
-__device__ __forceinline__ const __nv_bfloat16* src_ptr(const GnParams& p, int b, int pix, int c) {
-  return c < p.C0 ? p.x0 + ((size_t)b * p.HW + pix) * p.C0 + c : p.x1 + ((size_t)b * p.HW + pix) * p.C1 + (c - p.C0);
+// V bf16 channels per thread: 8 -> 128-bit, 4 -> 64-bit accesses
+template <int V> struct VecT;
+template <> struct VecT<8> { using type = uint4; };
+template <> struct VecT<4> { using type = uint2; };
+
+template <int V>
+__device__ __forceinline__ typename VecT<V>::type vraw(const __nv_bfloat16* p) {
+  return *reinterpret_cast<const typename VecT<V>::type*>(p);
+}
+template <int V>
+__device__ __forceinline__ void vunpack(const typename VecT<V>::type& raw, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int i = 0; i < V / 2; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+template <int V>
+__device__ __forceinline__ void vstore(__nv_bfloat16* p, const float* f) {
+  typename VecT<V>::type raw;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int i = 0; i < V / 2; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<typename VecT<V>::type*>(p) = raw;
 }
 
-// smem layout: float chan[2][C] | float gpart[2][32] | float gstat[2][32]
-__global__ void gn_fwd_kernel(const GnParams p) {
+// ------------------------------------------------------------------------------------------------ forward
+// smem: float chan[2][C] | float gpart[2][32] | float gstat[2][32]
+template <int V, int U>
+__global__ void __launch_bounds__(kGnThreads, 3) gn_fwd_kernel(const GnParams p) {
   extern __shared__ float sm[];
   float* chan = sm;
   float* gpart = sm + 2 * p.C;
@@ -45,7 +68,8 @@ __global__ void gn_fwd_kernel(const GnParams p) {
   cg::cluster_group cluster = cg::this_cluster();
   const int b = blockIdx.x / p.S, rank = blockIdx.x % p.S;
   const int vec = threadIdx.x % p.nvec, row = threadIdx.x / p.nvec;
-  const int c = vec * 8;
+  const bool active = row < p.R;
+  const int c = vec * V;
   const int per = (p.HW + p.S - 1) / p.S;
   const int p0 = rank * per, p1 = min(p.HW, p0 + per);
   const int cpg = p.C / kGroups;
@@ -53,17 +77,31 @@ __global__ void gn_fwd_kernel(const GnParams p) {
   for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) chan[i] = 0.f;
   __syncthreads();
 
-  float s[8], ss[8];
+  const bool in0 = c < p.C0;
+  const __nv_bfloat16* xbase = in0 ? p.x0 + (size_t)b * p.HW * p.C0 + c : p.x1 + (size_t)b * p.HW * p.C1 + (c - p.C0);
+  const int xpitch = in0 ? p.C0 : p.C1;
+  if (active) {
+    float s[V], ss[V];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { s[k] = 0.f; ss[k] = 0.f; }
-  for (int pix = p0 + row; pix < p1; pix += p.R) {
-    float f[8];
-    unpack8(ld8(src_ptr(p, b, pix, c)), f);
+    for (int k = 0; k < V; ++k) { s[k] = 0.f; ss[k] = 0.f; }
+    for (int pix = p0 + row; pix < p1; pix += U * p.R) {
+      typename VecT<V>::type v[U];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { s[k] += f[k]; ss[k] += f[k] * f[k]; }
+      for (int j = 0; j < U; ++j)
+        if (pix + j * p.R < p1) v[j] = vraw<V>(xbase + (size_t)(pix + j * p.R) * xpitch);
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        if (pix + j * p.R < p1) {
+          float f[V];
+          vunpack<V>(v[j], f);
+#pragma unroll
+          for (int k = 0; k < V; ++k) { s[k] += f[k]; ss[k] += f[k] * f[k]; }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) { atomicAdd(&chan[c + k], s[k]); atomicAdd(&chan[p.C + c + k], ss[k]); }
   }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) { atomicAdd(&chan[c + k], s[k]); atomicAdd(&chan[p.C + c + k], ss[k]); }
   __syncthreads();
   if (threadIdx.x < kGroups) {
     float a = 0.f, q = 0.f;
@@ -85,10 +123,11 @@ __global__ void gn_fwd_kernel(const GnParams p) {
     if (rank == 0) { p.mean[b * kGroups + threadIdx.x] = m; p.rstd[b * kGroups + threadIdx.x] = rs; }
   }
   cluster.sync();   // remote reads of gpart complete before any CTA may exit; also publishes gstat block-wide
+  if (!active) return;
 
-  float A[8], Bc[8];
+  float A[V], Bc[V];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
+  for (int k = 0; k < V; ++k) {
     const int ch = c + k, g = ch / cpg;
     const float m = gstat[g], rs = gstat[kGroups + g];
     const float ga = p.gamma[ch], be = p.beta[ch];
@@ -97,20 +136,35 @@ __global__ void gn_fwd_kernel(const GnParams p) {
     A[k] = rs * ga * sc1;
     Bc[k] = (be - m * rs * ga) * sc1 + sh;
   }
-  for (int pix = p0 + row; pix < p1; pix += p.R) {
-    float f[8];
-    unpack8(ld8(src_ptr(p, b, pix, c)), f);
+  __nv_bfloat16* ybase = p.y + (size_t)b * p.HW * p.C + c;
+  for (int pix = p0 + row; pix < p1; pix += U * p.R) {
+    typename VecT<V>::type v[U];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float u = f[k] * A[k] + Bc[k];
-      f[k] = p.silu ? silu_f(u) : u;
+    for (int j = 0; j < U; ++j)
+      if (pix + j * p.R < p1) v[j] = vraw<V>(xbase + (size_t)(pix + j * p.R) * xpitch);
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      if (pix + j * p.R < p1) {
+        float f[V];
+        vunpack<V>(v[j], f);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          const float u = f[k] * A[k] + Bc[k];
+          f[k] = p.silu ? silu_f(u) : u;
+        }
+        vstore<V>(ybase + (size_t)(pix + j * p.R) * p.C, f);
+      }
     }
-    st8(p.y + ((size_t)b * p.HW + pix) * p.C + c, pack8(f));
   }
 }
 
-// smem: float chan[2][C] (P = sum du, Q = sum du*xhat) | float tot[2][C] | float gs[2][32]
-__global__ void gn_bwd_kernel(const GnParams p) {
+// ------------------------------------------------------------------------------------------------ backward
+// With xhat = x*a1 + b1, u = xhat*G + Hh (G = gamma*(1+scale), Hh = beta*(1+scale)+shift), du = dy*silu'(u):
+//   P = sum du, Q = sum du*xhat per (sample, channel);  s1_g = sum_c G_c P_c, s2_g = sum_c G_c Q_c per group;
+//   dx = rstd*(G*du - s1/n - xhat*s2/n);  d shift = P, d scale = gamma*Q + beta*P, d beta += (1+scale)*P, d gamma += (1+scale)*Q.
+// smem: float chan[2][C] | float tot[2][C] | float gs[2][32]
+template <int V, int U>
+__global__ void __launch_bounds__(kGnThreads, 3) gn_bwd_kernel(const GnParams p) {
   extern __shared__ float sm[];
   float* chan = sm;
   float* tot = sm + 2 * p.C;
@@ -118,7 +172,8 @@ __global__ void gn_bwd_kernel(const GnParams p) {
   cg::cluster_group cluster = cg::this_cluster();
   const int b = blockIdx.x / p.S, rank = blockIdx.x % p.S;
   const int vec = threadIdx.x % p.nvec, row = threadIdx.x / p.nvec;
-  const int c = vec * 8;
+  const bool active = row < p.R;
+  const int c = vec * V;
   const int per = (p.HW + p.S - 1) / p.S;
   const int p0 = rank * per, p1 = min(p.HW, p0 + per);
   const int cpg = p.C / kGroups;
@@ -126,40 +181,57 @@ __global__ void gn_bwd_kernel(const GnParams p) {
   for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) chan[i] = 0.f;
   __syncthreads();
 
-  float mean[8], rs[8], ga[8], be[8], sc1[8], sh[8];
+  float a1[V], b1[V], G[V], Hh[V];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
+  for (int k = 0; k < V; ++k) {
     const int ch = c + k, g = ch / cpg;
-    mean[k] = p.mean[b * kGroups + g]; rs[k] = p.rstd[b * kGroups + g];
-    ga[k] = p.gamma[ch]; be[k] = p.beta[ch];
-    sc1[k] = 1.f; sh[k] = 0.f;
-    if (p.film) { const float* fr = p.film + (size_t)b * p.film_ld + p.film_off; sc1[k] = 1.f + fr[ch]; sh[k] = fr[p.C + ch]; }
+    const float m = p.mean[b * kGroups + g], rs = p.rstd[b * kGroups + g];
+    float sc1 = 1.f, sh = 0.f;
+    if (p.film) { const float* fr = p.film + (size_t)b * p.film_ld + p.film_off; sc1 = 1.f + fr[ch]; sh = fr[p.C + ch]; }
+    a1[k] = rs; b1[k] = -m * rs;
+    G[k] = p.gamma[ch] * sc1; Hh[k] = p.beta[ch] * sc1 + sh;
   }
   auto du_of = [&](float dyv, float xhat, int k) {
     if (!p.silu) return dyv;
-    const float u = (xhat * ga[k] + be[k]) * sc1[k] + sh[k];
+    const float u = xhat * G[k] + Hh[k];
     const float sg = sigmoid_f(u);
     return dyv * sg * (1.f + u * (1.f - sg));
   };
+  const bool in0 = c < p.C0;
+  const __nv_bfloat16* xbase = in0 ? p.x0 + (size_t)b * p.HW * p.C0 + c : p.x1 + (size_t)b * p.HW * p.C1 + (c - p.C0);
+  const int xpitch = in0 ? p.C0 : p.C1;
+  const __nv_bfloat16* dybase = p.dy + (size_t)b * p.HW * p.C + c;
 
-  float P[8], Q[8];
+  if (active) {
+    float P[V], Q[V];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { P[k] = 0.f; Q[k] = 0.f; }
-  for (int pix = p0 + row; pix < p1; pix += p.R) {
-    float f[8], d[8];
-    unpack8(ld8(src_ptr(p, b, pix, c)), f);
-    unpack8(ld8(p.dy + ((size_t)b * p.HW + pix) * p.C + c), d);
+    for (int k = 0; k < V; ++k) { P[k] = 0.f; Q[k] = 0.f; }
+    for (int pix = p0 + row; pix < p1; pix += U * p.R) {
+      typename VecT<V>::type vx[U], vd[U];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float xhat = (f[k] - mean[k]) * rs[k];
-      const float du = du_of(d[k], xhat, k);
-      P[k] += du; Q[k] += du * xhat;
+      for (int j = 0; j < U; ++j)
+        if (pix + j * p.R < p1) {
+          vx[j] = vraw<V>(xbase + (size_t)(pix + j * p.R) * xpitch);
+          vd[j] = vraw<V>(dybase + (size_t)(pix + j * p.R) * p.C);
+        }
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        if (pix + j * p.R < p1) {
+          float f[V], d[V];
+          vunpack<V>(vx[j], f); vunpack<V>(vd[j], d);
+#pragma unroll
+          for (int k = 0; k < V; ++k) {
+            const float xhat = f[k] * a1[k] + b1[k];
+            const float du = du_of(d[k], xhat, k);
+            P[k] += du; Q[k] += du * xhat;
+          }
+        }
+      }
     }
-  }
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { atomicAdd(&chan[c + k], P[k]); atomicAdd(&chan[p.C + c + k], Q[k]); }
+    for (int k = 0; k < V; ++k) { atomicAdd(&chan[c + k], P[k]); atomicAdd(&chan[p.C + c + k], Q[k]); }
+  }
   cluster.sync();
-  // per-sample channel totals (every CTA computes them; cheap) and group sums
   for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) {
     float a = 0.f;
     for (int r = 0; r < p.S; ++r) a += cluster.map_shared_rank(chan, r)[i];
@@ -193,69 +265,79 @@ __global__ void gn_bwd_kernel(const GnParams p) {
     }
   }
   __syncthreads();
+  if (!active) return;
 
+  // K2 = rstd*s1/n, K3 = rstd*s2/n ; dx = rstd*G*du - K2 - xhat*K3
   const float inv_n = 1.f / ((float)cpg * (float)p.HW);
-  float s1[8], s2[8], kc[8];
+  float K2[V], K3[V];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
+  for (int k = 0; k < V; ++k) {
     const int g = (c + k) / cpg;
-    s1[k] = gs[g] * inv_n; s2[k] = gs[kGroups + g] * inv_n; kc[k] = ga[k] * sc1[k];
+    K2[k] = a1[k] * gs[g] * inv_n; K3[k] = a1[k] * gs[kGroups + g] * inv_n;
   }
-  for (int pix = p0 + row; pix < p1; pix += p.R) {
-    float f[8], d[8];
-    unpack8(ld8(src_ptr(p, b, pix, c)), f);
-    unpack8(ld8(p.dy + ((size_t)b * p.HW + pix) * p.C + c), d);
-    __nv_bfloat16* dst = c < p.C0 ? p.dx0 + ((size_t)b * p.HW + pix) * p.C0 + c
-                                  : p.dx1 + ((size_t)b * p.HW + pix) * p.C1 + (c - p.C0);
-    float o[8];
-    const bool acc = (p.accumulate_dx >> (c < p.C0 ? 0 : 1)) & 1;
-    if (acc) unpack8(ld8(dst), o);
-    else {
+  __nv_bfloat16* dxbase = in0 ? p.dx0 + (size_t)b * p.HW * p.C0 + c : p.dx1 + (size_t)b * p.HW * p.C1 + (c - p.C0);
+  const __nv_bfloat16* daddbase = p.dadd ? p.dadd + (size_t)b * p.HW * p.C + c : nullptr;
+  const bool acc = (p.accumulate_dx >> (in0 ? 0 : 1)) & 1;
+  for (int pix = p0 + row; pix < p1; pix += U * p.R) {
+    typename VecT<V>::type vx[U], vd[U], vo[U], va[U];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = 0.f;
-    }
-    if (p.dadd) {
-      float a[8];
-      unpack8(ld8(p.dadd + ((size_t)b * p.HW + pix) * p.C + c), a);
+    for (int j = 0; j < U; ++j)
+      if (pix + j * p.R < p1) {
+        const size_t px = (size_t)(pix + j * p.R);
+        vx[j] = vraw<V>(xbase + px * xpitch);
+        vd[j] = vraw<V>(dybase + px * p.C);
+        if (acc) vo[j] = vraw<V>(dxbase + px * xpitch);
+        if (daddbase) va[j] = vraw<V>(daddbase + px * p.C);
+      }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] += a[k];
-    }
+    for (int j = 0; j < U; ++j) {
+      if (pix + j * p.R < p1) {
+        float f[V], d[V], o[V];
+        vunpack<V>(vx[j], f); vunpack<V>(vd[j], d);
+        if (acc) vunpack<V>(vo[j], o);
+        else {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float xhat = (f[k] - mean[k]) * rs[k];
-      const float du = du_of(d[k], xhat, k);
-      o[k] += rs[k] * (kc[k] * du - s1[k] - xhat * s2[k]);
+          for (int k = 0; k < V; ++k) o[k] = 0.f;
+        }
+        if (daddbase) {
+          float a[V];
+          vunpack<V>(va[j], a);
+#pragma unroll
+          for (int k = 0; k < V; ++k) o[k] += a[k];
+        }
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          const float xhat = f[k] * a1[k] + b1[k];
+          const float du = du_of(d[k], xhat, k);
+          o[k] += a1[k] * G[k] * du - K2[k] - xhat * K3[k];
+        }
+        vstore<V>(dxbase + (size_t)(pix + j * p.R) * xpitch, o);
+      }
     }
-    st8(dst, pack8(o));
   }
 }
 
-static int gn_config(GnParams& p, int B, int* threads, int* S_out) {
+template <int V>
+static int gn_config(GnParams& p, int* S_out) {
   p.C = p.C0 + p.C1;
   CDAE_CHECK_SHAPE(p.C % kGroups == 0, "groupnorm: C=%d not a multiple of 32", p.C);
   CDAE_CHECK_SHAPE(p.C0 % 8 == 0 && p.C1 % 8 == 0, "groupnorm: source channel counts must be multiples of 8");
-  CDAE_CHECK_SHAPE(p.C <= 2048, "groupnorm: C=%d too large", p.C);
-  p.nvec = p.C / 8;
-  int R = 512 / p.nvec;
-  while (R > 1 && (p.nvec * R) % 32 != 0) --R;
-  if (R < 1) R = 1;
-  CDAE_CHECK_SHAPE(p.nvec * R <= 1024 && p.nvec * R >= 1, "groupnorm: unsupported channel count %d", p.C);
-  p.R = R;
-  *threads = p.nvec * R;
+  p.nvec = p.C / V;
+  CDAE_CHECK_SHAPE(p.nvec <= kGnThreads, "groupnorm: C=%d too large for %d-channel vectors", p.C, V);
+  p.R = kGnThreads / p.nvec;           // rows of pixels per pass; threads with row >= R idle (C not a power of two)
   int S = 8;
-  while (S > 1 && ((int64_t)p.HW * p.C / S < 16384 || p.HW / S < R)) S >>= 1;
+  while (S > 1 && ((int64_t)p.HW * p.C / S < 8192 || p.HW / S < p.R)) S >>= 1;
   p.S = S;
   *S_out = S;
-  (void)B;
   return CDAE_OK;
 }
 
 template <typename K>
-static int gn_launch(K kernel, const GnParams& p, int B, int threads, int S, size_t smem, cudaStream_t st, const char* name) {
+static int gn_launch(K kernel, const GnParams& p, int B, int S, size_t smem, cudaStream_t st, const char* name) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(B * S));
-  cfg.blockDim = dim3((unsigned)threads);
+  cfg.blockDim = dim3((unsigned)((p.nvec * p.R + 31) / 32 * 32));   // no idle warps when C is not a power of two
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute at[1];
@@ -280,18 +362,19 @@ extern "C" int cdae_gn_fwd(const void* x0, int C0, const void* x1, int C1, int B
   p.x0 = (const __nv_bfloat16*)x0; p.x1 = (const __nv_bfloat16*)x1; p.C0 = C0; p.C1 = C1; p.HW = HW;
   p.gamma = gamma; p.beta = beta; p.film = film; p.film_ld = film_ld; p.film_off = film_off; p.silu = silu;
   p.y = (__nv_bfloat16*)y; p.mean = mean; p.rstd = rstd;
-  int threads, S;
-  int rc = gn_config(p, B, &threads, &S);
+  int S;
+  const bool wide = (C0 + C1) > 4 * kGnThreads;     // > 1024 channels: 8-channel vectors keep nvec <= 256
+  int rc = wide ? gn_config<8>(p, &S) : gn_config<4>(p, &S);
   if (rc) return rc;
   const size_t smem = sizeof(float) * (2 * p.C + 4 * kGroups);
-  return gn_launch(gn_fwd_kernel, p, B, threads, S, smem, (cudaStream_t)s, "gn_fwd_kernel");
+  if (wide) return gn_launch(gn_fwd_kernel<8, 4>, p, B, S, smem, (cudaStream_t)s, "gn_fwd_kernel");
+  return gn_launch(gn_fwd_kernel<4, 4>, p, B, S, smem, (cudaStream_t)s, "gn_fwd_kernel");
 }
 
 extern "C" int cdae_gn_bwd(const void* dy, const void* x0, int C0, const void* x1, int C1, int B, int HW,
                            const float* gamma, const float* beta, const float* film, int film_ld, int film_off, int silu,
                            const float* mean, const float* rstd, const void* dadd, void* dx0, void* dx1, int accumulate_dx,
-                           float* dgamma,
-                           float* dbeta, float* dfilm, cdae_stream s) {
+                           float* dgamma, float* dbeta, float* dfilm, cdae_stream s) {
   CDAE_CHECK_ARG(dy && x0 && gamma && beta && mean && rstd && dx0 && (C1 == 0 || (x1 && dx1)), "gn_bwd: null pointer");
   if (B == 0) return CDAE_OK;
   GnParams p;
@@ -299,11 +382,14 @@ extern "C" int cdae_gn_bwd(const void* dy, const void* x0, int C0, const void* x
   p.x0 = (const __nv_bfloat16*)x0; p.x1 = (const __nv_bfloat16*)x1; p.C0 = C0; p.C1 = C1; p.HW = HW;
   p.gamma = gamma; p.beta = beta; p.film = film; p.film_ld = film_ld; p.film_off = film_off; p.silu = silu;
   p.mean = const_cast<float*>(mean); p.rstd = const_cast<float*>(rstd);
-  p.dy = (const __nv_bfloat16*)dy; p.dadd = (const __nv_bfloat16*)dadd; p.dx0 = (__nv_bfloat16*)dx0; p.dx1 = (__nv_bfloat16*)dx1; p.accumulate_dx = accumulate_dx;
+  p.dy = (const __nv_bfloat16*)dy; p.dadd = (const __nv_bfloat16*)dadd; p.dx0 = (__nv_bfloat16*)dx0; p.dx1 = (__nv_bfloat16*)dx1;
+  p.accumulate_dx = accumulate_dx;
   p.dgamma = dgamma; p.dbeta = dbeta; p.dfilm = dfilm;
-  int threads, S;
-  int rc = gn_config(p, B, &threads, &S);
+  int S;
+  const bool wide = (C0 + C1) > 4 * kGnThreads;
+  int rc = wide ? gn_config<8>(p, &S) : gn_config<4>(p, &S);
   if (rc) return rc;
   const size_t smem = sizeof(float) * (4 * p.C + 2 * kGroups);
-  return gn_launch(gn_bwd_kernel, p, B, threads, S, smem, (cudaStream_t)s, "gn_bwd_kernel");
+  if (wide) return gn_launch(gn_bwd_kernel<8, 2>, p, B, S, smem, (cudaStream_t)s, "gn_bwd_kernel");
+  return gn_launch(gn_bwd_kernel<4, 4>, p, B, S, smem, (cudaStream_t)s, "gn_bwd_kernel");
 }

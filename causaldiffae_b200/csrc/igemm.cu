@@ -7,6 +7,7 @@
 // Replaces aten::convolution / convolution_backward (cuDNN) and addmm at the call sites listed in include/cdae.h.
 // Warp roles per CTA (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
 // warps 2..5 = epilogue (TMEM -> registers -> global), one TMEM lane quarter each.
+#include <cstdlib>
 #include <mutex>
 
 #include "sm100.cuh"
@@ -72,6 +73,7 @@ struct alignas(64) IgemmKParams {
   const float* bias2;
   const __nv_bfloat16* resid;
   int ldr;
+  int nboxes, ntn;   // v2: number of 128-pixel boxes and of N tiles
 };
 
 constexpr int kATileBytes = 128 * 128;  // 128 pixels x 64 bf16
@@ -214,6 +216,202 @@ __global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ Igem
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
 }
 
+
+// ------------------------------------------------------------------------------------------------ persistent kernel (v2)
+// One CTA per SM loops over output tiles of MT x 128 pixels by BN channels.  TMEM holds TWO accumulator sets so the
+// epilogue warps drain tile i while the TMA / MMA warps already run tile i+1 (mbarrier pairs tmem_full / tmem_empty);
+// the shared-memory ring (full / empty) runs continuously across tiles.  Larger tiles raise the FLOP : L2-byte ratio
+// (B is read once per MT A-tiles, N = 256 halves the A re-reads and takes the MMA off the smem-bandwidth limit).
+template <int BN, int MT, int STAGES>
+__global__ void __launch_bounds__(192, 1) igemm2_kernel(const __grid_constant__ IgemmKParams p) {
+  constexpr int kBTileBytes = BN * 128;
+  constexpr int kStageBytes = MT * kATileBytes + kBTileBytes;
+  constexpr uint32_t kAccCols = MT * BN;                      // one accumulator set
+  constexpr uint32_t kTmemCols = 2 * kAccCols <= 32 ? 32 : 2 * kAccCols <= 64 ? 64 : 2 * kAccCols <= 128 ? 128
+                                 : 2 * kAccCols <= 256 ? 256 : 512;
+  static_assert(2 * kAccCols <= 512, "accumulators exceed TMEM");
+  constexpr uint32_t kIdesc = make_idesc_bf16(128, BN, 0, 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+  // bars: [0,S) full | [S,2S) empty | [2S,2S+2) tmem_full | [2S+2,2S+4) tmem_empty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_m = (p.nboxes + MT - 1) / MT;
+  const int total_tiles = tiles_m * p.ntn;
+  const int boxes_per_img = p.tilesW * p.tilesH;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int kb = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int tm = tile / p.ntn, n0 = (tile % p.ntn) * BN;
+        int cw[MT], chh[MT], cn[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          const int box = tm * MT + m;
+          cw[m] = (box % p.tilesW) * p.BW * p.in_stride;
+          chh[m] = ((box / p.tilesW) % p.tilesH) * p.BH * p.in_stride;
+          cn[m] = (box / boxes_per_img) * p.BNI;          // boxes past the end land beyond N: TMA zero-fills them
+        }
+        for (int sg = 0; sg < p.nseg; ++sg) {
+          const cdae_seg g = p.seg[sg];
+          const CUtensorMap* tma = &p.tmA[g.src];
+          for (int ch = 0; ch < g.nchunk; ++ch, ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            mbar_wait(empty_bar(s), ph ^ 1);
+            mbar_expect_tx(full_bar(s), kStageBytes);
+            const uint32_t a_dst = smem_base + s * kStageBytes;
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+              tma_load_4d(a_dst + m * kATileBytes, tma, full_bar(s), g.c0 + ch * 64, cw[m] + g.dw, chh[m] + g.dh, cn[m]);
+            tma_load_2d(a_dst + MT * kATileBytes, &p.tmB, full_bar(s), g.wk + ch * 64, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    int kb = 0, it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(tempty_bar(as), aph ^ 1);          // epilogue has drained this accumulator set
+      tc_fence_after();
+      for (int kbl = 0; kbl < p.nkb; ++kbl, ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_base + s * kStageBytes;
+          const uint64_t bdesc = smem_desc_kmajor_sw128(a_addr + MT * kATileBytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+              const uint64_t adesc = smem_desc_kmajor_sw128(a_addr + m * kATileBytes);
+              umma_f16(tmem_base + (uint32_t)(as * kAccCols + m * BN), adesc + 2 * k, bdesc + 2 * k, kIdesc, (kbl | k) != 0);
+            }
+          }
+          umma_commit(empty_bar(s));
+          if (kbl == p.nkb - 1) umma_commit(tfull_bar(as));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int bw = r % p.BW, bh = (r / p.BW) % p.BH, bn = r / (p.BW * p.BH);
+    constexpr int CH = BN < 32 ? 16 : 32;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int tm = tile / p.ntn, n0 = (tile % p.ntn) * BN;
+      mbar_wait(tfull_bar(as), aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int m = 0; m < MT; ++m) {
+        const int box = tm * MT + m;
+        const int n = (box / boxes_per_img) * p.BNI + bn;
+        const int ty = ((box / p.tilesW) % p.tilesH) * p.BH + bh, tx = (box % p.tilesW) * p.BW + bw;
+        const bool row_ok = (n < p.Nimg) && (ty < p.OHt) && (tx < p.OWt);
+        const int oy = ty * p.sps + p.ooh, ox = tx * p.sps + p.oow;
+        const size_t pix = ((size_t)n * p.OH + oy) * p.OW + ox;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += CH) {
+          uint32_t acc[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccCols + m * BN + c);
+          __syncwarp();
+          if (CH == 32) tmem_ld32(taddr, acc); else tmem_ld16(taddr, acc);
+          tmem_ld_wait();
+          const int co0 = n0 + c;
+          if (!row_ok || co0 >= p.cout) {
+          } else if (p.out_mode == 0) {
+            __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + co0;
+            const __nv_bfloat16* rrow = p.resid ? p.resid + pix * p.ldr + co0 : nullptr;
+#pragma unroll
+            for (int j = 0; j < CH; j += 8) {
+              if (co0 + j >= p.cout) break;
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[j + e]);
+              if (p.bias) {
+                const float4 b0 = *reinterpret_cast<const float4*>(p.bias + co0 + j);
+                const float4 b1 = *reinterpret_cast<const float4*>(p.bias + co0 + j + 4);
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              }
+              if (p.bias2) {
+                const float4 b0 = *reinterpret_cast<const float4*>(p.bias2 + co0 + j);
+                const float4 b1 = *reinterpret_cast<const float4*>(p.bias2 + co0 + j + 4);
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              }
+              if (rrow) {
+                float rv[8]; unpack8(ld8(rrow + j), rv);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] += rv[e];
+              }
+              st8(orow + j, pack8(v));
+            }
+          } else {
+            float* o = reinterpret_cast<float*>(p.out);
+            for (int j = 0; j < CH; ++j) {
+              const int co = co0 + j;
+              if (co >= p.cout) break;
+              float v = __uint_as_float(acc[j]);
+              if (p.bias) v += p.bias[co];
+              o[(((size_t)n * p.cout + co) * p.OH + oy) * p.OW + ox] = v;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+    }
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+}
+
+template <int BN, int MT, int STAGES>
+static int launch_igemm2(const IgemmKParams& kp, cudaStream_t st) {
+  constexpr int smem = STAGES * (MT * kATileBytes + BN * 128) + 1024 + 256;
+  static_assert(smem <= 227 * 1024, "igemm2: shared memory budget");
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(igemm2_kernel<BN, MT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  });
+  if (attr_err != cudaSuccess) { set_error("igemm2 smem attribute: %s", cudaGetErrorString(attr_err)); return CDAE_ERR_CUDA; }
+  const int total = ((kp.nboxes + MT - 1) / MT) * kp.ntn;
+  const int grid = total < kNumSMs ? total : kNumSMs;
+  igemm2_kernel<BN, MT, STAGES><<<grid, 192, smem, st>>>(kp);
+  CDAE_CHECK_LAUNCH("igemm2_kernel");
+  return CDAE_OK;
+}
+
 template <int BN, int STAGES>
 static int launch_igemm(const IgemmKParams& kp, dim3 grid, cudaStream_t st) {
   constexpr int smem = STAGES * (kATileBytes + BN * 128) + 1024 + 256;
@@ -262,8 +460,17 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
     int rc = make_tmap_bf16(&kp.tmA[i], d->src[i], 4, dims, str, box, est);
     if (rc) return rc;
   }
-  int bn = d->bn;
-  if (bn == 0) bn = d->cout >= 128 ? 128 : d->cout >= 64 ? 64 : d->cout > 16 ? 32 : 16;
+  const int nboxes = kp.tilesW * kp.tilesH * tilesN;
+  static const bool use_v1 = getenv("CDAE_IGEMM_V1") != nullptr;
+  int bn = d->bn, mt = 1;
+  if (bn == 0) {
+    const int c = d->cout;
+    if (c >= 256 && c % 256 == 0 && (int64_t)nboxes * (c / 256) >= kNumSMs) bn = 256;
+    else if (c >= 192 && c % 192 == 0 && (int64_t)nboxes * (c / 192) >= kNumSMs && !use_v1) bn = 192;
+    else bn = c >= 128 ? 128 : c >= 64 ? 64 : c > 16 ? 32 : 16;
+  }
+  const int ntn = (d->cout + bn - 1) / bn;
+  if (!use_v1 && bn <= 128 && (int64_t)((nboxes + 1) / 2) * ntn >= kNumSMs) mt = 2;
   {
     uint64_t dims[2] = {(uint64_t)d->wk, (uint64_t)d->wrows};
     uint64_t str[1] = {(uint64_t)d->wk * 2};
@@ -279,15 +486,26 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
     kp.seg[i] = g;
     nkb += g.nchunk;
   }
-  kp.nseg = d->nseg; kp.nkb = nkb;
-  dim3 grid(kp.tilesW * kp.tilesH * tilesN, (d->cout + bn - 1) / bn);
+  kp.nseg = d->nseg; kp.nkb = nkb; kp.nboxes = nboxes; kp.ntn = ntn;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
+  if (use_v1) {
+    dim3 grid(nboxes, ntn);
+    switch (bn) {
+      case 16: return launch_igemm<16, 4>(kp, grid, st);
+      case 32: return launch_igemm<32, 4>(kp, grid, st);
+      case 64: return launch_igemm<64, 4>(kp, grid, st);
+      case 128: return launch_igemm<128, 3>(kp, grid, st);
+      case 256: return launch_igemm<256, 4>(kp, grid, st);
+      default: set_error("igemm: unsupported bn %d", bn); return CDAE_ERR_SHAPE;
+    }
+  }
   switch (bn) {
-    case 16: return launch_igemm<16, 4>(kp, grid, st);
-    case 32: return launch_igemm<32, 4>(kp, grid, st);
-    case 64: return launch_igemm<64, 4>(kp, grid, st);
-    case 128: return launch_igemm<128, 3>(kp, grid, st);
-    case 256: return launch_igemm<256, 4>(kp, grid, st);
+    case 16: return launch_igemm2<16, 1, 8>(kp, st);
+    case 32: return launch_igemm2<32, 1, 8>(kp, st);
+    case 64: return mt == 2 ? launch_igemm2<64, 2, 5>(kp, st) : launch_igemm2<64, 1, 8>(kp, st);
+    case 128: return mt == 2 ? launch_igemm2<128, 2, 4>(kp, st) : launch_igemm2<128, 1, 6>(kp, st);
+    case 192: return launch_igemm2<192, 1, 5>(kp, st);
+    case 256: return launch_igemm2<256, 1, 4>(kp, st);
     default: set_error("igemm: unsupported bn %d", bn); return CDAE_ERR_SHAPE;
   }
 }
@@ -464,12 +682,14 @@ extern "C" int cdae_wgrad(const cdae_wgrad_desc* d, cdae_stream s) {
     int rc = make_tmap_bf16(&kp.tmX, d->src, 4, dims, str, box, est);
     if (rc) return rc;
   }
-  const int bn = d->cin > 64 ? 128 : 64;
+  // N = 256 takes the MMA off the shared-memory bandwidth limit (A 4 KB + B 8 KB per 128 cycles); use it when Cin allows
+  const int bn = (d->cin >= 256 && d->cin % 256 == 0) ? 256 : d->cin > 64 ? 128 : 64;
   const int co_tiles = (d->cout + 127) / 128, ci_tiles = (d->cin + bn - 1) / bn;
   int splits = d->splits;
   if (splits <= 0) {
+    // one CTA per SM (the 192 KB ring excludes co-residency): fill exactly one wave when the tile count allows
     const int base = co_tiles * ci_tiles * kp.taps;
-    splits = (2 * kNumSMs + base - 1) / base;
+    splits = base >= kNumSMs ? 1 : kNumSMs / base;
     if (splits > kp.ntiles) splits = kp.ntiles;
     if (splits < 1) splits = 1;
   }
@@ -477,6 +697,7 @@ extern "C" int cdae_wgrad(const cdae_wgrad_desc* d, cdae_stream s) {
   splits = (kp.ntiles + kp.tiles_per_split - 1) / kp.tiles_per_split;
   dim3 grid(co_tiles, ci_tiles * kp.taps, splits);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
+  if (bn == 256) return launch_wgrad<256, 4>(kp, grid, st);
   if (bn == 128) return launch_wgrad<128, 6>(kp, grid, st);
   return launch_wgrad<64, 6>(kp, grid, st);
 }

@@ -27,34 +27,42 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* 
   }
 }
 
-// fp32 master [cout][taps][cin] -> bf16 [cout_pad][taps][cin_pad] and/or transposed bf16 [cin_pad][taps][cout_pad]
-__global__ void pack_weights_kernel(const float* __restrict__ arena, __nv_bfloat16* __restrict__ dst,
-                                    const cdae_pack_entry* __restrict__ entries) {
-  const cdae_pack_entry e = entries[blockIdx.x];
-  if (e.dst_fwd_off >= 0) {
-    const int64_t n = (int64_t)e.cout_pad * e.taps * e.cin_pad;
-    __nv_bfloat16* d = dst + e.dst_fwd_off;
-    for (int64_t i = blockIdx.y * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.y * blockDim.x) {
-      const int ci = (int)(i % e.cin_pad);
-      const int t = (int)((i / e.cin_pad) % e.taps);
-      const int co = (int)(i / ((int64_t)e.cin_pad * e.taps));
-      float v = 0.f;
-      if (ci < e.cin && co < e.cout) v = arena[e.src_off + ((int64_t)co * e.taps + t) * e.cin + ci];
+// fp32 master [cout][taps][cin] -> bf16 [cout_pad][taps][cin_pad] (row pitch fwd_ld) and/or transposed bf16
+// [cin_pad][taps][cout_pad] (row pitch tr_ld).  One 32x32 (co x ci) tile of one tap per block: the fp32 read and both
+// bf16 writes are coalesced (the transposed one goes through a padded shared-memory tile).  entry._pad holds the first
+// global tile index of the entry (prefix sum written by the host), found here by binary search.
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ arena, __nv_bfloat16* __restrict__ dst,
+                                                           const cdae_pack_entry* __restrict__ entries, int n_entries) {
+  int lo = 0, hi = n_entries - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (entries[mid]._pad <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const cdae_pack_entry e = entries[lo];
+  const int local = blockIdx.x - e._pad;
+  const int tci = (e.cin_pad + 31) / 32, tco = (e.cout_pad + 31) / 32;
+  const int ci0 = (local % tci) * 32, co0 = ((local / tci) % tco) * 32, t = local / (tci * tco);
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int co = co0 + ty + r * 8, ci = ci0 + tx;
+    float v = 0.f;
+    if (co < e.cout && ci < e.cin) v = arena[e.src_off + ((int64_t)co * e.taps + t) * e.cin + ci];
+    tile[ty + r * 8][tx] = v;
+    if (e.dst_fwd_off >= 0 && co < e.cout_pad && ci < e.cin_pad) {
       const int64_t ld = e.fwd_ld > 0 ? e.fwd_ld : (int64_t)e.taps * e.cin_pad;
-      d[(int64_t)co * ld + (int64_t)t * e.cin_pad + ci] = __float2bfloat16_rn(v);
+      dst[e.dst_fwd_off + (int64_t)co * ld + (int64_t)t * e.cin_pad + ci] = __float2bfloat16_rn(v);
     }
   }
   if (e.dst_tr_off >= 0) {
-    const int64_t n = (int64_t)e.cin_pad * e.taps * e.cout_pad;
-    __nv_bfloat16* d = dst + e.dst_tr_off;
-    for (int64_t i = blockIdx.y * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.y * blockDim.x) {
-      const int co = (int)(i % e.cout_pad);
-      const int t = (int)((i / e.cout_pad) % e.taps);
-      const int ci = (int)(i / ((int64_t)e.cout_pad * e.taps));
-      float v = 0.f;
-      if (ci < e.cin && co < e.cout) v = arena[e.src_off + ((int64_t)co * e.taps + t) * e.cin + ci];
-      const int64_t ld = e.tr_ld > 0 ? e.tr_ld : (int64_t)e.taps * e.cout_pad;
-      d[(int64_t)ci * ld + (int64_t)t * e.cout_pad + co] = __float2bfloat16_rn(v);
+    __syncthreads();
+    const int64_t ld = e.tr_ld > 0 ? e.tr_ld : (int64_t)e.taps * e.cout_pad;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int ci = ci0 + ty + r * 8, co = co0 + tx;
+      if (ci < e.cin_pad && co < e.cout_pad)
+        dst[e.dst_tr_off + (int64_t)ci * ld + (int64_t)t * e.cout_pad + co] = __float2bfloat16_rn(tile[tx][ty + r * 8]);
     }
   }
 }
@@ -157,13 +165,10 @@ extern "C" int cdae_nhwc_to_nchw(const void* x, float* out, int N, int C, int H,
 }
 
 extern "C" int cdae_pack_weights(const float* arena, void* bf16_arena, const cdae_pack_entry* entries_dev, int n_entries,
-                                 int64_t max_elems, cdae_stream s) {
+                                 int64_t total_tiles, cdae_stream s) {
   CDAE_CHECK_ARG(arena && bf16_arena && entries_dev, "pack_weights: null pointer");
-  if (n_entries == 0) return CDAE_OK;
-  int gy = (int)ceil_div(max_elems, 256 * 8);
-  if (gy < 1) gy = 1;
-  if (gy > 64) gy = 64;
-  pack_weights_kernel<<<dim3(n_entries, gy), 256, 0, (cudaStream_t)s>>>(arena, (__nv_bfloat16*)bf16_arena, entries_dev);
+  if (n_entries == 0 || total_tiles == 0) return CDAE_OK;
+  pack_weights_kernel<<<(unsigned)total_tiles, 256, 0, (cudaStream_t)s>>>(arena, (__nv_bfloat16*)bf16_arena, entries_dev, n_entries);
   CDAE_CHECK_LAUNCH("pack_weights_kernel");
   return CDAE_OK;
 }

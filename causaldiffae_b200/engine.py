@@ -299,6 +299,11 @@ class Engine:
                 cw.fwd = self.bf16_arena[cw.fwd_off:cw.fwd_off + n].view(cw.fwd_shape)
             n = cw.tr_shape[0] * cw.tr_shape[1]
             cw.tr = self.bf16_arena[cw.tr_off:cw.tr_off + n].view(cw.tr_shape)
+        tiles = 0
+        for e in entries:       # prefix sum of 32x32 tiles (see pack_weights_kernel)
+            e._pad = tiles
+            tiles += e.taps * ((e.cout_pad + 31) // 32) * ((e.cin_pad + 31) // 32)
+        self.pack_tiles = tiles
         arr = (PackEntry * len(entries))(*entries)
         host = th.frombuffer(bytearray(bytes(arr)), dtype=th.uint8)
         self.pack_entries = host.to(self.device)
@@ -311,7 +316,7 @@ class Engine:
         if not (force or self.dirty or ver != self._packed_version):
             return
         ops.check(_lib.lib().cdae_pack_weights(self.arena.data_ptr(), self.bf16_arena.data_ptr(),
-                                               self.pack_entries.data_ptr(), self.n_pack, self.pack_max, ops.stream()))
+                                               self.pack_entries.data_ptr(), self.n_pack, self.pack_tiles, ops.stream()))
         self._packed_version, self.dirty = ver, False
 
     # ------------------------------------------------------------------ planning helpers

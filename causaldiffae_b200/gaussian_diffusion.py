@@ -348,7 +348,8 @@ class GaussianDiffusion:
     # ------------------------------------------------------------------ losses (hot loop #1)
     def prior(self, scale, label, dim):
         """ref :718-725 vectorised: mean[b,j,:] = (label[b,j]-scale[j][0])/(scale[j][1]-0), var = 1."""
-        sc = th.as_tensor(np.asarray(scale), dtype=th.float32, device=label.device)
+        sc = self._dev_table(("prior_scale", tuple(map(tuple, np.asarray(scale).tolist()))), label.device,
+                             lambda: np.asarray(scale, dtype=np.float32))
         mean = ((label.float() - sc[:, 0]) / (sc[:, 1] - 0))[:, :, None].expand(-1, -1, dim)
         return mean, th.ones_like(mean)
 

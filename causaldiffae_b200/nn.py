@@ -87,10 +87,17 @@ def normalization(channels):
     return GroupNorm32(32, channels)
 
 
+_FREQ_CACHE = {}
+
+
 def timestep_embedding(timesteps, dim, max_period=10000):
     """ref nn.py:551-569: [cos | sin] halves, f_k = exp(-ln(max_period) k / half); int or float timesteps."""
     half = dim // 2
-    freqs = th.exp(-math.log(max_period) * th.arange(start=0, end=half, dtype=th.float32) / half).to(timesteps.device)
+    key = (half, max_period, str(timesteps.device))
+    freqs = _FREQ_CACHE.get(key)
+    if freqs is None:   # computed on the host exactly like the reference, uploaded once (no per-call H2D sync)
+        freqs = th.exp(-math.log(max_period) * th.arange(start=0, end=half, dtype=th.float32) / half).to(timesteps.device)
+        _FREQ_CACHE[key] = freqs
     args = timesteps[:, None].float() * freqs[None]
     emb = th.cat([th.cos(args), th.sin(args)], dim=-1)
     if dim % 2:

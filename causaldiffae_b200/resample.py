@@ -30,7 +30,10 @@ class ScheduleSampler(ABC):
 
     def sample(self, batch_size, device):
         idx, wts = self.sample_host(batch_size)
-        return th.from_numpy(idx).long().to(device), th.from_numpy(wts).float().to(device)
+        ti, tw = th.from_numpy(idx).long(), th.from_numpy(wts).float()
+        if th.device(device).type == "cuda":    # pinned staging + async copy: no stream synchronisation per step
+            return ti.pin_memory().to(device, non_blocking=True), tw.pin_memory().to(device, non_blocking=True)
+        return ti.to(device), tw.to(device)
 
 
 class UniformSampler(ScheduleSampler):

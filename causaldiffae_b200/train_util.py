@@ -47,7 +47,8 @@ class _FlatAdamW:
         g = self.param_groups[0]
         self.step_count += 1
         hyper = th.tensor(adam_hyper(g["lr"], self.step_count, g["betas"][0], g["betas"][1], g["eps"],
-                                     g["weight_decay"], ema_rate, grad_scale), device=self.engine.device)
+                                     g["weight_decay"], ema_rate, grad_scale)).pin_memory().to(self.engine.device,
+                                                                                               non_blocking=True)
         self.gsq.zero_()
         ops.adam_ema(self.engine.arena, self.engine.grad_arena, self.exp_avg, self.exp_avg_sq, ema, hyper, self.gsq)
         self.engine.dirty = True

@@ -241,6 +241,16 @@ class UNetModel(nn.Module):
             emb = emb + self.c_emb(c)
         return emb
 
+    def _adjacency(self, A, device):
+        """device copy of the DAG adjacency, uploaded once per device (the reference re-uploads it every forward)"""
+        if A is not None:
+            return th.as_tensor(A, dtype=th.float32, device=device)
+        cache = self.__dict__.setdefault("_A_dev", {})
+        t = cache.get(str(device))
+        if t is None:
+            t = cache[str(device)] = th.tensor(self.A, dtype=th.float32, device=device)
+        return t
+
     def forward(self, x, timesteps, y=None, c=None, x_start=None, z=None, A=None, mask=None):
         """ref unet.py:525-632 -> (eps, mu, var, z_post, mask)"""
         assert (y is not None) == (self.num_classes is not None), \
@@ -252,7 +262,7 @@ class UNetModel(nn.Module):
             if z is None:
                 mu, var = self.rep_emb.encode(x_start)
                 if self.causal_modeling:
-                    At = th.as_tensor(A if A is not None else self.A, dtype=th.float32, device=mu.device)
+                    At = self._adjacency(A, mu.device)
                     z_pre = self.causal_mask.causal_masking(mu, At)
                     z_post = self.causal_mask.nonlinearity_add_back_noise(mu, z_pre)
                     z = reparameterize(z_post, var * 0.001)

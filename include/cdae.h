@@ -69,10 +69,10 @@ typedef struct {
   int64_t dst_tr_off;   /* element offset into bf16 arena, -1: skip */
   int32_t cout, cin, taps, cout_pad, cin_pad;
   int32_t fwd_ld, tr_ld;  /* destination row pitch in elements (0: dense = taps*cin_pad / taps*cout_pad) */
-  int32_t _pad;
+  int32_t _pad;            /* first global tile index of this entry: prefix sum of taps*ceil(cout_pad/32)*ceil(cin_pad/32) */
 } cdae_pack_entry;
 int cdae_pack_weights(const float* arena, void* bf16_arena, const cdae_pack_entry* entries_dev, int n_entries,
-                      int64_t max_elems, cdae_stream s);
+                      int64_t total_tiles, cdae_stream s);
 /* nearest x2 upsample NHWC bf16 (unet.py:69-79 F.interpolate) and its adjoint (2x2 sum pool) */
 int cdae_upsample2x(const void* x, void* out, int N, int H, int W, int C, cdae_stream s);
 int cdae_sumpool2x(const void* dy, void* dx, int N, int H, int W, int C, int accumulate, cdae_stream s);
