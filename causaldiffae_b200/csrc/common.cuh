@@ -26,8 +26,9 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 constexpr int kNumSMs = 148;
 
 // ---- device helpers
-__device__ __forceinline__ float silu_f(float u) { return u / (1.0f + __expf(-u)); }
-__device__ __forceinline__ float sigmoid_f(float u) { return 1.0f / (1.0f + __expf(-u)); }
+// MUFU.EX2 + MUFU.RCP (2 ulp): the results are rounded to bf16 right after, full-precision division buys nothing
+__device__ __forceinline__ float sigmoid_f(float u) { return __fdividef(1.0f, 1.0f + __expf(-u)); }
+__device__ __forceinline__ float silu_f(float u) { return u * sigmoid_f(u); }
 
 struct __align__(16) bf16x8 { __nv_bfloat162 v[4]; };
 

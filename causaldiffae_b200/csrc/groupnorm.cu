@@ -269,19 +269,21 @@ __global__ void __launch_bounds__(kGnThreads, 3) gn_bwd_kernel(const GnParams p)
 
   // K2 = rstd*s1/n, K3 = rstd*s2/n ; dx = rstd*G*du - K2 - xhat*K3
   const float inv_n = 1.f / ((float)cpg * (float)p.HW);
-  float K2[V], K3[V];
+  float K1[V], K2[V], K3[V];
 #pragma unroll
   for (int k = 0; k < V; ++k) {
     const int g = (c + k) / cpg;
+    K1[k] = a1[k] * G[k];
     K2[k] = a1[k] * gs[g] * inv_n; K3[k] = a1[k] * gs[kGroups + g] * inv_n;
   }
+  constexpr int U2 = U > 2 ? 2 : U;   // four streams (x, dy, dx, dadd) are live here: halve the batching to stay in registers
   __nv_bfloat16* dxbase = in0 ? p.dx0 + (size_t)b * p.HW * p.C0 + c : p.dx1 + (size_t)b * p.HW * p.C1 + (c - p.C0);
   const __nv_bfloat16* daddbase = p.dadd ? p.dadd + (size_t)b * p.HW * p.C + c : nullptr;
   const bool acc = (p.accumulate_dx >> (in0 ? 0 : 1)) & 1;
-  for (int pix = p0 + row; pix < p1; pix += U * p.R) {
-    typename VecT<V>::type vx[U], vd[U], vo[U], va[U];
+  for (int pix = p0 + row; pix < p1; pix += U2 * p.R) {
+    typename VecT<V>::type vx[U2], vd[U2], vo[U2], va[U2];
 #pragma unroll
-    for (int j = 0; j < U; ++j)
+    for (int j = 0; j < U2; ++j)
       if (pix + j * p.R < p1) {
         const size_t px = (size_t)(pix + j * p.R);
         vx[j] = vraw<V>(xbase + px * xpitch);
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(kGnThreads, 3) gn_bwd_kernel(const GnParams p)
         if (daddbase) va[j] = vraw<V>(daddbase + px * p.C);
       }
 #pragma unroll
-    for (int j = 0; j < U; ++j) {
+    for (int j = 0; j < U2; ++j) {
       if (pix + j * p.R < p1) {
         float f[V], d[V], o[V];
         vunpack<V>(vx[j], f); vunpack<V>(vd[j], d);
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(kGnThreads, 3) gn_bwd_kernel(const GnParams p)
         for (int k = 0; k < V; ++k) {
           const float xhat = f[k] * a1[k] + b1[k];
           const float du = du_of(d[k], xhat, k);
-          o[k] += a1[k] * G[k] * du - K2[k] - xhat * K3[k];
+          o[k] += K1[k] * du - K2[k] - xhat * K3[k];
         }
         vstore<V>(dxbase + (size_t)(pix + j * p.R) * xpitch, o);
       }

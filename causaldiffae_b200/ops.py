@@ -223,7 +223,27 @@ def make_igemm_desc(srcs, segs, wgt, out, cout, in_stride=1, bias=None, resid=No
     return d
 
 
+PROFILE = None   # set to a list to record (kind, info, flops, start_event, end_event) per tensor-core launch (tools/)
+
+
+def _profiled(kind, info, flops, launch):
+    if PROFILE is None:
+        return launch()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    launch()
+    e1.record()
+    PROFILE.append((kind, info, flops, e0, e1))
+
+
 def igemm(desc):
+    if PROFILE is not None:
+        s = max(desc.in_stride, 1)
+        pix = desc.N * ((desc.H + s - 1) // s) * ((desc.W + s - 1) // s)
+        k = 64 * sum(desc.seg[i].nchunk for i in range(desc.nseg))
+        info = f"N{desc.N} {desc.H}x{desc.W} s{s} K{k} cout{desc.cout} nsrc{desc.nsrc}"
+        return _profiled("igemm", info, 2.0 * pix * k * desc.cout,
+                         lambda: check(_lib.lib().cdae_igemm(C.byref(desc), stream())))
     check(_lib.lib().cdae_igemm(C.byref(desc), stream()))
 
 
@@ -244,6 +264,11 @@ def make_wgrad_desc(dy, src, dw, cout, cin, ksize=3, in_stride=1, c0=0, ci_off=0
 
 
 def wgrad(desc):
+    if PROFILE is not None:
+        pix = desc.N * desc.OH * desc.OW
+        info = f"N{desc.N} {desc.OH}x{desc.OW} s{desc.in_stride} k{desc.ksize} cin{desc.cin} cout{desc.cout}"
+        return _profiled("wgrad", info, 2.0 * pix * desc.cin * desc.cout * desc.ksize ** 2,
+                         lambda: check(_lib.lib().cdae_wgrad(C.byref(desc), stream())))
     check(_lib.lib().cdae_wgrad(C.byref(desc), stream()))
 
 
