@@ -5,8 +5,9 @@
 //   weight gradient                      :  wgrad_kernel   (A = dY^T, B = X^T: both MN-major straight from NHWC)
 //
 // Replaces aten::convolution / convolution_backward (cuDNN) and addmm at the call sites listed in include/cdae.h.
-// Warp roles per CTA (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> global), one TMEM lane quarter each.
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2..5 = epilogue
+// (TMEM -> registers -> swizzled smem slab -> TMA store), one TMEM lane quarter each; igemm adds a 7th warp that
+// prefetches residual slabs.
 #include <cstdlib>
 #include <mutex>
 
@@ -30,14 +31,15 @@ EncodeTiledFn get_encode_tiled() {
 }
 
 int make_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box, const uint32_t* elem_strides) {
+                   const uint32_t* box, const uint32_t* elem_strides, bool swizzle128) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return CDAE_ERR_CUDA; }
   cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = elem_strides ? elem_strides[i] : 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu] box [%u %u %u %u]", (int)r, rank,
@@ -62,192 +64,66 @@ static void tile_geometry(int pixels, int OHt, int OWt, int* BW, int* BH, int* B
 struct alignas(64) IgemmKParams {
   CUtensorMap tmA[4];
   CUtensorMap tmB;
+  CUtensorMap tmO;   // output tile store  (out_mode 0): box {slab channels, BW, BH, BNI}
+  CUtensorMap tmR;   // residual tile load (same box)
   cdae_seg seg[CDAE_MAX_SEG];
   int nseg, nkb;
   int BW, BH, BNI, tilesW, tilesH;
   int in_stride;
   int Nimg, OHt, OWt;
-  int OH, OW, ldo, cout, sps, ooh, oow, out_mode;
+  int OH, OW, cout, out_mode, has_resid;
   void* out;
   const float* bias;
   const float* bias2;
-  const __nv_bfloat16* resid;
-  int ldr;
-  int nboxes, ntn;   // v2: number of 128-pixel boxes and of N tiles
+  int nboxes, ntn;   // number of 128-pixel boxes and of N tiles
 };
 
 constexpr int kATileBytes = 128 * 128;  // 128 pixels x 64 bf16
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(192) igemm_kernel(const __grid_constant__ IgemmKParams p) {
-  constexpr int kBTileBytes = BN * 128;
-  constexpr int kStageBytes = kATileBytes + kBTileBytes;
-  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
-  constexpr uint32_t kIdesc = make_idesc_bf16(128, BN, 0, 0);
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
-  // bars[0..S) full, [S..2S) empty, [2S] tmem_full ; then tmem base address
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t smem_base = smem_u32(smem);
-  const uint32_t bar_base = smem_u32(bars);
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(tmem_full_bar, 1);
-    mbar_fence_init();
-  }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  // tile coordinates
-  const int mt = blockIdx.x;
-  const int tw = mt % p.tilesW, th = (mt / p.tilesW) % p.tilesH, tn = mt / (p.tilesW * p.tilesH);
-  const int n0 = blockIdx.y * BN;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      const int cw = tw * p.BW * p.in_stride, chh = th * p.BH * p.in_stride, cn = tn * p.BNI;
-      int kb = 0;
-      for (int sg = 0; sg < p.nseg; ++sg) {
-        const cdae_seg g = p.seg[sg];
-        const CUtensorMap* tma = &p.tmA[g.src];
-        for (int ch = 0; ch < g.nchunk; ++ch, ++kb) {
-          const int s = kb % STAGES;
-          const uint32_t ph = (kb / STAGES) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1);
-          mbar_expect_tx(full_bar(s), kStageBytes);
-          const uint32_t a_dst = smem_base + s * kStageBytes;
-          tma_load_4d(a_dst, tma, full_bar(s), g.c0 + ch * 64, cw + g.dw, chh + g.dh, cn);
-          tma_load_2d(a_dst + kATileBytes, &p.tmB, full_bar(s), g.wk + ch * 64, n0);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    for (int kb = 0; kb < p.nkb; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (kb / STAGES) & 1;
-      mbar_wait(full_bar(s), ph);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_addr = smem_base + s * kStageBytes;
-        const uint64_t adesc = smem_desc_kmajor_sw128(a_addr);
-        const uint64_t bdesc = smem_desc_kmajor_sw128(a_addr + kATileBytes);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)  // 4 x (K = 16 bf16 = 32 B) inside the 128 B swizzle row: +2 in the >>4 address field
-          umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0);
-        umma_commit(empty_bar(s));
-        if (kb == p.nkb - 1) umma_commit(tmem_full_bar);
-      }
-      __syncwarp();
-    }
-  } else {
-    // epilogue: warp q owns TMEM lanes [32q, 32q+32)
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const int bw = r % p.BW, bh = (r / p.BW) % p.BH, bn = r / (p.BW * p.BH);
-    const int n = tn * p.BNI + bn, ty = th * p.BH + bh, tx = tw * p.BW + bw;
-    const bool row_ok = (n < p.Nimg) && (ty < p.OHt) && (tx < p.OWt);
-    const int oy = ty * p.sps + p.ooh, ox = tx * p.sps + p.oow;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    constexpr int CH = BN < 32 ? 16 : 32;
-#pragma unroll 1
-    for (int c = 0; c < BN; c += CH) {
-      uint32_t acc[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c;
-      __syncwarp();  // tcgen05.ld is warp-collective (.sync.aligned): keep the warp converged around it
-      if (CH == 32) tmem_ld32(taddr, acc); else tmem_ld16(taddr, acc);
-      tmem_ld_wait();
-      const int co0 = n0 + c;
-      if (!row_ok || co0 >= p.cout) {
-        // nothing to write for this lane / column chunk
-      } else if (p.out_mode == 0) {
-        const size_t pix = ((size_t)n * p.OH + oy) * p.OW + ox;
-        __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + co0;
-        const __nv_bfloat16* rrow = p.resid ? p.resid + pix * p.ldr + co0 : nullptr;
-#pragma unroll
-        for (int j = 0; j < CH; j += 8) {
-          if (co0 + j >= p.cout) break;
-          float v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[j + e]);
-          if (p.bias) {
-            const float4 b0 = *reinterpret_cast<const float4*>(p.bias + co0 + j);
-            const float4 b1 = *reinterpret_cast<const float4*>(p.bias + co0 + j + 4);
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-          }
-          if (p.bias2) {
-            const float4 b0 = *reinterpret_cast<const float4*>(p.bias2 + co0 + j);
-            const float4 b1 = *reinterpret_cast<const float4*>(p.bias2 + co0 + j + 4);
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-          }
-          if (rrow) {
-            float rv[8]; unpack8(ld8(rrow + j), rv);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] += rv[e];
-          }
-          st8(orow + j, pack8(v));
-        }
-      } else {
-        // NCHW fp32 (final eps conv): consecutive lanes are consecutive pixels -> coalesced per channel
-        float* o = reinterpret_cast<float*>(p.out);
-        for (int j = 0; j < CH; ++j) {
-          const int co = co0 + j;
-          if (co >= p.cout) break;
-          float v = __uint_as_float(acc[j]);
-          if (p.bias) v += p.bias[co];
-          o[(((size_t)n * p.cout + co) * p.OH + oy) * p.OW + ox] = v;
-        }
-      }
-    }
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
-}
-
-
-// ------------------------------------------------------------------------------------------------ persistent kernel (v2)
-// One CTA per SM loops over output tiles of MT x 128 pixels by BN channels.  TMEM holds TWO accumulator sets so the
-// epilogue warps drain tile i while the TMA / MMA warps already run tile i+1 (mbarrier pairs tmem_full / tmem_empty);
-// the shared-memory ring (full / empty) runs continuously across tiles.  Larger tiles raise the FLOP : L2-byte ratio
-// (B is read once per MT A-tiles, N = 256 halves the A re-reads and takes the MMA off the smem-bandwidth limit).
-template <int BN, int MT, int STAGES>
-__global__ void __launch_bounds__(192, 1) igemm2_kernel(const __grid_constant__ IgemmKParams p) {
+// One CTA per SM loops over output tiles of MT x 128 pixels by BN channels (persistent).  Warp roles (224 threads):
+//   warp 0    TMA producer: A (4-D NHWC boxes, zero fill = conv padding) and B (weights) into a STAGES-deep smem ring
+//   warp 1    TMEM allocator + single-thread tcgen05.mma issuer; TWO accumulator sets in TMEM, so the epilogue of
+//             tile i overlaps the main loop of tile i+1 (mbarrier pairs tfull / tempty)
+//   warps 2-5 epilogue: tcgen05.ld -> +bias (+bias2) (+residual) -> bf16 -> 128B-swizzled smem slab -> TMA store.
+//             Nothing in the epilogue waits on global memory: stores are asynchronous bulk copies, the residual
+//             slab is prefetched by warp 6 into the very staging buffer the result is written to (added in place).
+//   warp 6    staging-buffer manager: waits until a slab buffer has been drained by its TMA store, then either
+//             TMA-loads the residual slab into it or just marks it ready.
+template <int BN, int MT, int STAGES, int NS>
+__global__ void __launch_bounds__(224, 1) igemm2_kernel(const __grid_constant__ IgemmKParams p) {
   constexpr int kBTileBytes = BN * 128;
   constexpr int kStageBytes = MT * kATileBytes + kBTileBytes;
+  constexpr int SLABW = BN < 64 ? BN : 64;                    // channels per output slab
+  constexpr int kSlabBytes = 128 * SLABW * 2;
+  constexpr int kSlabStride = 128 * 128;                      // staging buffers are 16 KB apart (1024 B aligned)
   constexpr uint32_t kAccCols = MT * BN;                      // one accumulator set
   constexpr uint32_t kTmemCols = 2 * kAccCols <= 32 ? 32 : 2 * kAccCols <= 64 ? 64 : 2 * kAccCols <= 128 ? 128
                                  : 2 * kAccCols <= 256 ? 256 : 512;
   static_assert(2 * kAccCols <= 512, "accumulators exceed TMEM");
+  static_assert(NS >= 2, "need at least two staging buffers");
   constexpr uint32_t kIdesc = make_idesc_bf16(128, BN, 0, 0);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
-  // bars: [0,S) full | [S,2S) empty | [2S,2S+2) tmem_full | [2S+2,2S+4) tmem_empty
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint8_t* stg = smem + STAGES * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + NS * kSlabStride);
+  // bars: [0,S) full | [S,2S) empty | [2S,2S+2) tmem_full | [2S+2,2S+4) tmem_empty | NS sready | NS sfree
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + 2 * NS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = smem_u32(smem);
+  const uint32_t stg_base = smem_u32(stg);
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  auto sready_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 4 + b); };
+  auto sfree_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 4 + NS + b); };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int b = 0; b < NS; ++b) { mbar_init(sready_bar(b), 1); mbar_init(sfree_bar(b), 1); }
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
@@ -319,69 +195,110 @@ __global__ void __launch_bounds__(192, 1) igemm2_kernel(const __grid_constant__ 
         __syncwarp();
       }
     }
-  } else {
+  } else if (warp < 6) {
+    // ---------------------------------------------------------------- epilogue (warps 2..5; TMEM lane quarter = warp % 4)
     const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const int bw = r % p.BW, bh = (r / p.BW) % p.BH, bn = r / (p.BW * p.BH);
-    constexpr int CH = BN < 32 ? 16 : 32;
-    int it = 0;
+    const int r = q * 32 + lane;                     // pixel row inside a 128-pixel box
+    const bool elected = (threadIdx.x == 64);
+    const float* __restrict__ bias = p.bias;
+    const float* __restrict__ bias2 = p.bias2;
+    int it = 0, sidx = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       const int tm = tile / p.ntn, n0 = (tile % p.ntn) * BN;
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
+      if (p.out_mode == 0) {
 #pragma unroll 1
-      for (int m = 0; m < MT; ++m) {
-        const int box = tm * MT + m;
-        const int n = (box / boxes_per_img) * p.BNI + bn;
-        const int ty = ((box / p.tilesW) % p.tilesH) * p.BH + bh, tx = (box % p.tilesW) * p.BW + bw;
-        const bool row_ok = (n < p.Nimg) && (ty < p.OHt) && (tx < p.OWt);
-        const int oy = ty * p.sps + p.ooh, ox = tx * p.sps + p.oow;
-        const size_t pix = ((size_t)n * p.OH + oy) * p.OW + ox;
+        for (int m = 0; m < MT; ++m) {
+          const int box = tm * MT + m;
+          if (box >= p.nboxes) break;
+          const int w0 = (box % p.tilesW) * p.BW, h0 = ((box / p.tilesW) % p.tilesH) * p.BH;
+          const int nn0 = (box / boxes_per_img) * p.BNI;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += CH) {
-          uint32_t acc[32];
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccCols + m * BN + c);
-          __syncwarp();
-          if (CH == 32) tmem_ld32(taddr, acc); else tmem_ld16(taddr, acc);
-          tmem_ld_wait();
-          const int co0 = n0 + c;
-          if (!row_ok || co0 >= p.cout) {
-          } else if (p.out_mode == 0) {
-            __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ldo + co0;
-            const __nv_bfloat16* rrow = p.resid ? p.resid + pix * p.ldr + co0 : nullptr;
+          for (int c = 0; c < BN; c += SLABW) {
+            const int co0 = n0 + c;
+            if (co0 >= p.cout) break;
+            const int buf = sidx % NS;
+            const uint32_t sph = (sidx / NS) & 1;
+            uint32_t acc[SLABW];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccCols + m * BN + c);
+            __syncwarp();
+            if (SLABW >= 32) {
 #pragma unroll
-            for (int j = 0; j < CH; j += 8) {
-              if (co0 + j >= p.cout) break;
+              for (int h = 0; h < SLABW / 32; ++h) tmem_ld32(taddr + 32 * h, acc + 32 * h);
+            } else {
+              tmem_ld16(taddr, acc);
+            }
+            tmem_ld_wait();
+            mbar_wait(sready_bar(buf), sph);           // staging buffer drained (and residual slab landed)
+            const uint32_t row = stg_base + buf * kSlabStride + r * (SLABW * 2);
+#pragma unroll
+            for (int j = 0; j < SLABW / 8; ++j) {
               float v[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[j + e]);
-              if (p.bias) {
-                const float4 b0 = *reinterpret_cast<const float4*>(p.bias + co0 + j);
-                const float4 b1 = *reinterpret_cast<const float4*>(p.bias + co0 + j + 4);
-                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[j * 8 + e]);
+              if (co0 + j * 8 < p.cout) {
+                if (bias) {
+                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + co0 + j * 8));
+                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + co0 + j * 8 + 4));
+                  v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                }
+                if (bias2) {
+                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias2 + co0 + j * 8));
+                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias2 + co0 + j * 8 + 4));
+                  v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                }
               }
-              if (p.bias2) {
-                const float4 b0 = *reinterpret_cast<const float4*>(p.bias2 + co0 + j);
-                const float4 b1 = *reinterpret_cast<const float4*>(p.bias2 + co0 + j + 4);
-                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-              }
-              if (rrow) {
-                float rv[8]; unpack8(ld8(rrow + j), rv);
+              // 16 B chunk j of row r sits at chunk (j ^ (r & 7)) under the 128B swizzle (SLABW == 64); narrower slabs
+              // are stored unswizzled (their tensor maps use SWIZZLE_NONE)
+              const uint32_t a = SLABW == 64 ? row + (uint32_t)((j ^ (r & 7)) << 4) : row + (uint32_t)(j << 4);
+              if (p.has_resid) {
+                float rv[8];
+                unpack8(lds8(a), rv);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] += rv[e];
               }
-              st8(orow + j, pack8(v));
+              sts8(a, pack8(v));
             }
-          } else {
-            float* o = reinterpret_cast<float*>(p.out);
-            for (int j = 0; j < CH; ++j) {
-              const int co = co0 + j;
-              if (co >= p.cout) break;
-              float v = __uint_as_float(acc[j]);
-              if (p.bias) v += p.bias[co];
-              o[(((size_t)n * p.cout + co) * p.OH + oy) * p.OW + ox] = v;
+            fence_proxy_async();
+            named_bar_sync(1, 128);
+            if (elected) {
+              tma_store_4d(&p.tmO, stg_base + buf * kSlabStride, co0, w0, h0, nn0);
+              bulk_commit();
+              bulk_wait_read<NS - 2>();                 // every store but the newest NS-2 has finished reading smem
+              if (sidx >= NS - 2) mbar_arrive(sfree_bar((sidx - (NS - 2)) % NS));
+            }
+            ++sidx;
+          }
+        }
+      } else {
+        // NCHW fp32 (final eps conv, a handful of channels): consecutive lanes are consecutive pixels -> coalesced
+        const int bw = r % p.BW, bh = (r / p.BW) % p.BH, bn = r / (p.BW * p.BH);
+        constexpr int CH = BN < 32 ? 16 : 32;
+        float* __restrict__ o = reinterpret_cast<float*>(p.out);
+#pragma unroll 1
+        for (int m = 0; m < MT; ++m) {
+          const int box = tm * MT + m;
+          const int n = (box / boxes_per_img) * p.BNI + bn;
+          const int oy = ((box / p.tilesW) % p.tilesH) * p.BH + bh, ox = (box % p.tilesW) * p.BW + bw;
+          const bool row_ok = (n < p.Nimg) && (oy < p.OHt) && (ox < p.OWt);
+#pragma unroll 1
+          for (int c = 0; c < BN; c += CH) {
+            uint32_t acc[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccCols + m * BN + c);
+            __syncwarp();
+            if (CH == 32) tmem_ld32(taddr, acc); else tmem_ld16(taddr, acc);
+            tmem_ld_wait();
+            const int co0 = n0 + c;
+            if (row_ok && co0 < p.cout) {
+#pragma unroll
+              for (int j = 0; j < CH; ++j) {
+                const int co = co0 + j;
+                if (co < p.cout)
+                  o[(((size_t)n * p.cout + co) * p.OH + oy) * p.OW + ox] = __uint_as_float(acc[j]) + (bias ? __ldg(bias + co) : 0.f);
+              }
             }
           }
         }
@@ -390,39 +307,54 @@ __global__ void __launch_bounds__(192, 1) igemm2_kernel(const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
     }
+    if (elected) bulk_wait_all();                      // smem must stay valid until the last store has read it
+  } else {
+    // ---------------------------------------------------------------- warp 6: staging buffers / residual prefetch
+    if (lane == 0 && p.out_mode == 0) {
+      int sidx = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int tm = tile / p.ntn, n0 = (tile % p.ntn) * BN;
+        for (int m = 0; m < MT; ++m) {
+          const int box = tm * MT + m;
+          if (box >= p.nboxes) break;
+          const int w0 = (box % p.tilesW) * p.BW, h0 = ((box / p.tilesW) % p.tilesH) * p.BH;
+          const int nn0 = (box / boxes_per_img) * p.BNI;
+          for (int c = 0; c < BN; c += SLABW) {
+            const int co0 = n0 + c;
+            if (co0 >= p.cout) break;
+            const int buf = sidx % NS;
+            const uint32_t sph = (sidx / NS) & 1;
+            mbar_wait(sfree_bar(buf), sph ^ 1);
+            if (p.has_resid) {
+              mbar_expect_tx(sready_bar(buf), kSlabBytes);
+              tma_load_4d(stg_base + buf * kSlabStride, &p.tmR, sready_bar(buf), co0, w0, h0, nn0);
+            } else {
+              mbar_arrive(sready_bar(buf));
+            }
+            ++sidx;
+          }
+        }
+      }
+    }
   }
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
 }
 
-template <int BN, int MT, int STAGES>
+template <int BN, int MT, int STAGES, int NS>
 static int launch_igemm2(const IgemmKParams& kp, cudaStream_t st) {
-  constexpr int smem = STAGES * (MT * kATileBytes + BN * 128) + 1024 + 256;
+  constexpr int smem = STAGES * (MT * kATileBytes + BN * 128) + NS * 128 * 128 + 1024 + 256;
   static_assert(smem <= 227 * 1024, "igemm2: shared memory budget");
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(igemm2_kernel<BN, MT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_err = cudaFuncSetAttribute(igemm2_kernel<BN, MT, STAGES, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   });
   if (attr_err != cudaSuccess) { set_error("igemm2 smem attribute: %s", cudaGetErrorString(attr_err)); return CDAE_ERR_CUDA; }
   const int total = ((kp.nboxes + MT - 1) / MT) * kp.ntn;
   const int grid = total < kNumSMs ? total : kNumSMs;
-  igemm2_kernel<BN, MT, STAGES><<<grid, 192, smem, st>>>(kp);
+  igemm2_kernel<BN, MT, STAGES, NS><<<grid, 224, smem, st>>>(kp);
   CDAE_CHECK_LAUNCH("igemm2_kernel");
-  return CDAE_OK;
-}
-
-template <int BN, int STAGES>
-static int launch_igemm(const IgemmKParams& kp, dim3 grid, cudaStream_t st) {
-  constexpr int smem = STAGES * (kATileBytes + BN * 128) + 1024 + 256;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  });
-  if (attr_err != cudaSuccess) { set_error("igemm smem attribute: %s", cudaGetErrorString(attr_err)); return CDAE_ERR_CUDA; }
-  igemm_kernel<BN, STAGES><<<grid, 192, smem, st>>>(kp);
-  CDAE_CHECK_LAUNCH("igemm_kernel");
   return CDAE_OK;
 }
 
@@ -435,6 +367,7 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
   CDAE_CHECK_ARG(d->nseg >= 1 && d->nseg <= CDAE_MAX_SEG, "igemm: nseg %d out of range", d->nseg);
   CDAE_CHECK_SHAPE(d->in_stride == 1 || d->in_stride == 2, "igemm: in_stride %d", d->in_stride);
   CDAE_CHECK_SHAPE(d->wk % 8 == 0, "igemm: weight K %d must be a multiple of 8", d->wk);
+  CDAE_CHECK_SHAPE((d->sps == 0 || d->sps == 1) && d->ooh == 0 && d->oow == 0, "igemm: strided output placement is not supported");
   IgemmKParams kp;
   memset(&kp, 0, sizeof(kp));
   const int es = d->in_stride;
@@ -444,11 +377,12 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
   kp.tilesH = (OHt + kp.BH - 1) / kp.BH;
   const int tilesN = (d->N + kp.BNI - 1) / kp.BNI;
   kp.in_stride = es; kp.Nimg = d->N; kp.OHt = OHt; kp.OWt = OWt;
-  kp.OH = d->OH; kp.OW = d->OW; kp.ldo = d->ldo; kp.cout = d->cout;
-  kp.sps = d->sps > 0 ? d->sps : 1; kp.ooh = d->ooh; kp.oow = d->oow; kp.out_mode = d->out_mode;
-  kp.out = d->out; kp.bias = d->bias; kp.bias2 = d->bias2; kp.resid = reinterpret_cast<const __nv_bfloat16*>(d->resid); kp.ldr = d->ldr;
+  kp.OH = d->OH; kp.OW = d->OW; kp.cout = d->cout; kp.out_mode = d->out_mode;
+  kp.out = d->out; kp.bias = d->bias; kp.bias2 = d->bias2; kp.has_resid = d->resid != nullptr;
   CDAE_CHECK_SHAPE(kp.out_mode == 1 || (d->cout % 8 == 0 && d->ldo % 8 == 0), "igemm: NHWC output needs cout, ldo %% 8 == 0");
-  CDAE_CHECK_SHAPE(!d->resid || d->ldr % 8 == 0, "igemm: residual pitch %% 8");
+  CDAE_CHECK_SHAPE(kp.out_mode == 1 || (d->OH == OHt && d->OW == OWt), "igemm: output dims %dx%d do not match the tile grid %dx%d",
+                   d->OH, d->OW, OHt, OWt);
+  CDAE_CHECK_SHAPE(!d->resid || (d->ldr % 8 == 0 && kp.out_mode == 0), "igemm: residual needs NHWC output and pitch %% 8");
   for (int i = 0; i < d->nsrc; ++i) {
     CDAE_CHECK_ARG(d->src[i], "igemm: null source %d", i);
     CDAE_CHECK_SHAPE(d->src_c[i] % 8 == 0, "igemm: source %d channels %d must be a multiple of 8", i, d->src_c[i]);
@@ -461,22 +395,39 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
     if (rc) return rc;
   }
   const int nboxes = kp.tilesW * kp.tilesH * tilesN;
-  static const bool use_v1 = getenv("CDAE_IGEMM_V1") != nullptr;
   int bn = d->bn, mt = 1;
   if (bn == 0) {
     const int c = d->cout;
     if (c >= 256 && c % 256 == 0 && (int64_t)nboxes * (c / 256) >= kNumSMs) bn = 256;
-    else if (c >= 192 && c % 192 == 0 && (int64_t)nboxes * (c / 192) >= kNumSMs && !use_v1) bn = 192;
+    else if (c >= 192 && c % 192 == 0 && (int64_t)nboxes * (c / 192) >= kNumSMs) bn = 192;
     else bn = c >= 128 ? 128 : c >= 64 ? 64 : c > 16 ? 32 : 16;
   }
   const int ntn = (d->cout + bn - 1) / bn;
-  if (!use_v1 && bn <= 128 && (int64_t)((nboxes + 1) / 2) * ntn >= kNumSMs) mt = 2;
+  if (bn <= 128 && (int64_t)((nboxes + 1) / 2) * ntn >= kNumSMs) mt = 2;
   {
     uint64_t dims[2] = {(uint64_t)d->wk, (uint64_t)d->wrows};
     uint64_t str[1] = {(uint64_t)d->wk * 2};
     uint32_t box[2] = {64, (uint32_t)bn};
     int rc = make_tmap_bf16(&kp.tmB, d->wgt, 2, dims, str, box, nullptr);
     if (rc) return rc;
+  }
+  if (kp.out_mode == 0) {
+    const uint32_t slabw = bn < 64 ? bn : 64;
+    uint32_t box[4] = {slabw, (uint32_t)kp.BW, (uint32_t)kp.BH, (uint32_t)kp.BNI};
+    {
+      const uint64_t L = d->ldo;
+      uint64_t dims[4] = {(uint64_t)d->cout, (uint64_t)d->OW, (uint64_t)d->OH, (uint64_t)d->N};
+      uint64_t str[3] = {L * 2, L * 2 * d->OW, L * 2 * (uint64_t)d->OW * d->OH};
+      int rc = make_tmap_bf16(&kp.tmO, d->out, 4, dims, str, box, nullptr, slabw == 64);
+      if (rc) return rc;
+    }
+    if (d->resid) {
+      const uint64_t L = d->ldr;
+      uint64_t dims[4] = {(uint64_t)d->cout, (uint64_t)d->OW, (uint64_t)d->OH, (uint64_t)d->N};
+      uint64_t str[3] = {L * 2, L * 2 * d->OW, L * 2 * (uint64_t)d->OW * d->OH};
+      int rc = make_tmap_bf16(&kp.tmR, d->resid, 4, dims, str, box, nullptr, slabw == 64);
+      if (rc) return rc;
+    }
   }
   int nkb = 0;
   for (int i = 0; i < d->nseg; ++i) {
@@ -488,24 +439,13 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
   }
   kp.nseg = d->nseg; kp.nkb = nkb; kp.nboxes = nboxes; kp.ntn = ntn;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
-  if (use_v1) {
-    dim3 grid(nboxes, ntn);
-    switch (bn) {
-      case 16: return launch_igemm<16, 4>(kp, grid, st);
-      case 32: return launch_igemm<32, 4>(kp, grid, st);
-      case 64: return launch_igemm<64, 4>(kp, grid, st);
-      case 128: return launch_igemm<128, 3>(kp, grid, st);
-      case 256: return launch_igemm<256, 4>(kp, grid, st);
-      default: set_error("igemm: unsupported bn %d", bn); return CDAE_ERR_SHAPE;
-    }
-  }
   switch (bn) {
-    case 16: return launch_igemm2<16, 1, 8>(kp, st);
-    case 32: return launch_igemm2<32, 1, 8>(kp, st);
-    case 64: return mt == 2 ? launch_igemm2<64, 2, 5>(kp, st) : launch_igemm2<64, 1, 8>(kp, st);
-    case 128: return mt == 2 ? launch_igemm2<128, 2, 4>(kp, st) : launch_igemm2<128, 1, 6>(kp, st);
-    case 192: return launch_igemm2<192, 1, 5>(kp, st);
-    case 256: return launch_igemm2<256, 1, 4>(kp, st);
+    case 16: return launch_igemm2<16, 1, 8, 3>(kp, st);
+    case 32: return launch_igemm2<32, 1, 8, 3>(kp, st);
+    case 64: return mt == 2 ? launch_igemm2<64, 2, 4, 3>(kp, st) : launch_igemm2<64, 1, 7, 3>(kp, st);
+    case 128: return mt == 2 ? launch_igemm2<128, 2, 3, 3>(kp, st) : launch_igemm2<128, 1, 5, 3>(kp, st);
+    case 192: return launch_igemm2<192, 1, 4, 3>(kp, st);
+    case 256: return launch_igemm2<256, 1, 3, 3>(kp, st);
     default: set_error("igemm: unsupported bn %d", bn); return CDAE_ERR_SHAPE;
   }
 }
