@@ -41,7 +41,8 @@ class WgradDesc(C.Structure):
                 ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("OH", C.c_int32), ("OW", C.c_int32),
                 ("in_stride", C.c_int32), ("ksize", C.c_int32),
                 ("dw", C.c_void_p), ("dw_ld", C.c_int32),
-                ("ci_off", C.c_int32), ("cin_real", C.c_int32), ("splits", C.c_int32)]
+                ("ci_off", C.c_int32), ("cin_real", C.c_int32), ("splits", C.c_int32),
+                ("dbias", C.c_void_p)]
 
 
 class PackEntry(C.Structure):

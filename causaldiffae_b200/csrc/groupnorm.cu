@@ -9,6 +9,8 @@
 // cluster-barrier phases of one CTA overlap the streaming phases of the others.
 #include <cooperative_groups.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -20,8 +22,9 @@ constexpr int kGnThreads = 256;
 
 struct GnParams {
   const __nv_bfloat16* x0; const __nv_bfloat16* x1;
-  int C0, C1, C, HW, S;          // S = CTAs per sample (cluster size)
+  int C0, C1, C, HW, S;          // S = CTAs per unit (cluster size)
   int nvec, R;                   // channel vectors per pixel, pixel rows per pass
+  int CC, nchunk;                // resident kernels: channels per unit (whole groups, multiple of 8), units per sample
   const float* gamma; const float* beta;
   const float* film; int film_ld, film_off;
   int silu;
@@ -319,6 +322,379 @@ __global__ void __launch_bounds__(kGnThreads, 3) gn_bwd_kernel(const GnParams p)
   }
 }
 
+// ------------------------------------------------------------------------------------------------ resident kernels
+// Work unit = (sample, chunk of CC channels holding whole groups); a cluster of S CTAs shares the unit, each CTA owning
+// HW/S pixels.  The CTA's slab is copied global -> SHARED MEMORY with cp.async (the whole slab is in flight at once:
+// memory-level parallelism does not cost registers) and stays there between the statistics pass and the apply pass,
+// so every tensor crosses HBM (and the L2 -> SM fabric, which on B200 is barely faster than HBM) exactly once:
+// forward 2 B read + 2 B written per element, backward 4 B read + 2 B written.  128-bit accesses, 8 channels per
+// thread; partial sums go warp shuffle -> shared atomics -> DSMEM across the cluster.  The backward overwrites the dy
+// slab with du = dy*silu'(u) (bf16): the sigmoid is evaluated once per element.
+constexpr int kResElemsFwd = 32768;     // 64 KB slab (x)
+constexpr int kResElemsBwd = 32768;     // 64 KB slab (du)
+constexpr int kResThreads = 256;
+
+__device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// sigmoid(u) = 0.5*tanh(0.5u) + 0.5 : one MUFU op (the results are rounded to bf16 right after)
+__device__ __forceinline__ float sigmoid_t(float u) { return fmaf(0.5f, tanh_fast(0.5f * u), 0.5f); }
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// sum v over the lanes that share (lane % 8) - valid when nvec == 8
+__device__ __forceinline__ float vec8_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  return v;
+}
+
+// smem: bf16 slab[P][CC] | float chan[2][CC] | float gpart[2][32] | float gstat[2][32]
+__global__ void __launch_bounds__(kResThreads, 3) gn_fwd_res_kernel(const GnParams p) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int per = (p.HW + p.S - 1) / p.S;
+  uint4* slab = reinterpret_cast<uint4*>(smraw);
+  float* chan = reinterpret_cast<float*>(smraw + (size_t)per * p.CC * 2);
+  float* gpart = chan + 2 * p.CC;
+  float* gstat = gpart + 2 * kGroups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int unit = blockIdx.x / p.S, rank = blockIdx.x % p.S;
+  const int b = unit / p.nchunk, chunk = unit % p.nchunk;
+  const int vec = threadIdx.x % p.nvec, row = threadIdx.x / p.nvec;
+  const bool active = row < p.R;
+  const int cl = vec * 8, c = chunk * p.CC + cl;              // channel inside the chunk / absolute
+  const int p0 = rank * per, p1 = min(p.HW, p0 + per);
+  const int cpg = p.C / kGroups;
+  const int ng = p.CC / cpg;                                   // groups in this chunk
+
+  const bool in0 = c < p.C0;
+  const __nv_bfloat16* xbase = in0 ? p.x0 + (size_t)b * p.HW * p.C0 + c : p.x1 + (size_t)b * p.HW * p.C1 + (c - p.C0);
+  const int xpitch = in0 ? p.C0 : p.C1;
+  if (active)
+    for (int pix = p0 + row; pix < p1; pix += p.R)
+      cp_async16(&slab[(size_t)(pix - p0) * p.nvec + vec], xbase + (size_t)pix * xpitch);
+  // per-channel affine constants do not depend on the statistics: fetch them while the slab is in flight
+  float Gk[8], Hk[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int ch = active ? c + k : 0;
+    const float ga = p.gamma[ch], be = p.beta[ch];
+    float sc1 = 1.f, sh = 0.f;
+    if (p.film) { const float* fr = p.film + (size_t)b * p.film_ld + p.film_off; sc1 = 1.f + fr[ch]; sh = fr[p.C + ch]; }
+    Gk[k] = ga * sc1; Hk[k] = be * sc1 + sh;
+  }
+  for (int i = threadIdx.x; i < 2 * p.CC; i += blockDim.x) chan[i] = 0.f;
+  cp_async_wait_all();
+  __syncthreads();
+
+  float s[8], ss[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { s[k] = 0.f; ss[k] = 0.f; }
+  if (active) {
+#pragma unroll 4
+    for (int pix = p0 + row; pix < p1; pix += p.R) {
+      float f[8];
+      vunpack<8>(slab[(size_t)(pix - p0) * p.nvec + vec], f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { s[k] += f[k]; ss[k] = fmaf(f[k], f[k], ss[k]); }
+    }
+  }
+  if (p.nvec == 8) {            // warp = 4 pixel rows x 8 vectors: fold the rows before touching shared memory
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s[k] = vec8_sum(s[k]); ss[k] = vec8_sum(ss[k]); }
+    if ((threadIdx.x & 31) < 8) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { atomicAdd(&chan[cl + k], s[k]); atomicAdd(&chan[p.CC + cl + k], ss[k]); }
+    }
+  } else if (active) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { atomicAdd(&chan[cl + k], s[k]); atomicAdd(&chan[p.CC + cl + k], ss[k]); }
+  }
+  __syncthreads();
+  if (threadIdx.x < ng) {
+    float a = 0.f, q = 0.f;
+    for (int k = 0; k < cpg; ++k) { a += chan[threadIdx.x * cpg + k]; q += chan[p.CC + threadIdx.x * cpg + k]; }
+    gpart[threadIdx.x] = a; gpart[kGroups + threadIdx.x] = q;
+  }
+  cluster.sync();
+  if (threadIdx.x < ng) {
+    float a = 0.f, q = 0.f;
+    for (int r = 0; r < p.S; ++r) {
+      const float* rp = cluster.map_shared_rank(gpart, r);
+      a += rp[threadIdx.x]; q += rp[kGroups + threadIdx.x];
+    }
+    const float n = (float)cpg * (float)p.HW;
+    const float m = a / n;
+    const float var = fmaxf(q / n - m * m, 0.f);
+    const float rs = rsqrtf(var + 1e-5f);
+    gstat[threadIdx.x] = m; gstat[kGroups + threadIdx.x] = rs;
+    if (rank == 0) {
+      const int g = chunk * ng + threadIdx.x;
+      p.mean[b * kGroups + g] = m; p.rstd[b * kGroups + g] = rs;
+    }
+  }
+  cluster.sync();   // remote reads of gpart complete before any CTA may exit; also publishes gstat block-wide
+  if (!active) return;
+
+  float A[8], Bc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int g = (cl + k) / cpg;
+    const float m = gstat[g], rs = gstat[kGroups + g];
+    A[k] = rs * Gk[k];
+    Bc[k] = Hk[k] - m * rs * Gk[k];
+  }
+  __nv_bfloat16* ybase = p.y + (size_t)b * p.HW * p.C + c;
+#pragma unroll 2
+  for (int pix = p0 + row; pix < p1; pix += p.R) {
+    float f[8];
+    vunpack<8>(slab[(size_t)(pix - p0) * p.nvec + vec], f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float u = fmaf(f[k], A[k], Bc[k]);
+      f[k] = p.silu ? u * sigmoid_t(u) : u;
+    }
+    vstore<8>(ybase + (size_t)pix * p.C, f);
+  }
+}
+
+// smem: bf16 du slab[P][CC] | float chan[2][CC] | float tot[2][CC] | float gs[2][32]
+// With u = x*aG + bH (aG = rstd*G, bH = -mean*rstd*G + Hh), du = dy*silu'(u), P = sum du, Qx = sum du*x:
+//   Q = sum du*xhat = rstd*Qx - mean*rstd*P ;  dx = K1*du - K2' - x*K3'  with K1 = rstd*G, K3' = rstd^2*s2/n,
+//   K2' = rstd*s1/n - mean*rstd^2*s2/n.
+// x and dy are streamed through registers (two 128-bit loads per pixel per thread, U pixels in flight); du is kept in
+// shared memory, x is read again in the apply pass (an L2 hit: the same CTA streamed it microseconds earlier and the
+// in-flight footprint of all CTAs is a few tens of MB).
+template <int U>
+__global__ void __launch_bounds__(kResThreads, 3) gn_bwd_res_kernel(const GnParams p) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int per = (p.HW + p.S - 1) / p.S;
+  uint4* slab = reinterpret_cast<uint4*>(smraw);
+  float* chan = reinterpret_cast<float*>(smraw + (size_t)per * p.CC * 2);
+  float* tot = chan + 2 * p.CC;
+  float* gs = tot + 2 * p.CC;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int unit = blockIdx.x / p.S, rank = blockIdx.x % p.S;
+  const int b = unit / p.nchunk, chunk = unit % p.nchunk;
+  const int vec = threadIdx.x % p.nvec, row = threadIdx.x / p.nvec;
+  const bool active = row < p.R;
+  const int cl = vec * 8, c = chunk * p.CC + cl;
+  const int p0 = rank * per, p1 = min(p.HW, p0 + per);
+  const int cpg = p.C / kGroups;
+  const int ng = p.CC / cpg;
+  const int c0 = chunk * p.CC;
+
+  for (int i = threadIdx.x; i < 2 * p.CC; i += blockDim.x) chan[i] = 0.f;
+  __syncthreads();
+
+  float aG[8], bH[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int ch = active ? c + k : 0, g = ch / cpg;
+    const float m = p.mean[b * kGroups + g], rs = p.rstd[b * kGroups + g];
+    float sc1 = 1.f, sh = 0.f;
+    if (p.film) { const float* fr = p.film + (size_t)b * p.film_ld + p.film_off; sc1 = 1.f + fr[ch]; sh = fr[p.C + ch]; }
+    const float G = p.gamma[ch] * sc1, Hh = p.beta[ch] * sc1 + sh;
+    aG[k] = rs * G; bH[k] = Hh - m * rs * G;
+  }
+  const bool in0 = c < p.C0;
+  const __nv_bfloat16* xbase = in0 ? p.x0 + (size_t)b * p.HW * p.C0 + c : p.x1 + (size_t)b * p.HW * p.C1 + (c - p.C0);
+  const int xpitch = in0 ? p.C0 : p.C1;
+  const __nv_bfloat16* dybase = p.dy + (size_t)b * p.HW * p.C + c;
+
+  float P[8], Qx[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { P[k] = 0.f; Qx[k] = 0.f; }
+  if (active) {
+    for (int pix = p0 + row; pix < p1; pix += U * p.R) {
+      uint4 vx[U], vd[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j)
+        if (pix + j * p.R < p1) {
+          vx[j] = __ldg(reinterpret_cast<const uint4*>(xbase + (size_t)(pix + j * p.R) * xpitch));
+          vd[j] = __ldg(reinterpret_cast<const uint4*>(dybase + (size_t)(pix + j * p.R) * p.C));
+        }
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        if (pix + j * p.R < p1) {
+          float f[8], d[8];
+          vunpack<8>(vx[j], f); vunpack<8>(vd[j], d);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float du = d[k];
+            if (p.silu) {
+              const float u = fmaf(f[k], aG[k], bH[k]);
+              const float sg = sigmoid_t(u);
+              du = d[k] * sg * fmaf(u, 1.f - sg, 1.f);
+            }
+            P[k] += du; Qx[k] = fmaf(du, f[k], Qx[k]);
+            d[k] = du;
+          }
+          uint4 raw;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(d[2 * k], d[2 * k + 1]);
+          slab[(size_t)(pix + j * p.R - p0) * p.nvec + vec] = raw;
+        }
+      }
+    }
+  }
+  if (p.nvec == 8) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { P[k] = vec8_sum(P[k]); Qx[k] = vec8_sum(Qx[k]); }
+    if ((threadIdx.x & 31) < 8) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { atomicAdd(&chan[cl + k], P[k]); atomicAdd(&chan[p.CC + cl + k], Qx[k]); }
+    }
+  } else if (active) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { atomicAdd(&chan[cl + k], P[k]); atomicAdd(&chan[p.CC + cl + k], Qx[k]); }
+  }
+  cluster.sync();
+  for (int i = threadIdx.x; i < 2 * p.CC; i += blockDim.x) {
+    float a = 0.f;
+    for (int r = 0; r < p.S; ++r) a += cluster.map_shared_rank(chan, r)[i];
+    tot[i] = a;
+  }
+  cluster.sync();
+  // tot[0][c] = P_c, tot[1][c] = sum du*x ; Q_c = rstd*(Qx_c - mean*P_c)
+  if (threadIdx.x < ng) {
+    const int g = chunk * ng + threadIdx.x;
+    const float m = p.mean[b * kGroups + g], rs = p.rstd[b * kGroups + g];
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = 0; k < cpg; ++k) {
+      const int lc = threadIdx.x * cpg + k, ch = c0 + lc;
+      float kc = p.gamma[ch];
+      if (p.film) kc *= 1.f + p.film[(size_t)b * p.film_ld + p.film_off + ch];
+      const float Pc = tot[lc], Qc = rs * (tot[p.CC + lc] - m * Pc);
+      s1 += kc * Pc; s2 += kc * Qc;
+    }
+    gs[threadIdx.x] = s1; gs[kGroups + threadIdx.x] = s2;
+  }
+  if (rank == 0) {
+    for (int lc = threadIdx.x; lc < p.CC; lc += blockDim.x) {
+      const int ch = c0 + lc, g = ch / cpg;
+      const float m = p.mean[b * kGroups + g], rs = p.rstd[b * kGroups + g];
+      const float Pc = tot[lc], Qc = rs * (tot[p.CC + lc] - m * Pc);
+      float s1c = 1.f;
+      if (p.film) {
+        const size_t fo = (size_t)b * p.film_ld + p.film_off;
+        s1c = 1.f + p.film[fo + ch];
+        if (p.dfilm) {
+          p.dfilm[fo + ch] += p.gamma[ch] * Qc + p.beta[ch] * Pc;   // d scale  (columns owned by this layer & sample)
+          p.dfilm[fo + p.C + ch] += Pc;                              // d shift
+        }
+      }
+      if (p.dgamma) atomicAdd(p.dgamma + ch, s1c * Qc);
+      if (p.dbeta) atomicAdd(p.dbeta + ch, s1c * Pc);
+    }
+  }
+  __syncthreads();
+  if (!active) return;
+
+  const float inv_n = 1.f / ((float)cpg * (float)p.HW);
+  float K2[8], K3[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int ch = c + k, g = ch / cpg, lg = (cl + k) / cpg;
+    const float m = p.mean[b * kGroups + g], rs = p.rstd[b * kGroups + g];
+    K3[k] = rs * rs * gs[kGroups + lg] * inv_n;
+    K2[k] = rs * gs[lg] * inv_n - m * K3[k];
+  }
+  __nv_bfloat16* dxbase = in0 ? p.dx0 + (size_t)b * p.HW * p.C0 + c : p.dx1 + (size_t)b * p.HW * p.C1 + (c - p.C0);
+  const __nv_bfloat16* daddbase = p.dadd ? p.dadd + (size_t)b * p.HW * p.C + c : nullptr;
+  const bool acc = (p.accumulate_dx >> (in0 ? 0 : 1)) & 1;
+  for (int pix = p0 + row; pix < p1; pix += U * p.R) {
+    uint4 vx[U], vo[U], va[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j)
+      if (pix + j * p.R < p1) {
+        const size_t px = (size_t)(pix + j * p.R);
+        vx[j] = __ldg(reinterpret_cast<const uint4*>(xbase + px * xpitch));
+        if (acc) vo[j] = *reinterpret_cast<const uint4*>(dxbase + px * xpitch);
+        if (daddbase) va[j] = __ldg(reinterpret_cast<const uint4*>(daddbase + px * p.C));
+      }
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      if (pix + j * p.R < p1) {
+        float f[8], d[8], o[8];
+        vunpack<8>(vx[j], f);
+        vunpack<8>(slab[(size_t)(pix + j * p.R - p0) * p.nvec + vec], d);
+        if (acc) vunpack<8>(vo[j], o);
+        else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = 0.f;
+        }
+        if (daddbase) {
+          float a[8];
+          vunpack<8>(va[j], a);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] += a[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] += fmaf(aG[k], d[k], -fmaf(f[k], K3[k], K2[k]));
+        vstore<8>(dxbase + (size_t)(pix + j * p.R) * xpitch, o);
+      }
+    }
+  }
+}
+
+// pick the unit decomposition of the resident kernels; returns false when the sample does not fit (huge images)
+static bool gn_res_config(GnParams& p, int max_elems, int max_cluster) {
+  p.C = p.C0 + p.C1;
+  if (p.C % kGroups || p.C0 % 8 || p.C1 % 8) return false;
+  const int cpg = p.C / kGroups;
+  int base = cpg;                                   // lcm(8, cpg)
+  while (base % 8) base += cpg;
+  // candidates: multiples of lcm(8, cpg) that divide C.  Prefer the smallest one with >= 128 B rows whose unit fits a
+  // cluster; otherwise the largest narrower one that fits.
+  auto fits = [&](int m, int* S_out) {
+    if (m / 8 > kResThreads || m / cpg > kGroups) return false;
+    int S = 1;
+    while (S < max_cluster && (int64_t)((p.HW + S - 1) / S) * m > max_elems) S <<= 1;
+    *S_out = S;
+    return (int64_t)((p.HW + S - 1) / S) * m <= max_elems;
+  };
+  int CC = 0, S = 1;
+  for (int m = base; m <= p.C && !CC; m += base)
+    if (p.C % m == 0 && m >= 64 && fits(m, &S)) CC = m;
+  if (!CC)
+    for (int m = base; m < 64 && m <= p.C; m += base)
+      if (p.C % m == 0 && fits(m, &S)) CC = m;       // keeps the largest
+  if (!CC) return false;
+  fits(CC, &S);
+  p.CC = CC; p.nchunk = p.C / CC; p.S = S;
+  p.nvec = CC / 8; p.R = kResThreads / p.nvec;
+  return true;
+}
+
+template <int TAG, typename K>
+static int gn_res_launch(K kernel, const GnParams& p, int B, size_t smem, cudaStream_t st, const char* name) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  });
+  if (attr_err != cudaSuccess) { set_error("%s attributes: %s", name, cudaGetErrorString(attr_err)); return CDAE_ERR_CUDA; }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(B * p.nchunk * p.S));
+  cfg.blockDim = dim3((unsigned)((p.nvec * p.R + 31) / 32 * 32));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)p.S; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p);
+  if (e != cudaSuccess) { set_error("%s: %s", name, cudaGetErrorString(e)); return CDAE_ERR_CUDA; }
+  return CDAE_OK;
+}
+
 template <int V>
 static int gn_config(GnParams& p, int* S_out) {
   p.C = p.C0 + p.C1;
@@ -364,6 +740,11 @@ extern "C" int cdae_gn_fwd(const void* x0, int C0, const void* x1, int C1, int B
   p.x0 = (const __nv_bfloat16*)x0; p.x1 = (const __nv_bfloat16*)x1; p.C0 = C0; p.C1 = C1; p.HW = HW;
   p.gamma = gamma; p.beta = beta; p.film = film; p.film_ld = film_ld; p.film_off = film_off; p.silu = silu;
   p.y = (__nv_bfloat16*)y; p.mean = mean; p.rstd = rstd;
+  if (gn_res_config(p, kResElemsFwd, 8)) {
+    const size_t per = (size_t)((HW + p.S - 1) / p.S);
+    const size_t smem_res = per * p.CC * 2 + sizeof(float) * (2 * p.CC + 4 * kGroups);
+    return gn_res_launch<0>(gn_fwd_res_kernel, p, B, smem_res, (cudaStream_t)s, "gn_fwd_res_kernel");
+  }
   int S;
   const bool wide = (C0 + C1) > 4 * kGnThreads;     // > 1024 channels: 8-channel vectors keep nvec <= 256
   int rc = wide ? gn_config<8>(p, &S) : gn_config<4>(p, &S);
@@ -387,6 +768,11 @@ extern "C" int cdae_gn_bwd(const void* dy, const void* x0, int C0, const void* x
   p.dy = (const __nv_bfloat16*)dy; p.dadd = (const __nv_bfloat16*)dadd; p.dx0 = (__nv_bfloat16*)dx0; p.dx1 = (__nv_bfloat16*)dx1;
   p.accumulate_dx = accumulate_dx;
   p.dgamma = dgamma; p.dbeta = dbeta; p.dfilm = dfilm;
+  if (gn_res_config(p, kResElemsBwd, 8)) {
+    const size_t per = (size_t)((HW + p.S - 1) / p.S);
+    const size_t smem_res = per * p.CC * 2 + sizeof(float) * (4 * p.CC + 2 * kGroups);
+    return gn_res_launch<1>(gn_bwd_res_kernel<2>, p, B, smem_res, (cudaStream_t)s, "gn_bwd_res_kernel");
+  }
   int S;
   const bool wide = (C0 + C1) > 4 * kGnThreads;
   int rc = wide ? gn_config<8>(p, &S) : gn_config<4>(p, &S);

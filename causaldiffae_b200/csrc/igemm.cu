@@ -587,6 +587,213 @@ static int launch_wgrad(const WgradKParams& kp, dim3 grid, cudaStream_t st) {
   return CDAE_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ 3x3 stride-1 weight gradient
+// One CTA = (128 output channels) x (BN input channels) x (ONE KERNEL ROW: the three taps dw = -1,0,+1) over a split of
+// the pixel tiles.  Per 8x8-pixel K tile the CTA loads dY once (64 px x 128 co) and ONE halo tile of the source
+// (8 rows x 10 columns x BN channels); the three taps read that halo tile through row-shifted MN-major descriptors
+// (start address + (dw+1)*128 B, 8-pixel groups 1280 B apart - the 128B swizzle is a pure function of the shared-memory
+// address, see tools/exp_desc.cu), each into its own TMEM accumulator.  L2 -> SM traffic per MMA drops 2.7x against the
+// one-tap kernel.  The bias gradient (column sums of dY, aten::convolution_backward's third output) rides along as an
+// N = 8 MMA against a tile of ones.
+struct alignas(64) Wgrad3KParams {
+  CUtensorMap tmDy;   // dY  [N, OH, OW, ldy]  box {64, 8, 8, 1}
+  CUtensorMap tmX;    // src [N, H, W, C]      box {64, 10, 8, 1}
+  int tilesW, tilesH, ntiles, tiles_per_split;
+  int c0;
+  float* dw; int dw_ld, ci_off, cin_real, cout;
+  float* dbias;
+};
+
+constexpr int kW3DyBytes = 2 * kWgBoxBytes;        // 64 px x 128 co
+constexpr int kW3XBlk = 80 * 128;                  // 8 rows x 10 columns of pixels x 64 channels
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192) wgrad3_kernel(const __grid_constant__ Wgrad3KParams p) {
+  constexpr int kXBytes = (BN / 64) * kW3XBlk;
+  constexpr int kStageBytes = kW3DyBytes + ((kXBytes + 1023) & ~1023);
+  constexpr uint32_t kTmemCols = 3 * BN + 8 <= 256 ? 256 : 512;
+  constexpr uint32_t kIdesc = make_idesc_bf16(128, BN, 1, 1);
+  constexpr uint32_t kIdescOnes = make_idesc_bf16(128, 8, 1, 1);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ones = smem + STAGES * kStageBytes;                      // 16 rows x 128 B of bf16 1.0
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ones + 2048);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+
+  const int co0 = blockIdx.x * 128;
+  const int ci_tiles = gridDim.y / 3;
+  const int krow = blockIdx.y / ci_tiles, ci0 = (blockIdx.y % ci_tiles) * BN;     // kernel row 0..2 -> dh = krow - 1
+  const bool do_bias = p.dbias != nullptr && krow == 1 && ci0 == 0;
+  const int t_begin = blockIdx.z * p.tiles_per_split;
+  int t_end = t_begin + p.tiles_per_split; if (t_end > p.ntiles) t_end = p.ntiles;
+  const int nkb = t_end - t_begin;
+
+  for (int i = threadIdx.x; i < 2048 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (nkb > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int t = t_begin + kb;
+          const int tw = t % p.tilesW, th = (t / p.tilesW) % p.tilesH, tn = t / (p.tilesW * p.tilesH);
+          const int s = kb % STAGES;
+          const uint32_t ph = (kb / STAGES) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_expect_tx(full_bar(s), kW3DyBytes + kXBytes);
+          const uint32_t a_dst = smem_base + s * kStageBytes;
+          tma_load_4d(a_dst, &p.tmDy, full_bar(s), co0, tw * 8, th * 8, tn);
+          tma_load_4d(a_dst + kWgBoxBytes, &p.tmDy, full_bar(s), co0 + 64, tw * 8, th * 8, tn);
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_4d(a_dst + kW3DyBytes + j * kW3XBlk, &p.tmX, full_bar(s), p.c0 + ci0 + j * 64, tw * 8 - 1,
+                        th * 8 + krow - 1, tn);
+        }
+      }
+    } else if (warp == 1) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_base + s * kStageBytes;
+          // A = dY^T: 64-channel blocks kWgBoxBytes apart (LBO), 8-pixel K groups 1024 B apart (SBO)
+          const uint64_t adesc = smem_desc_mnmajor_sw128(a_addr, kWgBoxBytes, 1024);
+#pragma unroll
+          for (int tap = 0; tap < 3; ++tap) {
+            // B = shifted source window: pixel (h, w) of the tile sits at halo row h*10 + w + tap
+            const uint64_t bdesc = smem_desc_mnmajor_sw128(a_addr + kW3DyBytes + tap * 128, kW3XBlk, 1280);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)   // K = 16 pixels = two image rows of the tile: +2 SBO steps per MMA
+              umma_f16(tmem_base + tap * BN, adesc + 128 * k, bdesc + 160 * k, kIdesc, (kb | k) != 0);
+          }
+          if (do_bias) {
+            const uint64_t odesc = smem_desc_mnmajor_sw128(smem_u32(ones), 0, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(tmem_base + 3 * BN, adesc + 128 * k, odesc, kIdescOnes, (kb | k) != 0);
+          }
+          umma_commit(empty_bar(s));
+          if (kb == nkb - 1) umma_commit(tmem_full_bar);
+        }
+        __syncwarp();
+      }
+    } else {
+      const int q = warp & 3;
+      const int co = co0 + q * 32 + lane;
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int tap = 0; tap < 3; ++tap) {
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t acc[32];
+          __syncwarp();
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tap * BN + c), acc);
+          tmem_ld_wait();
+          float* row = p.dw + ((size_t)co * 9 + krow * 3 + tap) * p.dw_ld + p.ci_off + ci0 + c;
+          const int lim = p.cin_real - (ci0 + c);
+          if (co >= p.cout) {
+            // padded output-channel row: nothing to accumulate
+          } else if (lim >= 32 && (p.dw_ld % 4 == 0) && ((p.ci_off & 3) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              atomicAdd(reinterpret_cast<float4*>(row + j),
+                        make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]),
+                                    __uint_as_float(acc[j + 3])));
+          } else {
+            for (int j = 0; j < 32 && j < lim; ++j) atomicAdd(row + j, __uint_as_float(acc[j]));
+          }
+        }
+      }
+      if (do_bias) {
+        uint32_t acc[16];
+        __syncwarp();
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(3 * BN), acc);   // columns 0..7 hold the same sum
+        tmem_ld_wait();
+        if (co < p.cout) atomicAdd(p.dbias + co, __uint_as_float(acc[0]));
+      }
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+}
+
+template <int BN, int STAGES>
+static int launch_wgrad3(const Wgrad3KParams& kp, dim3 grid, cudaStream_t st) {
+  constexpr int xb = ((BN / 64) * kW3XBlk + 1023) & ~1023;
+  constexpr int smem = STAGES * (kW3DyBytes + xb) + 2048 + 1024 + 256;
+  static_assert(smem <= 227 * 1024, "wgrad3: shared memory budget");
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(wgrad3_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  });
+  if (attr_err != cudaSuccess) { set_error("wgrad3 smem attribute: %s", cudaGetErrorString(attr_err)); return CDAE_ERR_CUDA; }
+  wgrad3_kernel<BN, STAGES><<<grid, 192, smem, st>>>(kp);
+  CDAE_CHECK_LAUNCH("wgrad3_kernel");
+  return CDAE_OK;
+}
+
+static int wgrad3(const cdae_wgrad_desc* d, cudaStream_t st) {
+  Wgrad3KParams kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.tilesW = (d->OW + 7) / 8; kp.tilesH = (d->OH + 7) / 8;
+  kp.ntiles = kp.tilesW * kp.tilesH * d->N;
+  kp.c0 = d->c0;
+  kp.dw = d->dw; kp.dw_ld = d->dw_ld; kp.ci_off = d->ci_off;
+  kp.cin_real = d->cin_real > 0 ? d->cin_real : d->cin; kp.cout = d->cout;
+  kp.dbias = d->dbias;
+  {
+    const uint64_t C = d->ldy;
+    uint64_t dims[4] = {C, (uint64_t)d->OW, (uint64_t)d->OH, (uint64_t)d->N};
+    uint64_t str[3] = {C * 2, C * 2 * d->OW, C * 2 * (uint64_t)d->OW * d->OH};
+    uint32_t box[4] = {64, 8, 8, 1};
+    int rc = make_tmap_bf16(&kp.tmDy, d->dy, 4, dims, str, box, nullptr);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t C = d->src_c;
+    uint64_t dims[4] = {C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
+    uint64_t str[3] = {C * 2, C * 2 * d->W, C * 2 * (uint64_t)d->W * d->H};
+    uint32_t box[4] = {64, 10, 8, 1};
+    int rc = make_tmap_bf16(&kp.tmX, d->src, 4, dims, str, box, nullptr);
+    if (rc) return rc;
+  }
+  const int bn = d->cin > 64 ? 128 : 64;
+  const int co_tiles = (d->cout + 127) / 128, ci_tiles = (d->cin + bn - 1) / bn;
+  int splits = d->splits;
+  if (splits <= 0) {
+    const int base = co_tiles * ci_tiles * 3;
+    splits = base >= kNumSMs ? 1 : kNumSMs / base;
+    if (splits > kp.ntiles) splits = kp.ntiles;
+    if (splits < 1) splits = 1;
+  }
+  kp.tiles_per_split = (kp.ntiles + splits - 1) / splits;
+  splits = (kp.ntiles + kp.tiles_per_split - 1) / kp.tiles_per_split;
+  dim3 grid(co_tiles, ci_tiles * 3, splits);
+  if (bn == 128) return launch_wgrad3<128, 5>(kp, grid, st);
+  return launch_wgrad3<64, 7>(kp, grid, st);
+}
+
 }  // namespace cdae
 
 extern "C" int cdae_wgrad(const cdae_wgrad_desc* d, cdae_stream s) {
@@ -594,6 +801,11 @@ extern "C" int cdae_wgrad(const cdae_wgrad_desc* d, cdae_stream s) {
   CDAE_CHECK_SHAPE(d->ksize == 1 || d->ksize == 3, "wgrad: ksize %d", d->ksize);
   CDAE_CHECK_SHAPE(d->in_stride == 1 || d->in_stride == 2, "wgrad: in_stride %d", d->in_stride);
   CDAE_CHECK_SHAPE(d->ldy % 8 == 0 && d->src_c % 8 == 0, "wgrad: pitches must be multiples of 8");
+  static const bool no_w3 = getenv("CDAE_WGRAD_V1") != nullptr;
+  // one-kernel-row kernel (N = 128 per tap): wins wherever the one-tap kernel cannot run its N = 256 tile
+  if (d->ksize == 3 && d->in_stride == 1 && d->H == d->OH && d->W == d->OW && !no_w3 && (d->cin % 256 != 0 || d->dbias))
+    return wgrad3(d, reinterpret_cast<cudaStream_t>(s));
+  CDAE_CHECK_SHAPE(!d->dbias, "wgrad: the fused bias gradient needs the 3x3 stride-1 kernel");
   WgradKParams kp;
   memset(&kp, 0, sizeof(kp));
   tile_geometry(64, d->OH, d->OW, &kp.bw, &kp.bh, &kp.bni);

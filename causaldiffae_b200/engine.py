@@ -346,7 +346,11 @@ class Engine:
         """gradients of out = conv(concat(srcs)): bias, weight, and data (into srcs[i].grad()). dy: bf16 NHWC tensor."""
         fns = []
         gb, gw = self._gparam(cw.bias), self._gparam(cw.param)
-        if cw.cout % 8 == 0:
+        # the bias gradient rides along in the one-kernel-row 3x3 weight-gradient kernel (used when Cin % 256 != 0)
+        fused_bias = ksize == 3 and stride == 1 and cw.cout % 8 == 0 and srcs[0].shape[3] % 256 != 0
+        if fused_bias:
+            pass
+        elif cw.cout % 8 == 0:
             fns.append(lambda: ops.colsum_(dy, gb, c=cw.cout))
         else:   # final eps conv: 3 real channels inside a 64-wide padded gradient
             tmp = pl.alloc((dy.shape[-1],), th.float32)
@@ -354,11 +358,11 @@ class Engine:
             fns.append(lambda: ops.colsum_(dy, tmp))
             fns.append(lambda: gb.add_(tmp[:cw.cout]))
         off = 0
-        for s in srcs:
+        for si, s in enumerate(srcs):
             c = s.shape[3]
             real = max(0, min(c, cw.cin - off))
             wd = ops.make_wgrad_desc(dy, s.t, gw, cw.cout, c, ksize=ksize, in_stride=stride, ci_off=off, cin_real=real,
-                                     dw_ld=cw.cin)
+                                     dw_ld=cw.cin, dbias=gb if (fused_bias and si == 0) else None)
             fns.append(lambda wd=wd: ops.wgrad(wd))
             off += c
         if need_dgrad:

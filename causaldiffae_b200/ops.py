@@ -247,7 +247,8 @@ def igemm(desc):
     check(_lib.lib().cdae_igemm(C.byref(desc), stream()))
 
 
-def make_wgrad_desc(dy, src, dw, cout, cin, ksize=3, in_stride=1, c0=0, ci_off=0, cin_real=None, dw_ld=None, splits=0):
+def make_wgrad_desc(dy, src, dw, cout, cin, ksize=3, in_stride=1, c0=0, ci_off=0, cin_real=None, dw_ld=None, splits=0,
+                    dbias=None):
     """dw (fp32 [cout, taps, dw_ld]) += dy^T * shifted(src).  dy: bf16 [N,OH,OW,ldy]; src: bf16 [N,H,W,C]."""
     _bf16c(dy); _bf16c(src)
     d = WgradDesc()
@@ -259,7 +260,8 @@ def make_wgrad_desc(dy, src, dw, cout, cin, ksize=3, in_stride=1, c0=0, ci_off=0
     d.dw = dw.data_ptr()
     d.dw_ld = dw_ld if dw_ld is not None else cin
     d.ci_off, d.cin_real, d.splits = ci_off, (cin_real if cin_real is not None else cin), splits
-    d._keep = (dy, src, dw)
+    d.dbias = ptr(dbias)
+    d._keep = (dy, src, dw, dbias)
     return d
 
 

@@ -131,6 +131,7 @@ typedef struct {
   float* dw; int32_t dw_ld;                /* fp32 dW[co][tap][dw_ld] ; columns start at ci_off */
   int32_t ci_off, cin_real;                /* only ci < cin_real written */
   int32_t splits;                          /* split-K factor over pixel tiles (0: auto) */
+  float* dbias;                            /* fp32 [cout] += column sums of dy (bias gradient); 3x3 stride-1 only, or NULL */
 } cdae_wgrad_desc;
 int cdae_wgrad(const cdae_wgrad_desc* d, cdae_stream s);
 

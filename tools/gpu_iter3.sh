@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_model_gpu.py -q -x --timeout=300 --timeout-method=thread 2>&1 | tail -8 | tee gpurun_out/iter_tests.log
+timeout 300 python tools/gpu_gn_bench.py 2>&1 | tee gpurun_out/gn_bench.log
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu 2>&1 | grep '^{' | tee gpurun_out/bench_iter.log
