@@ -76,9 +76,186 @@ struct alignas(64) IgemmKParams {
   const float* bias;
   const float* bias2;
   int nboxes, ntn;   // number of 128-pixel boxes and of N tiles
+  // halo kernel (3x3 stride 1): K is walked source-chunk-major; each 64-channel chunk brings ONE halo tile per box
+  struct { int src, c0, nchunk, ntap, wk0; } hs[8];
+  int nhs, tap_stride, flip;
 };
 
 constexpr int kATileBytes = 128 * 128;  // 128 pixels x 64 bf16
+
+// Barrier addresses and buffers the epilogue roles need (identical in the tap-streaming and the halo kernel).
+struct EpiCtx {
+  uint32_t tmem_base, stg_base;
+  uint32_t tfull0, tempty0, sready0, sfree0;   // shared addresses of the first barrier of each kind (8 B apart)
+  int total_tiles, boxes_per_img;
+};
+
+// warps 2..5: tcgen05.ld -> +bias (+bias2) (+residual) -> bf16 -> 128B-swizzled smem slab -> TMA store.  Nothing here
+// waits on global memory: stores are asynchronous bulk copies, the residual slab is prefetched by the staging warp
+// into the very buffer the result is written to (added in place).
+template <int BN, int MT, int NS>
+__device__ __forceinline__ void igemm_epilogue(const IgemmKParams& p, const EpiCtx& cx, int warp, int lane) {
+  constexpr int SLABW = BN < 64 ? BN : 64;                    // channels per output slab
+  constexpr int kSlabStride = 128 * 128;                      // staging buffers are 16 KB apart (1024 B aligned)
+  constexpr uint32_t kAccCols = MT * BN;
+  const uint32_t tmem_base = cx.tmem_base, stg_base = cx.stg_base;
+  const int total_tiles = cx.total_tiles, boxes_per_img = cx.boxes_per_img;
+  auto tfull_bar = [&](int a) { return cx.tfull0 + 8u * a; };
+  auto tempty_bar = [&](int a) { return cx.tempty0 + 8u * a; };
+  auto sready_bar = [&](int b) { return cx.sready0 + 8u * b; };
+  auto sfree_bar = [&](int b) { return cx.sfree0 + 8u * b; };
+  // ---------------------------------------------------------------- epilogue (warps 2..5; TMEM lane quarter = warp % 4)
+  const int q = warp & 3;
+  const int r = q * 32 + lane;                     // pixel row inside a 128-pixel box
+  const bool elected = (threadIdx.x == 64);
+  const float* __restrict__ bias = p.bias;
+  const float* __restrict__ bias2 = p.bias2;
+  int it = 0, sidx = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    const int as = it & 1;
+    const uint32_t aph = (it >> 1) & 1;
+    const int tm = tile / p.ntn, n0 = (tile % p.ntn) * BN;
+    mbar_wait(tfull_bar(as), aph);
+    tc_fence_after();
+    if (p.out_mode == 0) {
+#pragma unroll 1
+      for (int m = 0; m < MT; ++m) {
+        const int box = tm * MT + m;
+        if (box >= p.nboxes) break;
+        const int w0 = (box % p.tilesW) * p.BW, h0 = ((box / p.tilesW) % p.tilesH) * p.BH;
+        const int nn0 = (box / boxes_per_img) * p.BNI;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += SLABW) {
+          const int co0 = n0 + c;
+          if (co0 >= p.cout) break;
+          const int buf = sidx % NS;
+          const uint32_t sph = (sidx / NS) & 1;
+          uint32_t acc[SLABW];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccCols + m * BN + c);
+          __syncwarp();
+          if (SLABW >= 32) {
+#pragma unroll
+            for (int h = 0; h < SLABW / 32; ++h) tmem_ld32(taddr + 32 * h, acc + 32 * h);
+          } else {
+            tmem_ld16(taddr, acc);
+          }
+          tmem_ld_wait();
+          mbar_wait(sready_bar(buf), sph);           // staging buffer drained (and residual slab landed)
+          const uint32_t row = stg_base + buf * kSlabStride + r * (SLABW * 2);
+#pragma unroll
+          for (int j = 0; j < SLABW / 8; ++j) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[j * 8 + e]);
+            if (co0 + j * 8 < p.cout) {
+              if (bias) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + co0 + j * 8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + co0 + j * 8 + 4));
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              }
+              if (bias2) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias2 + co0 + j * 8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias2 + co0 + j * 8 + 4));
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              }
+            }
+            // 16 B chunk j of row r sits at chunk (j ^ (r & 7)) under the 128B swizzle (SLABW == 64); narrower slabs
+            // are stored unswizzled (their tensor maps use SWIZZLE_NONE)
+            const uint32_t a = SLABW == 64 ? row + (uint32_t)((j ^ (r & 7)) << 4) : row + (uint32_t)(j << 4);
+            if (p.has_resid) {
+              float rv[8];
+              unpack8(lds8(a), rv);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] += rv[e];
+            }
+            sts8(a, pack8(v));
+          }
+          fence_proxy_async();
+          named_bar_sync(1, 128);
+          if (elected) {
+            tma_store_4d(&p.tmO, stg_base + buf * kSlabStride, co0, w0, h0, nn0);
+            bulk_commit();
+            bulk_wait_read<NS - 2>();                 // every store but the newest NS-2 has finished reading smem
+            if (sidx >= NS - 2) mbar_arrive(sfree_bar((sidx - (NS - 2)) % NS));
+          }
+          ++sidx;
+        }
+      }
+    } else {
+      // NCHW fp32 (final eps conv, a handful of channels): consecutive lanes are consecutive pixels -> coalesced
+      const int bw = r % p.BW, bh = (r / p.BW) % p.BH, bn = r / (p.BW * p.BH);
+      constexpr int CH = BN < 32 ? 16 : 32;
+      float* __restrict__ o = reinterpret_cast<float*>(p.out);
+#pragma unroll 1
+      for (int m = 0; m < MT; ++m) {
+        const int box = tm * MT + m;
+        const int n = (box / boxes_per_img) * p.BNI + bn;
+        const int oy = ((box / p.tilesW) % p.tilesH) * p.BH + bh, ox = (box % p.tilesW) * p.BW + bw;
+        const bool row_ok = (n < p.Nimg) && (oy < p.OHt) && (ox < p.OWt);
+#pragma unroll 1
+        for (int c = 0; c < BN; c += CH) {
+          uint32_t acc[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccCols + m * BN + c);
+          __syncwarp();
+          if (CH == 32) tmem_ld32(taddr, acc); else tmem_ld16(taddr, acc);
+          tmem_ld_wait();
+          const int co0 = n0 + c;
+          if (row_ok && co0 < p.cout) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+              const int co = co0 + j;
+              if (co < p.cout)
+                o[(((size_t)n * p.cout + co) * p.OH + oy) * p.OW + ox] = __uint_as_float(acc[j]) + (bias ? __ldg(bias + co) : 0.f);
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tempty_bar(as));
+  }
+  if (elected) bulk_wait_all();                      // smem must stay valid until the last store has read it
+}
+
+// staging-buffer manager (one thread): waits until a slab buffer has been drained by its TMA store, then either
+// TMA-loads the residual slab into it or just marks it ready.
+template <int BN, int MT, int NS>
+__device__ __forceinline__ void igemm_stage_manager(const IgemmKParams& p, const EpiCtx& cx, int lane) {
+  constexpr int SLABW = BN < 64 ? BN : 64;
+  constexpr int kSlabBytes = 128 * SLABW * 2;
+  constexpr int kSlabStride = 128 * 128;
+  const uint32_t stg_base = cx.stg_base;
+  const int total_tiles = cx.total_tiles, boxes_per_img = cx.boxes_per_img;
+  auto sready_bar = [&](int b) { return cx.sready0 + 8u * b; };
+  auto sfree_bar = [&](int b) { return cx.sfree0 + 8u * b; };
+  if (lane == 0 && p.out_mode == 0) {
+    int sidx = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int tm = tile / p.ntn, n0 = (tile % p.ntn) * BN;
+      for (int m = 0; m < MT; ++m) {
+        const int box = tm * MT + m;
+        if (box >= p.nboxes) break;
+        const int w0 = (box % p.tilesW) * p.BW, h0 = ((box / p.tilesW) % p.tilesH) * p.BH;
+        const int nn0 = (box / boxes_per_img) * p.BNI;
+        for (int c = 0; c < BN; c += SLABW) {
+          const int co0 = n0 + c;
+          if (co0 >= p.cout) break;
+          const int buf = sidx % NS;
+          const uint32_t sph = (sidx / NS) & 1;
+          mbar_wait(sfree_bar(buf), sph ^ 1);
+          if (p.has_resid) {
+            mbar_expect_tx(sready_bar(buf), kSlabBytes);
+            tma_load_4d(stg_base + buf * kSlabStride, &p.tmR, sready_bar(buf), co0, w0, h0, nn0);
+          } else {
+            mbar_arrive(sready_bar(buf));
+          }
+          ++sidx;
+        }
+      }
+    }
+  }
+}
 
 // One CTA per SM loops over output tiles of MT x 128 pixels by BN channels (persistent).  Warp roles (224 threads):
 //   warp 0    TMA producer: A (4-D NHWC boxes, zero fill = conv padding) and B (weights) into a STAGES-deep smem ring
@@ -135,6 +312,7 @@ __global__ void __launch_bounds__(224, 1) igemm2_kernel(const __grid_constant__ 
   const int tiles_m = (p.nboxes + MT - 1) / MT;
   const int total_tiles = tiles_m * p.ntn;
   const int boxes_per_img = p.tilesW * p.tilesH;
+  const EpiCtx cx{tmem_base, stg_base, tfull_bar(0), tempty_bar(0), sready_bar(0), sfree_bar(0), total_tiles, boxes_per_img};
 
   if (warp == 0) {
     if (lane == 0) {
@@ -196,146 +374,9 @@ __global__ void __launch_bounds__(224, 1) igemm2_kernel(const __grid_constant__ 
       }
     }
   } else if (warp < 6) {
-    // ---------------------------------------------------------------- epilogue (warps 2..5; TMEM lane quarter = warp % 4)
-    const int q = warp & 3;
-    const int r = q * 32 + lane;                     // pixel row inside a 128-pixel box
-    const bool elected = (threadIdx.x == 64);
-    const float* __restrict__ bias = p.bias;
-    const float* __restrict__ bias2 = p.bias2;
-    int it = 0, sidx = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int as = it & 1;
-      const uint32_t aph = (it >> 1) & 1;
-      const int tm = tile / p.ntn, n0 = (tile % p.ntn) * BN;
-      mbar_wait(tfull_bar(as), aph);
-      tc_fence_after();
-      if (p.out_mode == 0) {
-#pragma unroll 1
-        for (int m = 0; m < MT; ++m) {
-          const int box = tm * MT + m;
-          if (box >= p.nboxes) break;
-          const int w0 = (box % p.tilesW) * p.BW, h0 = ((box / p.tilesW) % p.tilesH) * p.BH;
-          const int nn0 = (box / boxes_per_img) * p.BNI;
-#pragma unroll 1
-          for (int c = 0; c < BN; c += SLABW) {
-            const int co0 = n0 + c;
-            if (co0 >= p.cout) break;
-            const int buf = sidx % NS;
-            const uint32_t sph = (sidx / NS) & 1;
-            uint32_t acc[SLABW];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccCols + m * BN + c);
-            __syncwarp();
-            if (SLABW >= 32) {
-#pragma unroll
-              for (int h = 0; h < SLABW / 32; ++h) tmem_ld32(taddr + 32 * h, acc + 32 * h);
-            } else {
-              tmem_ld16(taddr, acc);
-            }
-            tmem_ld_wait();
-            mbar_wait(sready_bar(buf), sph);           // staging buffer drained (and residual slab landed)
-            const uint32_t row = stg_base + buf * kSlabStride + r * (SLABW * 2);
-#pragma unroll
-            for (int j = 0; j < SLABW / 8; ++j) {
-              float v[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[j * 8 + e]);
-              if (co0 + j * 8 < p.cout) {
-                if (bias) {
-                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + co0 + j * 8));
-                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + co0 + j * 8 + 4));
-                  v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                }
-                if (bias2) {
-                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias2 + co0 + j * 8));
-                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias2 + co0 + j * 8 + 4));
-                  v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                }
-              }
-              // 16 B chunk j of row r sits at chunk (j ^ (r & 7)) under the 128B swizzle (SLABW == 64); narrower slabs
-              // are stored unswizzled (their tensor maps use SWIZZLE_NONE)
-              const uint32_t a = SLABW == 64 ? row + (uint32_t)((j ^ (r & 7)) << 4) : row + (uint32_t)(j << 4);
-              if (p.has_resid) {
-                float rv[8];
-                unpack8(lds8(a), rv);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] += rv[e];
-              }
-              sts8(a, pack8(v));
-            }
-            fence_proxy_async();
-            named_bar_sync(1, 128);
-            if (elected) {
-              tma_store_4d(&p.tmO, stg_base + buf * kSlabStride, co0, w0, h0, nn0);
-              bulk_commit();
-              bulk_wait_read<NS - 2>();                 // every store but the newest NS-2 has finished reading smem
-              if (sidx >= NS - 2) mbar_arrive(sfree_bar((sidx - (NS - 2)) % NS));
-            }
-            ++sidx;
-          }
-        }
-      } else {
-        // NCHW fp32 (final eps conv, a handful of channels): consecutive lanes are consecutive pixels -> coalesced
-        const int bw = r % p.BW, bh = (r / p.BW) % p.BH, bn = r / (p.BW * p.BH);
-        constexpr int CH = BN < 32 ? 16 : 32;
-        float* __restrict__ o = reinterpret_cast<float*>(p.out);
-#pragma unroll 1
-        for (int m = 0; m < MT; ++m) {
-          const int box = tm * MT + m;
-          const int n = (box / boxes_per_img) * p.BNI + bn;
-          const int oy = ((box / p.tilesW) % p.tilesH) * p.BH + bh, ox = (box % p.tilesW) * p.BW + bw;
-          const bool row_ok = (n < p.Nimg) && (oy < p.OHt) && (ox < p.OWt);
-#pragma unroll 1
-          for (int c = 0; c < BN; c += CH) {
-            uint32_t acc[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccCols + m * BN + c);
-            __syncwarp();
-            if (CH == 32) tmem_ld32(taddr, acc); else tmem_ld16(taddr, acc);
-            tmem_ld_wait();
-            const int co0 = n0 + c;
-            if (row_ok && co0 < p.cout) {
-#pragma unroll
-              for (int j = 0; j < CH; ++j) {
-                const int co = co0 + j;
-                if (co < p.cout)
-                  o[(((size_t)n * p.cout + co) * p.OH + oy) * p.OW + ox] = __uint_as_float(acc[j]) + (bias ? __ldg(bias + co) : 0.f);
-              }
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
-    }
-    if (elected) bulk_wait_all();                      // smem must stay valid until the last store has read it
+    igemm_epilogue<BN, MT, NS>(p, cx, warp, lane);
   } else {
-    // ---------------------------------------------------------------- warp 6: staging buffers / residual prefetch
-    if (lane == 0 && p.out_mode == 0) {
-      int sidx = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int tm = tile / p.ntn, n0 = (tile % p.ntn) * BN;
-        for (int m = 0; m < MT; ++m) {
-          const int box = tm * MT + m;
-          if (box >= p.nboxes) break;
-          const int w0 = (box % p.tilesW) * p.BW, h0 = ((box / p.tilesW) % p.tilesH) * p.BH;
-          const int nn0 = (box / boxes_per_img) * p.BNI;
-          for (int c = 0; c < BN; c += SLABW) {
-            const int co0 = n0 + c;
-            if (co0 >= p.cout) break;
-            const int buf = sidx % NS;
-            const uint32_t sph = (sidx / NS) & 1;
-            mbar_wait(sfree_bar(buf), sph ^ 1);
-            if (p.has_resid) {
-              mbar_expect_tx(sready_bar(buf), kSlabBytes);
-              tma_load_4d(stg_base + buf * kSlabStride, &p.tmR, sready_bar(buf), co0, w0, h0, nn0);
-            } else {
-              mbar_arrive(sready_bar(buf));
-            }
-            ++sidx;
-          }
-        }
-      }
-    }
+    igemm_stage_manager<BN, MT, NS>(p, cx, lane);
   }
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
@@ -358,6 +399,239 @@ static int launch_igemm2(const IgemmKParams& kp, cudaStream_t st) {
   return CDAE_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ halo kernel (3x3, stride 1)
+// Same tile loop, TMEM double buffering and epilogue as igemm2_kernel, but the nine filter taps of a 64-channel chunk
+// read ONE halo tile per pixel box: box = 8 wide x 16 high output pixels, halo tile = 10 x 18 input pixels x 64 channels
+// (180 rows of 128 B, 128B-swizzled by TMA; out-of-image rows are zero filled = the conv padding).  Tap (dh, dw) is the
+// K-major operand whose descriptor starts (1+dh)*10 + (1+dw) rows into the tile with 8-row groups 1280 B apart - the
+// swizzle is a pure function of the shared-memory address, so row-shifted windows need no re-layout (tools/exp_desc.cu).
+// Shared-memory fill traffic for A falls 6.4x (180 instead of 9 x 128 rows per chunk), which is what bounds the
+// tap-streaming kernel (operand reads + TMA fills > 128 B/clk/SM).  A and B tiles run in separate rings with their own
+// producer warps: an A stage lives for nine B stages.
+//   warp 0 A producer | warp 1 MMA | warps 2-5 epilogue | warp 6 staging manager | warp 7 B producer
+constexpr int kHaloRows = 180;
+constexpr int kHaloBytes = kHaloRows * 128;            // 23040
+constexpr int kHaloStride = 23 * 1024;                 // tiles 1024 B aligned
+
+__device__ __forceinline__ uint64_t smem_desc_kmajor_sw128_sbo(uint32_t saddr, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int BN, int MT, int AST, int BST, int NS>
+__global__ void __launch_bounds__(256, 1) igemm3_kernel(const __grid_constant__ IgemmKParams p) {
+  constexpr int kBTileBytes = BN * 128;
+  constexpr int kAStage = MT * kHaloStride;
+  constexpr int kSlabStride = 128 * 128;
+  constexpr uint32_t kAccCols = MT * BN;
+  constexpr uint32_t kTmemCols = 2 * kAccCols <= 32 ? 32 : 2 * kAccCols <= 64 ? 64 : 2 * kAccCols <= 128 ? 128
+                                 : 2 * kAccCols <= 256 ? 256 : 512;
+  static_assert(2 * kAccCols <= 512, "accumulators exceed TMEM");
+  constexpr uint32_t kIdesc = make_idesc_bf16(128, BN, 0, 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* bsm = smem + AST * kAStage;
+  uint8_t* stg = bsm + BST * kBTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + NS * kSlabStride);
+  // bars: afull[AST] aempty[AST] bfull[BST] bempty[BST] tfull[2] tempty[2] sready[NS] sfree[NS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * AST + 2 * BST + 4 + 2 * NS);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_base = smem_u32(smem), b_base = smem_u32(bsm), stg_base = smem_u32(stg);
+  const uint32_t bar_base = smem_u32(bars);
+  auto afull = [&](int s) { return bar_base + 8u * s; };
+  auto aempty = [&](int s) { return bar_base + 8u * (AST + s); };
+  auto bfull = [&](int s) { return bar_base + 8u * (2 * AST + s); };
+  auto bempty = [&](int s) { return bar_base + 8u * (2 * AST + BST + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * AST + 2 * BST + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * AST + 2 * BST + 2 + a); };
+  auto sready_bar = [&](int b) { return bar_base + 8u * (2 * AST + 2 * BST + 4 + b); };
+  auto sfree_bar = [&](int b) { return bar_base + 8u * (2 * AST + 2 * BST + 4 + NS + b); };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < AST; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
+    for (int s = 0; s < BST; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int b = 0; b < NS; ++b) { mbar_init(sready_bar(b), 1); mbar_init(sfree_bar(b), 1); }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_m = (p.nboxes + MT - 1) / MT;
+  const int total_tiles = tiles_m * p.ntn;
+  const int boxes_per_img = p.tilesW * p.tilesH;
+  const EpiCtx cx{tmem_base, stg_base, tfull_bar(0), tempty_bar(0), sready_bar(0), sfree_bar(0), total_tiles, boxes_per_img};
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int ca = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int tm = tile / p.ntn;
+        int cw[MT], chh[MT], cn[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          const int box = tm * MT + m;
+          cw[m] = (box % p.tilesW) * 8 - 1;
+          chh[m] = ((box / p.tilesW) % p.tilesH) * 16 - 1;
+          cn[m] = box / boxes_per_img;                    // boxes past the end land beyond N: TMA zero-fills them
+        }
+        for (int h = 0; h < p.nhs; ++h) {
+          const CUtensorMap* tma = &p.tmA[p.hs[h].src];
+          const int c0 = p.hs[h].c0, nch = p.hs[h].nchunk;
+          for (int j = 0; j < nch; ++j, ++ca) {
+            const int s = ca % AST;
+            const uint32_t ph = (ca / AST) & 1;
+            mbar_wait(aempty(s), ph ^ 1);
+            mbar_expect_tx(afull(s), MT * kHaloBytes);
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+              tma_load_4d(a_base + s * kAStage + m * kHaloStride, tma, afull(s), c0 + j * 64, cw[m], chh[m], cn[m]);
+          }
+        }
+      }
+    }
+  } else if (warp == 7) {
+    if (lane == 0) {
+      int cb = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.ntn) * BN;
+        for (int h = 0; h < p.nhs; ++h) {
+          const int nch = p.hs[h].nchunk, ntap = p.hs[h].ntap, wk0 = p.hs[h].wk0;
+          for (int j = 0; j < nch; ++j) {
+            for (int t = 0; t < ntap; ++t, ++cb) {
+              const int s = cb % BST;
+              const uint32_t ph = (cb / BST) & 1;
+              mbar_wait(bempty(s), ph ^ 1);
+              mbar_expect_tx(bfull(s), kBTileBytes);
+              tma_load_2d(b_base + s * kBTileBytes, &p.tmB, bfull(s), wk0 + t * p.tap_stride + j * 64, n0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    int ca = 0, cb = 0, it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(tempty_bar(as), aph ^ 1);          // epilogue has drained this accumulator set
+      tc_fence_after();
+      uint32_t first = 1;
+      for (int h = 0; h < p.nhs; ++h) {
+        const int nch = p.hs[h].nchunk, ntap = p.hs[h].ntap;
+        for (int j = 0; j < nch; ++j, ++ca) {
+          const int sa = ca % AST;
+          mbar_wait(afull(sa), (ca / AST) & 1);
+          for (int t = 0; t < ntap; ++t, ++cb) {
+            // tap index -> window origin inside the halo tile (flip: data-gradient taps are negated)
+            const int ti = ntap == 9 ? (p.flip ? 8 - t : t) : 4;
+            const uint32_t row0 = (uint32_t)((ti / 3) * 10 + (ti % 3));
+            const int sb = cb % BST;
+            mbar_wait(bfull(sb), (cb / BST) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+              const uint64_t bdesc = smem_desc_kmajor_sw128(b_base + sb * kBTileBytes);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+                  const uint64_t adesc = smem_desc_kmajor_sw128_sbo(a_base + sa * kAStage + m * kHaloStride + row0 * 128, 1280);
+                  umma_f16(tmem_base + (uint32_t)(as * kAccCols + m * BN), adesc + 2 * k, bdesc + 2 * k, kIdesc,
+                           (first && k == 0) ? 0u : 1u);
+                }
+              }
+              umma_commit(bempty(sb));
+            }
+            first = 0;
+            __syncwarp();
+          }
+          if (lane == 0) umma_commit(aempty(sa));
+          __syncwarp();
+        }
+      }
+      if (lane == 0) umma_commit(tfull_bar(as));
+      __syncwarp();
+    }
+  } else if (warp < 6) {
+    igemm_epilogue<BN, MT, NS>(p, cx, warp, lane);
+  } else {
+    igemm_stage_manager<BN, MT, NS>(p, cx, lane);
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+}
+
+template <int BN, int MT, int AST, int BST, int NS>
+static int launch_igemm3(const IgemmKParams& kp, cudaStream_t st) {
+  constexpr int smem = AST * MT * kHaloStride + BST * BN * 128 + NS * 128 * 128 + 1024 + 512;
+  static_assert(smem <= 227 * 1024, "igemm3: shared memory budget");
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(igemm3_kernel<BN, MT, AST, BST, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  });
+  if (attr_err != cudaSuccess) { set_error("igemm3 smem attribute: %s", cudaGetErrorString(attr_err)); return CDAE_ERR_CUDA; }
+  const int total = ((kp.nboxes + MT - 1) / MT) * kp.ntn;
+  const int grid = total < kNumSMs ? total : kNumSMs;
+  igemm3_kernel<BN, MT, AST, BST, NS><<<grid, 256, smem, st>>>(kp);
+  CDAE_CHECK_LAUNCH("igemm3_kernel");
+  return CDAE_OK;
+}
+
+// Does the segment list describe "3x3 stride-1 conv over some sources (+ optional 1x1 taps over others)" in the packing
+// the engine uses (weight column = wk0 + tap*stride + channel)?  Fills kp.hs / tap_stride / flip when it does.
+static bool halo_plan(const cdae_igemm_desc* d, IgemmKParams& kp) {
+  if (d->in_stride != 1 || d->H % 16 != 0 || d->W % 8 != 0) return false;
+  int stride = -1, flip = -1, nhs = 0;
+  bool any9 = false;
+  for (int s = 0; s < d->nsrc; ++s) {
+    const cdae_seg* first = nullptr; const cdae_seg* last = nullptr; const cdae_seg* center = nullptr;
+    int cnt = 0;
+    for (int i = 0; i < d->nseg; ++i) {
+      const cdae_seg& g = d->seg[i];
+      if (g.src != s) continue;
+      ++cnt;
+      if (g.dh == -1 && g.dw == -1) first = &g;
+      if (g.dh == 1 && g.dw == 1) last = &g;
+      if (g.dh == 0 && g.dw == 0) center = &g;
+    }
+    if (cnt == 0) continue;
+    if (nhs >= 8) return false;
+    if (cnt == 1) {
+      if (!center) return false;
+      kp.hs[nhs].src = s; kp.hs[nhs].c0 = center->c0; kp.hs[nhs].nchunk = center->nchunk; kp.hs[nhs].ntap = 1;
+      kp.hs[nhs].wk0 = center->wk;
+      ++nhs;
+      continue;
+    }
+    if (cnt != 9 || !first || !last || !center) return false;
+    const int fl = first->wk < last->wk ? 0 : 1;
+    const int wk0 = fl ? last->wk : first->wk;
+    const int diff = fl ? first->wk - last->wk : last->wk - first->wk;
+    if (diff % 8) return false;
+    const int st = diff / 8;
+    if ((stride >= 0 && st != stride) || (flip >= 0 && fl != flip)) return false;
+    stride = st; flip = fl;
+    for (int i = 0; i < d->nseg; ++i) {
+      const cdae_seg& g = d->seg[i];
+      if (g.src != s) continue;
+      if (g.dh < -1 || g.dh > 1 || g.dw < -1 || g.dw > 1) return false;
+      const int ti = fl ? (1 - g.dh) * 3 + (1 - g.dw) : (g.dh + 1) * 3 + (g.dw + 1);
+      if (g.wk != wk0 + ti * st || g.c0 != center->c0 || g.nchunk != center->nchunk) return false;
+    }
+    kp.hs[nhs].src = s; kp.hs[nhs].c0 = center->c0; kp.hs[nhs].nchunk = center->nchunk; kp.hs[nhs].ntap = 9;
+    kp.hs[nhs].wk0 = wk0;
+    ++nhs;
+    any9 = true;
+  }
+  if (!any9) return false;
+  kp.nhs = nhs; kp.tap_stride = stride; kp.flip = flip;
+  return true;
+}
+
 }  // namespace cdae
 
 using namespace cdae;
@@ -372,7 +646,10 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
   memset(&kp, 0, sizeof(kp));
   const int es = d->in_stride;
   const int OHt = (d->H + es - 1) / es, OWt = (d->W + es - 1) / es;
-  tile_geometry(128, OHt, OWt, &kp.BW, &kp.BH, &kp.BNI);
+  static const bool no_halo = getenv("CDAE_NO_HALO") != nullptr;
+  const bool halo = !no_halo && halo_plan(d, kp);
+  if (halo) { kp.BW = 8; kp.BH = 16; kp.BNI = 1; }
+  else tile_geometry(128, OHt, OWt, &kp.BW, &kp.BH, &kp.BNI);
   kp.tilesW = (OWt + kp.BW - 1) / kp.BW;
   kp.tilesH = (OHt + kp.BH - 1) / kp.BH;
   const int tilesN = (d->N + kp.BNI - 1) / kp.BNI;
@@ -390,6 +667,7 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
     uint64_t dims[4] = {C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
     uint64_t str[3] = {C * 2, C * 2 * d->W, C * 2 * (uint64_t)d->W * d->H};
     uint32_t box[4] = {64, (uint32_t)(kp.BW * es), (uint32_t)(kp.BH * es), (uint32_t)kp.BNI};
+    if (halo) { box[1] = 10; box[2] = 18; box[3] = 1; }     // 8x16 output pixels + one pixel of halo on every side
     uint32_t est[4] = {1, (uint32_t)es, (uint32_t)es, 1};
     int rc = make_tmap_bf16(&kp.tmA[i], d->src[i], 4, dims, str, box, est);
     if (rc) return rc;
@@ -439,6 +717,17 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
   }
   kp.nseg = d->nseg; kp.nkb = nkb; kp.nboxes = nboxes; kp.ntn = ntn;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
+  if (halo) {
+    switch (bn) {
+      case 16: return launch_igemm3<16, 2, 2, 8, 3>(kp, st);
+      case 32: return launch_igemm3<32, 2, 2, 8, 3>(kp, st);
+      case 64: return mt == 2 ? launch_igemm3<64, 2, 2, 8, 3>(kp, st) : launch_igemm3<64, 1, 3, 8, 3>(kp, st);
+      case 128: return mt == 2 ? launch_igemm3<128, 2, 2, 5, 3>(kp, st) : launch_igemm3<128, 1, 3, 6, 3>(kp, st);
+      case 192: return launch_igemm3<192, 1, 2, 5, 3>(kp, st);
+      case 256: return launch_igemm3<256, 1, 2, 4, 3>(kp, st);
+      default: set_error("igemm: unsupported bn %d", bn); return CDAE_ERR_SHAPE;
+    }
+  }
   switch (bn) {
     case 16: return launch_igemm2<16, 1, 8, 3>(kp, st);
     case 32: return launch_igemm2<32, 1, 8, 3>(kp, st);

@@ -213,6 +213,9 @@ def _conv_case(N, H, chans, cout, ksize=3, stride=1, bias=True, resid=False, see
     (2, 32, [128], 128, 3, 2, False),         # stride-2 (Downsample) via TMA element strides
     (2, 16, [192], 64, 1, 1, True),           # 1x1 skip conv, cout 64
     (1, 64, [64], 64, 3, 1, False),
+    (2, 48, [64, 128], 192, 3, 1, True),      # halo kernel: non-power-of-two image, concat, residual, N tile 192
+    (3, 24, [64], 64, 3, 1, False),           # 24 % 16 != 0: falls back to the tap-streaming kernel
+    (67, 16, [128], 128, 3, 1, True),         # many boxes, odd box count (MT = 2 tail)
 ])
 def test_igemm_conv_forward(N, H, chans, cout, ksize, stride, resid):
     err = _conv_case(N, H, chans, cout, ksize, stride, True, resid, seed=H + cout)

@@ -20,6 +20,8 @@ FWD = [
     (64, 16, [384], 384, 3, 1, True), (64, 8, [512], 512, 3, 1, True), (64, 8, [512, 512], 512, 3, 1, False),
     (64, 64, [128], 128, 1, 1, True), (64, 16, [384], 1152, 1, 1, False), (64, 16, [384], 384, 1, 1, True),
     (64, 8, [512], 512, 1, 1, True), (64, 64, [128], 128, 3, 2, False),
+    (64, 64, [256], 256, 3, 1, False, 128), (64, 32, [256], 256, 3, 1, True, 128), (64, 16, [384], 384, 3, 1, True, 128),
+    (64, 32, [384, 256], 256, 3, 1, False, 128), (64, 64, [128], 3, 3, 1, False),
 ]
 WG = [(64, 64, 128, 128, 3), (64, 32, 256, 256, 3), (64, 16, 384, 384, 3), (64, 8, 512, 512, 3), (64, 64, 256, 128, 3),
       (64, 64, 128, 128, 1), (64, 16, 384, 384, 1)]
@@ -42,23 +44,26 @@ def main():
     only = sys.argv[1] if len(sys.argv) > 1 else ""
     g = torch.Generator(device=dev).manual_seed(0)
     if only in ("", "fwd"):
-        for (N, H, chans, cout, ks, st, resid) in FWD:
+        for case in FWD:
+            (N, H, chans, cout, ks, st, resid), bn = case[:7], (case[7] if len(case) > 7 else 0)
             cin = sum(chans)
             OH = H // st
-            w = (torch.randn(cout, ks * ks * cin, device=dev, generator=g) * 0.02).to(bf16)
+            w = (torch.randn(max(cout, 16), ks * ks * cin, device=dev, generator=g) * 0.02).to(bf16)
             bias = torch.randn(cout, device=dev, generator=g)
             fns = []
             for _ in range(3):
                 xs = [torch.randn(N, H, H, c, device=dev, generator=g).to(bf16) for c in chans]
-                out = torch.empty(N, OH, OH, cout, device=dev, dtype=bf16)
+                mode1 = cout < 8
+                out = torch.empty(N, cout, OH, OH, device=dev) if mode1 else torch.empty(N, OH, OH, cout, device=dev, dtype=bf16)
                 r = torch.randn(N, OH, OH, cout, device=dev, generator=g).to(bf16) if resid else None
                 segs, K = ops.conv_segments(chans, ks)
-                d = ops.make_igemm_desc(xs, segs, w, out, cout, in_stride=st, bias=bias, resid=r)
+                d = ops.make_igemm_desc(xs, segs, w, out, cout, in_stride=st, bias=bias, resid=r, bn=bn,
+                                        out_mode=1 if mode1 else 0)
                 fns.append(lambda d=d: ops.igemm(d))
             ms = timeit(fns)
             fl = 2.0 * N * OH * OH * cout * ks * ks * cin
             byts = 2.0 * N * (H * H * cin + OH * OH * cout * (2 if resid else 1))
-            print(f"igemm N{N} {H}x{H} cin{chans} cout{cout} k{ks} s{st} resid{int(resid)}: {ms*1e3:8.1f} us "
+            print(f"igemm N{N} {H}x{H} cin{chans} cout{cout} k{ks} s{st} resid{int(resid)} bn{bn}: {ms*1e3:8.1f} us "
                   f"{fl/ms/1e9:7.1f} TF/s ({fl/ms/1e9/PEAK:5.1%} of measured peak)  {byts/ms/1e6:6.0f} GB/s algorithmic", flush=True)
     if only in ("", "wgrad"):
         for (N, H, cin, cout, ks) in WG:
