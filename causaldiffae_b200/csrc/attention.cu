@@ -3,16 +3,21 @@
 // that keep S/P on chip (flash-style, online softmax, recompute in the backward).
 //
 // Sequence lengths are tiny (T = H*W <= 1024 at the attention resolutions) and attention is < 1 % of the UNet FLOPs,
-// so this kernel uses warp-level tensor-core MMAs (mma.sync m16n8k16 bf16, fp32 accumulate) with the whole K/V block
-// staged in shared memory; the tcgen05 budget goes to the convolutions (igemm.cu).
+// so these kernels use warp-level tensor-core MMAs (mma.sync m16n8k16 bf16, fp32 accumulate); the tcgen05 budget goes
+// to the convolutions (igemm.cu).  What makes them fast is the data path:
+//   * every operand tile is copied global -> shared memory ONCE, row-major, by cp.async (16 B, zero fill past T) into a
+//     two-stage ring, so the next 64-row block streams in while the current one is multiplied;
+//   * fragments come out of shared memory with ldmatrix (x4): the "transposed" operands (V in P.V, K in dS.K, Q / dO in
+//     the dK / dV products) use ldmatrix.trans on the same row-major tile - no transposed copies exist;
+//   * rows are padded by 16 B, which makes all eight 16 B row segments of an ldmatrix phase hit distinct banks.
 // Layout: qkv [B, T, 3*C] bf16 with head h at channels [h*3*ch, (h+1)*3*ch) = [q | k | v]; out [B, T, C] (head h at h*ch).
 #include "common.cuh"
 
 namespace cdae {
 
-constexpr int kBQ = 64;   // queries per CTA (4 warps x 16)
-constexpr int kBK = 64;   // keys per inner block
-constexpr int kPadT = 8;
+constexpr int kBK = 64;   // rows of a streamed tile (keys in fwd / dq, queries in dkv)
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
 
 __device__ __forceinline__ void mma_bf16(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -24,64 +29,98 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ uint32_t lds32(const __nv_bfloat16* p) { return *reinterpret_cast<const uint32_t*>(p); }
+__device__ __forceinline__ float2 unpack_bf16(uint32_t r) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r));
+}
+__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldsm4(uint32_t* r, uint32_t a) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm4t(uint32_t* r, uint32_t a) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void cp16z(uint32_t dst, const void* src, bool ok) {
+  const int n = ok ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp4z(uint32_t dst, const void* src, bool ok) {
+  const int n = ok ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// copy a [rows x CH] tile (row pitch ld in global) into smem row-major with pitch CH+8; rows >= valid are zero
-template <int CH>
-__device__ __forceinline__ void load_tile(__nv_bfloat16* dst, const __nv_bfloat16* src, int ld, int valid, int tid, int nthr) {
-  constexpr int V = CH / 8;
-  for (int i = tid; i < kBK * V; i += nthr) {
-    const int r = i / V, v = i % V;
-    bf16x8 x;
-    if (r < valid) x = ld8(src + (size_t)r * ld + v * 8);
-    else { float z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; x = pack8(z); }
-    st8(dst + r * (CH + 8) + v * 8, x);
+// rows [row0, row0+nrows) x CH channels of a [T, ld] matrix -> shared tile with a (CH+8)-element pitch; rows >= T are zero
+template <int CH, int NT>
+__device__ __forceinline__ void tile_async(uint32_t dst, const __nv_bfloat16* src, int ld, int row0, int nrows, int T, int tid) {
+  constexpr int V = CH / 8, P = (CH + 8) * 2;
+  for (int i = tid; i < nrows * V; i += NT) {
+    const int r = i / V, v = i - r * V;
+    const bool ok = row0 + r < T;
+    cp16z(dst + r * P + v * 16, src + (size_t)(ok ? row0 + r : 0) * ld + v * 8, ok);
   }
 }
-// same tile, stored transposed: dst[c][r] with pitch kBK + 8
+
+// Fragment addresses inside a tile with byte pitch P (lane-dependent parts precomputed by the callers where it pays).
+// A operand (16 rows from r0, k chunk kk): regs = {rows 0-7 | k lo, rows 8-15 | k lo, rows 0-7 | k hi, rows 8-15 | k hi}
+template <int P>
+__device__ __forceinline__ uint32_t a_frag_addr(uint32_t base, int r0, int kk, int lane) {
+  return base + (r0 + (lane & 7) + ((lane >> 3) & 1) * 8) * P + (kk * 16 + (lane >> 4) * 8) * 2;
+}
+// B operand from a tile stored [n][k] (non-transposed ldmatrix): n tiles (nt, nt+1), k chunk kk -> {b0,b1 | nt, b0,b1 | nt+1}
+template <int P>
+__device__ __forceinline__ uint32_t b_frag_addr(uint32_t base, int nt, int kk, int lane) {
+  return base + ((nt + (lane >> 4)) * 8 + (lane & 7)) * P + (kk * 16 + ((lane >> 3) & 1) * 8) * 2;
+}
+// B operand from a tile stored [k][n] (ldmatrix.trans): k chunk kk (16 rows), n tiles (nt, nt+1) -> {b0,b1 | nt, b0,b1 | nt+1}
+template <int P>
+__device__ __forceinline__ uint32_t bt_frag_addr(uint32_t base, int nt, int kk, int lane) {
+  return base + (kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * P + ((nt + (lane >> 4)) * 8) * 2;
+}
+
+// c[8][4] (16 x 64) = A(16 x CH, rows r0.. of tile `at`) * B^T where tile `bt` is [64][CH]
 template <int CH>
-__device__ __forceinline__ void load_tile_t(__nv_bfloat16* dst, const __nv_bfloat16* src, int ld, int valid, int tid, int nthr) {
-  constexpr int V = CH / 8;
-  for (int i = tid; i < kBK * V; i += nthr) {
-    const int r = i % kBK, v = i / kBK;
-    __nv_bfloat16 e[8];
-    if (r < valid) *reinterpret_cast<bf16x8*>(e) = ld8(src + (size_t)r * ld + v * 8);
-    else { for (int k = 0; k < 8; ++k) e[k] = __float2bfloat16(0.f); }
+__device__ __forceinline__ void gemm_16x64(float (*c)[4], uint32_t at, int r0, uint32_t bt, int lane) {
+  constexpr int P = (CH + 8) * 2;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) dst[(v * 8 + k) * (kBK + kPadT) + r] = e[k];
-  }
-}
-
-// A fragments (16 rows x CH) straight from global memory (rows beyond `valid` read as zero)
-template <int CH>
-__device__ __forceinline__ void load_a_frags(uint32_t (*a)[4], const __nv_bfloat16* base, int ld, int row0, int valid, int lane) {
-  const int g = lane >> 2, t = lane & 3;
+  for (int nt = 0; nt < 8; ++nt) c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
 #pragma unroll
   for (int kk = 0; kk < CH / 16; ++kk) {
-    const int r0 = row0 + g, r1 = row0 + g + 8, c = kk * 16 + t * 2;
-    a[kk][0] = r0 < valid ? lds32(base + (size_t)r0 * ld + c) : 0u;
-    a[kk][1] = r1 < valid ? lds32(base + (size_t)r1 * ld + c) : 0u;
-    a[kk][2] = r0 < valid ? lds32(base + (size_t)r0 * ld + c + 8) : 0u;
-    a[kk][3] = r1 < valid ? lds32(base + (size_t)r1 * ld + c + 8) : 0u;
+    uint32_t a[4];
+    ldsm4(a, a_frag_addr<P>(at, r0, kk, lane));
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b[4];
+      ldsm4(b, b_frag_addr<P>(bt, 2 * np, kk, lane));
+      mma_bf16(c[2 * np], a, b[0], b[1]);
+      mma_bf16(c[2 * np + 1], a, b[2], b[3]);
+    }
   }
 }
-
-// C[16 x 64] = A[16 x CH] * Bt where Bsm is [64 rows(n)][CH (k)] row-major (pitch CH+8)
+// same with the A fragments already in registers
 template <int CH>
-__device__ __forceinline__ void gemm_a_bT(float (*c)[4], const uint32_t (*a)[4], const __nv_bfloat16* Bsm, int lane) {
-  const int g = lane >> 2, t = lane & 3;
+__device__ __forceinline__ void gemm_16x64_reg(float (*c)[4], const uint32_t (*a)[4], uint32_t bt, int lane) {
+  constexpr int P = (CH + 8) * 2;
 #pragma unroll
-  for (int nt = 0; nt < kBK / 8; ++nt) {
-    c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
-    const __nv_bfloat16* brow = Bsm + (nt * 8 + g) * (CH + 8) + t * 2;
+  for (int nt = 0; nt < 8; ++nt) c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
 #pragma unroll
-    for (int kk = 0; kk < CH / 16; ++kk) mma_bf16(c[nt], a[kk], lds32(brow + kk * 16), lds32(brow + kk * 16 + 8));
+  for (int kk = 0; kk < CH / 16; ++kk) {
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b[4];
+      ldsm4(b, b_frag_addr<P>(bt, 2 * np, kk, lane));
+      mma_bf16(c[2 * np], a[kk], b[0], b[1]);
+      mma_bf16(c[2 * np + 1], a[kk], b[2], b[3]);
+    }
   }
 }
-// acc[16 x CH] += P[16 x 64] * B where Btsm is the transposed tile [CH (n)][64 (k)] (pitch 64+8); P given as C-layout regs
+// acc[CH/8][4] (16 x CH) += P(16 x 64, accumulator-layout registers) * B where tile `bt` is [64 (k)][CH (n)]
 template <int CH>
-__device__ __forceinline__ void gemm_p_b(float (*acc)[4], const float (*p)[4], const __nv_bfloat16* Btsm, int lane) {
-  const int g = lane >> 2, t = lane & 3;
+__device__ __forceinline__ void gemm_p_tile(float (*acc)[4], const float (*p)[4], uint32_t bt, int lane) {
+  constexpr int P = (CH + 8) * 2;
 #pragma unroll
   for (int kk = 0; kk < kBK / 16; ++kk) {
     uint32_t a[4];
@@ -90,73 +129,100 @@ __device__ __forceinline__ void gemm_p_b(float (*acc)[4], const float (*p)[4], c
     a[2] = pack_bf16(p[2 * kk + 1][0], p[2 * kk + 1][1]);
     a[3] = pack_bf16(p[2 * kk + 1][2], p[2 * kk + 1][3]);
 #pragma unroll
-    for (int nt = 0; nt < CH / 8; ++nt) {
-      const __nv_bfloat16* brow = Btsm + (nt * 8 + g) * (kBK + kPadT) + kk * 16 + t * 2;
-      mma_bf16(acc[nt], a, lds32(brow), lds32(brow + 8));
+    for (int np = 0; np < CH / 16; ++np) {
+      uint32_t b[4];
+      ldsm4t(b, bt_frag_addr<P>(bt, 2 * np, kk, lane));
+      mma_bf16(acc[2 * np], a, b[0], b[1]);
+      mma_bf16(acc[2 * np + 1], a, b[2], b[3]);
     }
   }
 }
 
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
 // ---------------------------------------------------------------- forward
-template <int CH>
-__global__ void __launch_bounds__(128) attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                                                       float* __restrict__ lse, int T, int heads, float scale2) {
+// CTA = NW warps x 16 queries of one (batch, head); K/V stream through a two-stage ring in blocks of 64 keys.
+// smem: stage s = { K[64][CH+8], V[64][CH+8] } x 2; the Q tile is staged through the same bytes before the loop starts.
+template <int CH, int NW>
+__global__ void __launch_bounds__(NW * 32) attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                                                           float* __restrict__ lse, int T, int heads, float sl2) {
+  constexpr int P = (CH + 8) * 2, NT = NW * 32, BQ = NW * 16, kTile = kBK * P;
+  static_assert(BQ * P <= 4 * kTile, "Q staging must fit the K/V ring");
   extern __shared__ __align__(16) uint8_t smraw[];
-  __nv_bfloat16* Ksm = reinterpret_cast<__nv_bfloat16*>(smraw);          // [64][CH+8]
-  __nv_bfloat16* Vtsm = Ksm + kBK * (CH + 8);                            // [CH][64+8]
+  const uint32_t sm = smem_addr(smraw);
   const int bh = blockIdx.y, b = bh / heads, h = bh % heads;
   const int ld = 3 * CH * heads;
   const __nv_bfloat16* qb = qkv + (size_t)b * T * ld + (size_t)h * 3 * CH;
   const __nv_bfloat16* kb = qb + CH;
   const __nv_bfloat16* vb = qb + 2 * CH;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int q0 = blockIdx.x * kBQ + warp * 16;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int q0 = blockIdx.x * BQ;
 
+  tile_async<CH, NT>(sm, qb, ld, q0, BQ, T, tid);
+  cp_commit(); cp_wait_all();
+  __syncthreads();
   uint32_t qa[CH / 16][4];
-  load_a_frags<CH>(qa, qb, ld, q0, T, lane);
+#pragma unroll
+  for (int kk = 0; kk < CH / 16; ++kk) ldsm4(qa[kk], a_frag_addr<P>(sm, warp * 16, kk, lane));
+  __syncthreads();
+
   float o[CH / 8][4];
 #pragma unroll
   for (int i = 0; i < CH / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
-  for (int k0 = 0; k0 < T; k0 += kBK) {
-    const int valid = min(kBK, T - k0);
+  const int nkb = (T + kBK - 1) / kBK;
+  tile_async<CH, NT>(sm, kb, ld, 0, kBK, T, tid);
+  tile_async<CH, NT>(sm + kTile, vb, ld, 0, kBK, T, tid);
+  cp_commit();
+  for (int ib = 0; ib < nkb; ++ib) {
+    cp_wait_all();
     __syncthreads();
-    load_tile<CH>(Ksm, kb + (size_t)k0 * ld, ld, valid, threadIdx.x, blockDim.x);
-    load_tile_t<CH>(Vtsm, vb + (size_t)k0 * ld, ld, valid, threadIdx.x, blockDim.x);
-    __syncthreads();
-    float s[kBK / 8][4];
-    gemm_a_bT<CH>(s, qa, Ksm, lane);
+    if (ib + 1 < nkb) {
+      const uint32_t nx = sm + ((ib + 1) & 1) * 2 * kTile;
+      tile_async<CH, NT>(nx, kb, ld, (ib + 1) * kBK, kBK, T, tid);
+      tile_async<CH, NT>(nx + kTile, vb, ld, (ib + 1) * kBK, kBK, T, tid);
+      cp_commit();
+    }
+    const uint32_t ks = sm + (ib & 1) * 2 * kTile, vs = ks + kTile;
+    const int valid = min(kBK, T - ib * kBK);
+    float s[8][4];
+    gemm_16x64_reg<CH>(s, qa, ks, lane);
     float mx0 = m0, mx1 = m1;
 #pragma unroll
-    for (int nt = 0; nt < kBK / 8; ++nt) {
+    for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int col = nt * 8 + t * 2 + (e & 1);
-        s[nt][e] = col < valid ? s[nt][e] * scale2 : -INFINITY;
+        s[nt][e] = col < valid ? s[nt][e] * sl2 : -INFINITY;
       }
       mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
       mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
     }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    const float c0 = __expf(m0 - mx0), c1 = __expf(m1 - mx1);
+    mx0 = quad_max(mx0); mx1 = quad_max(mx1);
+    const float c0 = ex2(m0 - mx0), c1 = ex2(m1 - mx1);
     float r0 = 0.f, r1 = 0.f;
 #pragma unroll
-    for (int nt = 0; nt < kBK / 8; ++nt) {
-      s[nt][0] = __expf(s[nt][0] - mx0); s[nt][1] = __expf(s[nt][1] - mx0);
-      s[nt][2] = __expf(s[nt][2] - mx1); s[nt][3] = __expf(s[nt][3] - mx1);
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = ex2(s[nt][0] - mx0); s[nt][1] = ex2(s[nt][1] - mx0);
+      s[nt][2] = ex2(s[nt][2] - mx1); s[nt][3] = ex2(s[nt][3] - mx1);
       r0 += s[nt][0] + s[nt][1]; r1 += s[nt][2] + s[nt][3];
     }
-    r0 += __shfl_xor_sync(0xffffffffu, r0, 1); r0 += __shfl_xor_sync(0xffffffffu, r0, 2);
-    r1 += __shfl_xor_sync(0xffffffffu, r1, 1); r1 += __shfl_xor_sync(0xffffffffu, r1, 2);
+    r0 = quad_sum(r0); r1 = quad_sum(r1);
     l0 = l0 * c0 + r0; l1 = l1 * c1 + r1; m0 = mx0; m1 = mx1;
 #pragma unroll
     for (int i = 0; i < CH / 8; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
-    gemm_p_b<CH>(o, s, Vtsm, lane);
+    gemm_p_tile<CH>(o, s, vs, lane);
   }
   const float i0 = 1.f / l0, i1 = 1.f / l1;
-  const int r0 = q0 + g, r1 = q0 + g + 8;
+  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
   const int ldo = CH * heads;
   __nv_bfloat16* ob = out + (size_t)b * T * ldo + (size_t)h * CH;
 #pragma unroll
@@ -165,21 +231,23 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const __nv_bfloat16* __re
     if (r0 < T) *reinterpret_cast<uint32_t*>(ob + (size_t)r0 * ldo + c) = pack_bf16(o[i][0] * i0, o[i][1] * i0);
     if (r1 < T) *reinterpret_cast<uint32_t*>(ob + (size_t)r1 * ldo + c) = pack_bf16(o[i][2] * i1, o[i][3] * i1);
   }
-  if (lse && t == 0) {
-    if (r0 < T) lse[(size_t)bh * T + r0] = m0 + __logf(l0);
-    if (r1 < T) lse[(size_t)bh * T + r1] = m1 + __logf(l1);
+  if (lse && t == 0) {   // natural-log units (the kernels work in base 2 internally)
+    if (r0 < T) lse[(size_t)bh * T + r0] = (m0 + __log2f(l0)) * kLn2;
+    if (r1 < T) lse[(size_t)bh * T + r1] = (m1 + __log2f(l1)) * kLn2;
   }
 }
 
-// ---------------------------------------------------------------- backward, pass 1: dQ  (grid: query blocks)
-template <int CH>
-__global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
-                                                          const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
-                                                          __nv_bfloat16* __restrict__ dqkv, int T, int heads, float scale2) {
+// ---------------------------------------------------------------- backward, pass 1: dQ and D = rowsum(dO * O)
+// CTA = NW warps x 16 queries; the CTA's Q and dO tiles stay in shared memory, K/V stream through the ring.
+// smem: Q[BQ][CH+8] | dO[BQ][CH+8] | stage { K[64][CH+8], V[64][CH+8] } x 2 (O is staged through the ring first)
+template <int CH, int NW>
+__global__ void __launch_bounds__(NW * 32) attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
+                                                              const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
+                                                              float* __restrict__ dsum, __nv_bfloat16* __restrict__ dqkv, int T,
+                                                              int heads, float scale2) {
+  constexpr int P = (CH + 8) * 2, NT = NW * 32, BQ = NW * 16, kTile = kBK * P;
   extern __shared__ __align__(16) uint8_t smraw[];
-  __nv_bfloat16* Ksm = reinterpret_cast<__nv_bfloat16*>(smraw);          // [64][CH+8]
-  __nv_bfloat16* Vsm = Ksm + kBK * (CH + 8);                             // [64][CH+8]
-  __nv_bfloat16* Ktsm = Vsm + kBK * (CH + 8);                            // [CH][64+8]
+  const uint32_t qs = smem_addr(smraw), dos = qs + BQ * P, ring = dos + BQ * P;
   const int bh = blockIdx.y, b = bh / heads, h = bh % heads;
   const int ld = 3 * CH * heads, ldo = CH * heads;
   const __nv_bfloat16* qb = qkv + (size_t)b * T * ld + (size_t)h * 3 * CH;
@@ -187,60 +255,69 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const __nv_bfloat16* _
   const __nv_bfloat16* vb = qb + 2 * CH;
   const __nv_bfloat16* ob = out + (size_t)b * T * ldo + (size_t)h * CH;
   const __nv_bfloat16* dob = dout + (size_t)b * T * ldo + (size_t)h * CH;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int q0 = blockIdx.x * kBQ + warp * 16;
-  const int r0 = q0 + g, r1 = q0 + g + 8;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int q0 = blockIdx.x * BQ;
+  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+  const float sl2 = scale2 * kLog2e;
 
-  uint32_t qa[CH / 16][4], da[CH / 16][4];
-  load_a_frags<CH>(qa, qb, ld, q0, T, lane);
-  load_a_frags<CH>(da, dob, ldo, q0, T, lane);
-  // D = rowsum(dO * O)
+  tile_async<CH, NT>(qs, qb, ld, q0, BQ, T, tid);
+  tile_async<CH, NT>(dos, dob, ldo, q0, BQ, T, tid);
+  tile_async<CH, NT>(ring, ob, ldo, q0, BQ, T, tid);
+  cp_commit(); cp_wait_all();
+  __syncthreads();
   float D0 = 0.f, D1 = 0.f;
 #pragma unroll
   for (int kk = 0; kk < CH / 16; ++kk) {
+    uint32_t a[4], d[4];
+    ldsm4(a, a_frag_addr<P>(ring, warp * 16, kk, lane));
+    ldsm4(d, a_frag_addr<P>(dos, warp * 16, kk, lane));
 #pragma unroll
-    for (int hlf = 0; hlf < 2; ++hlf) {
-      const int c = kk * 16 + t * 2 + hlf * 8;
-      if (r0 < T) {
-        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ob + (size_t)r0 * ldo + c));
-        const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dob + (size_t)r0 * ldo + c));
-        D0 += a.x * d.x + a.y * d.y;
-      }
-      if (r1 < T) {
-        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ob + (size_t)r1 * ldo + c));
-        const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dob + (size_t)r1 * ldo + c));
-        D1 += a.x * d.x + a.y * d.y;
-      }
+    for (int j = 0; j < 4; ++j) {
+      const float2 x = unpack_bf16(a[j]), y = unpack_bf16(d[j]);
+      const float v = x.x * y.x + x.y * y.y;
+      if (j & 1) D1 += v; else D0 += v;
     }
   }
-  D0 += __shfl_xor_sync(0xffffffffu, D0, 1); D0 += __shfl_xor_sync(0xffffffffu, D0, 2);
-  D1 += __shfl_xor_sync(0xffffffffu, D1, 1); D1 += __shfl_xor_sync(0xffffffffu, D1, 2);
-  const float L0 = r0 < T ? lse[(size_t)bh * T + r0] : 0.f, L1 = r1 < T ? lse[(size_t)bh * T + r1] : 0.f;
+  D0 = quad_sum(D0); D1 = quad_sum(D1);
+  if (t == 0) {
+    if (r0 < T) dsum[(size_t)bh * T + r0] = D0;
+    if (r1 < T) dsum[(size_t)bh * T + r1] = D1;
+  }
+  const float L0 = r0 < T ? lse[(size_t)bh * T + r0] * kLog2e : 0.f, L1 = r1 < T ? lse[(size_t)bh * T + r1] * kLog2e : 0.f;
+  __syncthreads();      // every warp has read its O rows: the ring may be overwritten
 
   float dq[CH / 8][4];
 #pragma unroll
   for (int i = 0; i < CH / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
-  for (int k0 = 0; k0 < T; k0 += kBK) {
-    const int valid = min(kBK, T - k0);
+  const int nkb = (T + kBK - 1) / kBK;
+  tile_async<CH, NT>(ring, kb, ld, 0, kBK, T, tid);
+  tile_async<CH, NT>(ring + kTile, vb, ld, 0, kBK, T, tid);
+  cp_commit();
+  for (int ib = 0; ib < nkb; ++ib) {
+    cp_wait_all();
     __syncthreads();
-    load_tile<CH>(Ksm, kb + (size_t)k0 * ld, ld, valid, threadIdx.x, blockDim.x);
-    load_tile<CH>(Vsm, vb + (size_t)k0 * ld, ld, valid, threadIdx.x, blockDim.x);
-    load_tile_t<CH>(Ktsm, kb + (size_t)k0 * ld, ld, valid, threadIdx.x, blockDim.x);
-    __syncthreads();
-    float s[kBK / 8][4], dp[kBK / 8][4];
-    gemm_a_bT<CH>(s, qa, Ksm, lane);
-    gemm_a_bT<CH>(dp, da, Vsm, lane);
+    if (ib + 1 < nkb) {
+      const uint32_t nx = ring + ((ib + 1) & 1) * 2 * kTile;
+      tile_async<CH, NT>(nx, kb, ld, (ib + 1) * kBK, kBK, T, tid);
+      tile_async<CH, NT>(nx + kTile, vb, ld, (ib + 1) * kBK, kBK, T, tid);
+      cp_commit();
+    }
+    const uint32_t ks = ring + (ib & 1) * 2 * kTile, vs = ks + kTile;
+    const int valid = min(kBK, T - ib * kBK);
+    float s[8][4], dp[8][4];
+    gemm_16x64<CH>(s, qs, warp * 16, ks, lane);
+    gemm_16x64<CH>(dp, dos, warp * 16, vs, lane);
 #pragma unroll
-    for (int nt = 0; nt < kBK / 8; ++nt) {
+    for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int col = nt * 8 + t * 2 + (e & 1);
         const float L = e < 2 ? L0 : L1, Dd = e < 2 ? D0 : D1;
-        const float p = col < valid ? __expf(s[nt][e] * scale2 - L) : 0.f;
+        const float p = col < valid ? ex2(fmaf(s[nt][e], sl2, -L)) : 0.f;
         s[nt][e] = p * (dp[nt][e] - Dd) * scale2;      // dS
       }
     }
-    gemm_p_b<CH>(dq, s, Ktsm, lane);
+    gemm_p_tile<CH>(dq, s, ks, lane);                  // dQ += dS K   (K tile is [k = key][n = ch])
   }
   __nv_bfloat16* dqb = dqkv + (size_t)b * T * ld + (size_t)h * 3 * CH;
 #pragma unroll
@@ -251,77 +328,78 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const __nv_bfloat16* _
   }
 }
 
-// ---------------------------------------------------------------- backward, pass 2: dK, dV  (grid: key blocks)
+// ---------------------------------------------------------------- backward, pass 2: dK, dV  (CTA = NW warps x 16 keys)
 // Works on the transposed problem: S^T = K Q^T so that P^T / dS^T come out in accumulator layout and feed the next MMA.
-template <int CH>
-__global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
-                                                           const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
-                                                           __nv_bfloat16* __restrict__ dqkv, int T, int heads, float scale2) {
+// smem: K[BKC][CH+8] | V[BKC][CH+8] | stage { Q[64][CH+8], dO[64][CH+8] } x 2 | L[2][64] | D[2][64]
+template <int CH, int NW>
+__global__ void __launch_bounds__(NW * 32) attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
+                                                               const float* __restrict__ lse, const float* __restrict__ dsum,
+                                                               __nv_bfloat16* __restrict__ dqkv, int T, int heads, float scale2) {
+  constexpr int P = (CH + 8) * 2, NT = NW * 32, BKC = NW * 16, kTile = kBK * P;
   extern __shared__ __align__(16) uint8_t smraw[];
-  __nv_bfloat16* Qsm = reinterpret_cast<__nv_bfloat16*>(smraw);          // [64 q][CH+8]
-  __nv_bfloat16* dOsm = Qsm + kBK * (CH + 8);                            // [64 q][CH+8]
-  __nv_bfloat16* Qtsm = dOsm + kBK * (CH + 8);                           // [CH][64+8]
-  __nv_bfloat16* dOtsm = Qtsm + CH * (kBK + kPadT);                      // [CH][64+8]
-  float* Lsm = reinterpret_cast<float*>(dOtsm + CH * (kBK + kPadT));     // [64]
-  float* Dsm = Lsm + kBK;                                                // [64]
+  const uint32_t ksm = smem_addr(smraw), vsm = ksm + BKC * P, ring = vsm + BKC * P;
+  float* LD = reinterpret_cast<float*>(smraw + 2 * BKC * P + 4 * kTile);     // [stage][L 64 | D 64]
+  const uint32_t ldsm = ring + 4 * kTile;
   const int bh = blockIdx.y, b = bh / heads, h = bh % heads;
   const int ld = 3 * CH * heads, ldo = CH * heads;
   const __nv_bfloat16* qb = qkv + (size_t)b * T * ld + (size_t)h * 3 * CH;
   const __nv_bfloat16* kb = qb + CH;
   const __nv_bfloat16* vb = qb + 2 * CH;
-  const __nv_bfloat16* ob = out + (size_t)b * T * ldo + (size_t)h * CH;
   const __nv_bfloat16* dob = dout + (size_t)b * T * ldo + (size_t)h * CH;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int kr0 = blockIdx.x * kBQ + warp * 16;     // this warp's 16 keys
-  const int r0 = kr0 + g, r1 = kr0 + g + 8;
+  const float* lrow = lse + (size_t)bh * T;
+  const float* drow = dsum + (size_t)bh * T;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int k0 = blockIdx.x * BKC;
+  const int r0 = k0 + warp * 16 + g, r1 = r0 + 8;
+  const float sl2 = scale2 * kLog2e;
 
-  uint32_t ka[CH / 16][4], va[CH / 16][4];
-  load_a_frags<CH>(ka, kb, ld, kr0, T, lane);
-  load_a_frags<CH>(va, vb, ld, kr0, T, lane);
+  auto load_stage = [&](int st, int qrow0) {
+    const uint32_t base = ring + st * 2 * kTile;
+    tile_async<CH, NT>(base, qb, ld, qrow0, kBK, T, tid);
+    tile_async<CH, NT>(base + kTile, dob, ldo, qrow0, kBK, T, tid);
+    if (tid < 2 * kBK) {
+      const int j = tid & (kBK - 1), q = qrow0 + j;
+      const bool ok = q < T;
+      const float* src = (tid < kBK ? lrow : drow) + (ok ? q : 0);
+      cp4z(ldsm + (st * 2 * kBK + tid) * 4, src, ok);
+    }
+  };
+  tile_async<CH, NT>(ksm, kb, ld, k0, BKC, T, tid);
+  tile_async<CH, NT>(vsm, vb, ld, k0, BKC, T, tid);
+  load_stage(0, 0);
+  cp_commit();
+
   float dk[CH / 8][4], dv[CH / 8][4];
 #pragma unroll
   for (int i = 0; i < CH / 8; ++i) { dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f; dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f; }
-
-  for (int q0 = 0; q0 < T; q0 += kBK) {
-    const int valid = min(kBK, T - q0);
+  const int nqb = (T + kBK - 1) / kBK;
+  for (int ib = 0; ib < nqb; ++ib) {
+    cp_wait_all();
     __syncthreads();
-    load_tile<CH>(Qsm, qb + (size_t)q0 * ld, ld, valid, threadIdx.x, blockDim.x);
-    load_tile<CH>(dOsm, dob + (size_t)q0 * ldo, ldo, valid, threadIdx.x, blockDim.x);
-    load_tile_t<CH>(Qtsm, qb + (size_t)q0 * ld, ld, valid, threadIdx.x, blockDim.x);
-    load_tile_t<CH>(dOtsm, dob + (size_t)q0 * ldo, ldo, valid, threadIdx.x, blockDim.x);
-    if (threadIdx.x < kBK) {
-      const int q = q0 + threadIdx.x;
-      float Dd = 0.f, L = 0.f;
-      if (q < T) {
-        L = lse[(size_t)bh * T + q];
-        for (int c = 0; c < CH; c += 8) {
-          float a[8], d[8];
-          unpack8(ld8(ob + (size_t)q * ldo + c), a);
-          unpack8(ld8(dob + (size_t)q * ldo + c), d);
+    if (ib + 1 < nqb) { load_stage((ib + 1) & 1, (ib + 1) * kBK); cp_commit(); }
+    const uint32_t qs = ring + (ib & 1) * 2 * kTile, dos = qs + kTile;
+    const float* Ls = LD + (ib & 1) * 2 * kBK;
+    const float* Ds = Ls + kBK;
+    const int valid = min(kBK, T - ib * kBK);
+    float st[8][4], dpt[8][4];
+    gemm_16x64<CH>(st, ksm, warp * 16, qs, lane);       // S^T  [16 keys x 64 q]
+    gemm_16x64<CH>(dpt, vsm, warp * 16, dos, lane);     // dP^T [16 keys x 64 q]
 #pragma unroll
-          for (int k = 0; k < 8; ++k) Dd += a[k] * d[k];
-        }
-      }
-      Lsm[threadIdx.x] = L; Dsm[threadIdx.x] = Dd;
-    }
-    __syncthreads();
-    float st[kBK / 8][4], dpt[kBK / 8][4];
-    gemm_a_bT<CH>(st, ka, Qsm, lane);      // S^T  [16 keys x 64 q]
-    gemm_a_bT<CH>(dpt, va, dOsm, lane);    // dP^T [16 keys x 64 q]
-    float pt[kBK / 8][4];
-#pragma unroll
-    for (int nt = 0; nt < kBK / 8; ++nt) {
+    for (int nt = 0; nt < 8; ++nt) {
+      const int cb = nt * 8 + t * 2;
+      const float2 Lc = *reinterpret_cast<const float2*>(Ls + cb), Dc = *reinterpret_cast<const float2*>(Ds + cb);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int col = nt * 8 + t * 2 + (e & 1);
+        const int col = cb + (e & 1);
         const int krow = e < 2 ? r0 : r1;
-        const float p = (col < valid && krow < T) ? __expf(st[nt][e] * scale2 - Lsm[col]) : 0.f;
-        pt[nt][e] = p;
-        st[nt][e] = p * (dpt[nt][e] - Dsm[col]) * scale2;   // dS^T
+        const float L = ((e & 1) ? Lc.y : Lc.x) * kLog2e, Dd = (e & 1) ? Dc.y : Dc.x;
+        const float p = (col < valid && krow < T) ? ex2(fmaf(st[nt][e], sl2, -L)) : 0.f;
+        st[nt][e] = p;
+        dpt[nt][e] = p * (dpt[nt][e] - Dd) * scale2;    // dS^T
       }
     }
-    gemm_p_b<CH>(dv, pt, dOtsm, lane);     // dV += P^T dO
-    gemm_p_b<CH>(dk, st, Qtsm, lane);      // dK += dS^T Q
+    gemm_p_tile<CH>(dv, st, dos, lane);      // dV += P^T dO    (dO tile is [k = q][n = ch])
+    gemm_p_tile<CH>(dk, dpt, qs, lane);      // dK += dS^T Q
   }
   __nv_bfloat16* dkb = dqkv + (size_t)b * T * ld + (size_t)h * 3 * CH + CH;
   __nv_bfloat16* dvb = dkb + CH;
@@ -339,34 +417,43 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const __nv_bfloat16* 
   }
 }
 
-template <int CH>
+template <typename K>
+static int set_smem(K kernel, size_t smem, const char* name) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("%s smem attribute (%zu B): %s", name, smem, cudaGetErrorString(e)); return CDAE_ERR_CUDA; }
+  return CDAE_OK;
+}
+
+template <int CH, int NW>
 static int attn_fwd_launch(const void* qkv, void* out, float* lse, int B, int T, int heads, cudaStream_t st) {
-  const size_t smem = sizeof(__nv_bfloat16) * (kBK * (CH + 8) + CH * (kBK + kPadT));
-  const float scale2 = 1.0f / sqrtf((float)CH);
-  dim3 grid((T + kBQ - 1) / kBQ, B * heads);
-  attn_fwd_kernel<CH><<<grid, 128, smem, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, lse, T, heads, scale2);
+  constexpr size_t smem = 4 * kBK * (CH + 8) * 2;
+  static int attr_rc = set_smem(attn_fwd_kernel<CH, NW>, smem, "attn_fwd_kernel");   // thread-safe one-time init
+  if (attr_rc) return attr_rc;
+  const float sl2 = kLog2e / sqrtf((float)CH);
+  dim3 grid((T + NW * 16 - 1) / (NW * 16), B * heads);
+  attn_fwd_kernel<CH, NW><<<grid, NW * 32, smem, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, lse, T, heads, sl2);
   CDAE_CHECK_LAUNCH("attn_fwd_kernel");
   return CDAE_OK;
 }
 
-template <int CH>
-static int attn_bwd_launch(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int T,
-                           int heads, cudaStream_t st) {
+template <int CH, int NW>
+static int attn_bwd_launch(const void* qkv, const void* out, const void* dout, const float* lse, float* dsum, void* dqkv,
+                           int B, int T, int heads, cudaStream_t st) {
   const float scale2 = 1.0f / sqrtf((float)CH);
-  dim3 grid((T + kBQ - 1) / kBQ, B * heads);
-  const size_t smem1 = sizeof(__nv_bfloat16) * (2 * kBK * (CH + 8) + CH * (kBK + kPadT));
-  const size_t smem2 = sizeof(__nv_bfloat16) * (2 * kBK * (CH + 8) + 2 * CH * (kBK + kPadT)) + sizeof(float) * 2 * kBK;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(attn_bwd_dq_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-    cudaFuncSetAttribute(attn_bwd_dkv_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-    attr_done = true;
-  }
-  attn_bwd_dq_kernel<CH><<<grid, 128, smem1, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)out,
-                                                    (const __nv_bfloat16*)dout, lse, (__nv_bfloat16*)dqkv, T, heads, scale2);
+  constexpr size_t smem1 = (2 * NW * 16 + 4 * kBK) * (CH + 8) * 2;
+  constexpr size_t smem2 = smem1 + 4 * kBK * sizeof(float);
+  static_assert(smem2 <= 227 * 1024, "attention backward: shared memory budget");
+  static int rc1 = set_smem(attn_bwd_dq_kernel<CH, NW>, smem1, "attn_bwd_dq_kernel");
+  static int rc2 = set_smem(attn_bwd_dkv_kernel<CH, NW>, smem2, "attn_bwd_dkv_kernel");
+  if (rc1) return rc1;
+  if (rc2) return rc2;
+  dim3 grid((T + NW * 16 - 1) / (NW * 16), B * heads);
+  attn_bwd_dq_kernel<CH, NW><<<grid, NW * 32, smem1, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)out,
+                                                           (const __nv_bfloat16*)dout, lse, dsum, (__nv_bfloat16*)dqkv, T,
+                                                           heads, scale2);
   CDAE_CHECK_LAUNCH("attn_bwd_dq_kernel");
-  attn_bwd_dkv_kernel<CH><<<grid, 128, smem2, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)out,
-                                                     (const __nv_bfloat16*)dout, lse, (__nv_bfloat16*)dqkv, T, heads, scale2);
+  attn_bwd_dkv_kernel<CH, NW><<<grid, NW * 32, smem2, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)dout, lse, dsum,
+                                                            (__nv_bfloat16*)dqkv, T, heads, scale2);
   CDAE_CHECK_LAUNCH("attn_bwd_dkv_kernel");
   return CDAE_OK;
 }
@@ -374,6 +461,7 @@ static int attn_bwd_launch(const void* qkv, const void* out, const void* dout, c
 }  // namespace cdae
 using namespace cdae;
 
+// 8 warps (128 rows) per CTA for long sequences, 4 warps (64 rows) when T <= 64 would leave half a CTA idle
 #define CDAE_ATTN_DISPATCH(CALL)                                                              \
   switch (ch) {                                                                               \
     case 16: return CALL(16); case 32: return CALL(32); case 48: return CALL(48);             \
@@ -386,16 +474,18 @@ using namespace cdae;
 extern "C" int cdae_attn_fwd(const void* qkv, void* out, float* lse, int B, int T, int heads, int ch, cdae_stream s) {
   CDAE_CHECK_ARG(qkv && out, "attn_fwd: null pointer");
   if (B == 0 || T == 0) return CDAE_OK;
-#define CALL(N) attn_fwd_launch<N>(qkv, out, lse, B, T, heads, (cudaStream_t)s)
+#define CALL(N) (T <= 64 ? attn_fwd_launch<N, 4>(qkv, out, lse, B, T, heads, (cudaStream_t)s) \
+                         : attn_fwd_launch<N, 8>(qkv, out, lse, B, T, heads, (cudaStream_t)s))
   CDAE_ATTN_DISPATCH(CALL)
 #undef CALL
 }
 
-extern "C" int cdae_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B,
-                             int T, int heads, int ch, cdae_stream s) {
-  CDAE_CHECK_ARG(qkv && out && dout && lse && dqkv, "attn_bwd: null pointer");
+extern "C" int cdae_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* dsum, void* dqkv,
+                             int B, int T, int heads, int ch, cdae_stream s) {
+  CDAE_CHECK_ARG(qkv && out && dout && lse && dsum && dqkv, "attn_bwd: null pointer");
   if (B == 0 || T == 0) return CDAE_OK;
-#define CALL(N) attn_bwd_launch<N>(qkv, out, dout, lse, dqkv, B, T, heads, (cudaStream_t)s)
+#define CALL(N) (T <= 64 ? attn_bwd_launch<N, 4>(qkv, out, dout, lse, dsum, dqkv, B, T, heads, (cudaStream_t)s) \
+                         : attn_bwd_launch<N, 8>(qkv, out, dout, lse, dsum, dqkv, B, T, heads, (cudaStream_t)s))
   CDAE_ATTN_DISPATCH(CALL)
 #undef CALL
 }

@@ -352,7 +352,29 @@ __device__ __forceinline__ float vec8_sum(float v) {
   return v;
 }
 
+// bf16 pair -> two fp32 (one shift, one mask)
+__device__ __forceinline__ void unpack2(uint32_t u, float& lo, float& hi) {
+  lo = __uint_as_float(u << 16); hi = __uint_as_float(u & 0xffff0000u);
+}
+__device__ __forceinline__ void unpack_u4(const uint4& v, float* f) {
+  unpack2(v.x, f[0], f[1]); unpack2(v.y, f[2], f[3]); unpack2(v.z, f[4], f[5]); unpack2(v.w, f[6], f[7]);
+}
+__device__ __forceinline__ uint4 pack_u4(const float* f) {
+  uint4 r;
+  __nv_bfloat162 h;
+  h = __floats2bfloat162_rn(f[0], f[1]); r.x = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(f[2], f[3]); r.y = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(f[4], f[5]); r.z = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(f[6], f[7]); r.w = *reinterpret_cast<uint32_t*>(&h);
+  return r;
+}
+
+// The inner loops are written for instruction count (the first version of these kernels was ISSUE bound: 21 / 42
+// thread instructions per element forward / backward, ncu r1): thread `tid` owns slab entries tid, tid + RN, ... (RN =
+// active threads), so every stream is a pointer that advances by a loop-invariant stride; SiLU is evaluated through
+// h = u/2: silu(u) = h + h*tanh(h) and silu'(u) = (1 + t + h*(1 - t^2))/2 with t = tanh(h) (one MUFU per element).
 // smem: bf16 slab[P][CC] | float chan[2][CC] | float gpart[2][32] | float gstat[2][32]
+template <bool SILU>
 __global__ void __launch_bounds__(kResThreads, 3) gn_fwd_res_kernel(const GnParams p) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int per = (p.HW + p.S - 1) / p.S;
@@ -369,13 +391,19 @@ __global__ void __launch_bounds__(kResThreads, 3) gn_fwd_res_kernel(const GnPara
   const int p0 = rank * per, p1 = min(p.HW, p0 + per);
   const int cpg = p.C / kGroups;
   const int ng = p.CC / cpg;                                   // groups in this chunk
+  const int RN = p.R * p.nvec;
+  const int nit = active ? max(0, (p1 - p0 - row + p.R - 1) / p.R) : 0;   // pixels owned by this thread
 
   const bool in0 = c < p.C0;
   const __nv_bfloat16* xbase = in0 ? p.x0 + (size_t)b * p.HW * p.C0 + c : p.x1 + (size_t)b * p.HW * p.C1 + (c - p.C0);
   const int xpitch = in0 ? p.C0 : p.C1;
-  if (active)
-    for (int pix = p0 + row; pix < p1; pix += p.R)
-      cp_async16(&slab[(size_t)(pix - p0) * p.nvec + vec], xbase + (size_t)pix * xpitch);
+  uint4* const sl = slab + threadIdx.x;
+  {
+    const __nv_bfloat16* g = xbase + (size_t)(p0 + row) * xpitch;
+    const size_t gstep = (size_t)p.R * xpitch;
+    uint4* s_ = sl;
+    for (int i = 0; i < nit; ++i) { cp_async16(s_, g); s_ += RN; g += gstep; }
+  }
   // per-channel affine constants do not depend on the statistics: fetch them while the slab is in flight
   float Gk[8], Hk[8];
 #pragma unroll
@@ -393,11 +421,13 @@ __global__ void __launch_bounds__(kResThreads, 3) gn_fwd_res_kernel(const GnPara
   float s[8], ss[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { s[k] = 0.f; ss[k] = 0.f; }
-  if (active) {
+  {
+    const uint4* s_ = sl;
 #pragma unroll 4
-    for (int pix = p0 + row; pix < p1; pix += p.R) {
+    for (int i = 0; i < nit; ++i) {
       float f[8];
-      vunpack<8>(slab[(size_t)(pix - p0) * p.nvec + vec], f);
+      unpack_u4(*s_, f);
+      s_ += RN;
 #pragma unroll
       for (int k = 0; k < 8; ++k) { s[k] += f[k]; ss[k] = fmaf(f[k], f[k], ss[k]); }
     }
@@ -440,24 +470,31 @@ __global__ void __launch_bounds__(kResThreads, 3) gn_fwd_res_kernel(const GnPara
   if (!active) return;
 
   float A[8], Bc[8];
+  const float half = SILU ? 0.5f : 1.f;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int g = (cl + k) / cpg;
     const float m = gstat[g], rs = gstat[kGroups + g];
-    A[k] = rs * Gk[k];
-    Bc[k] = Hk[k] - m * rs * Gk[k];
+    A[k] = half * rs * Gk[k];
+    Bc[k] = half * (Hk[k] - m * rs * Gk[k]);
   }
-  __nv_bfloat16* ybase = p.y + (size_t)b * p.HW * p.C + c;
+  {
+    __nv_bfloat16* y = p.y + (size_t)b * p.HW * p.C + c + (size_t)(p0 + row) * p.C;
+    const size_t ystep = (size_t)p.R * p.C;
+    const uint4* s_ = sl;
 #pragma unroll 2
-  for (int pix = p0 + row; pix < p1; pix += p.R) {
-    float f[8];
-    vunpack<8>(slab[(size_t)(pix - p0) * p.nvec + vec], f);
+    for (int i = 0; i < nit; ++i) {
+      float f[8];
+      unpack_u4(*s_, f);
+      s_ += RN;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float u = fmaf(f[k], A[k], Bc[k]);
-      f[k] = p.silu ? u * sigmoid_t(u) : u;
+      for (int k = 0; k < 8; ++k) {
+        const float h = fmaf(f[k], A[k], Bc[k]);
+        f[k] = SILU ? fmaf(h, tanh_fast(h), h) : h;
+      }
+      *reinterpret_cast<uint4*>(y) = pack_u4(f);
+      y += ystep;
     }
-    vstore<8>(ybase + (size_t)pix * p.C, f);
   }
 }
 
@@ -465,10 +502,10 @@ __global__ void __launch_bounds__(kResThreads, 3) gn_fwd_res_kernel(const GnPara
 // With u = x*aG + bH (aG = rstd*G, bH = -mean*rstd*G + Hh), du = dy*silu'(u), P = sum du, Qx = sum du*x:
 //   Q = sum du*xhat = rstd*Qx - mean*rstd*P ;  dx = K1*du - K2' - x*K3'  with K1 = rstd*G, K3' = rstd^2*s2/n,
 //   K2' = rstd*s1/n - mean*rstd^2*s2/n.
-// x and dy are streamed through registers (two 128-bit loads per pixel per thread, U pixels in flight); du is kept in
+// x and dy are streamed through registers (two 128-bit loads per pixel per thread, two pixels in flight); du is kept in
 // shared memory, x is read again in the apply pass (an L2 hit: the same CTA streamed it microseconds earlier and the
 // in-flight footprint of all CTAs is a few tens of MB).
-template <int U>
+template <bool SILU>
 __global__ void __launch_bounds__(kResThreads, 3) gn_bwd_res_kernel(const GnParams p) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int per = (p.HW + p.S - 1) / p.S;
@@ -486,11 +523,13 @@ __global__ void __launch_bounds__(kResThreads, 3) gn_bwd_res_kernel(const GnPara
   const int cpg = p.C / kGroups;
   const int ng = p.CC / cpg;
   const int c0 = chunk * p.CC;
+  const int RN = p.R * p.nvec;
+  const int nit = active ? max(0, (p1 - p0 - row + p.R - 1) / p.R) : 0;
 
   for (int i = threadIdx.x; i < 2 * p.CC; i += blockDim.x) chan[i] = 0.f;
   __syncthreads();
 
-  float aG[8], bH[8];
+  float aGh[8], bHh[8];      // halved affine: h = u/2 = x*aGh + bHh
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int ch = active ? c + k : 0, g = ch / cpg;
@@ -498,48 +537,49 @@ __global__ void __launch_bounds__(kResThreads, 3) gn_bwd_res_kernel(const GnPara
     float sc1 = 1.f, sh = 0.f;
     if (p.film) { const float* fr = p.film + (size_t)b * p.film_ld + p.film_off; sc1 = 1.f + fr[ch]; sh = fr[p.C + ch]; }
     const float G = p.gamma[ch] * sc1, Hh = p.beta[ch] * sc1 + sh;
-    aG[k] = rs * G; bH[k] = Hh - m * rs * G;
+    aGh[k] = 0.5f * rs * G; bHh[k] = 0.5f * (Hh - m * rs * G);
   }
   const bool in0 = c < p.C0;
   const __nv_bfloat16* xbase = in0 ? p.x0 + (size_t)b * p.HW * p.C0 + c : p.x1 + (size_t)b * p.HW * p.C1 + (c - p.C0);
   const int xpitch = in0 ? p.C0 : p.C1;
-  const __nv_bfloat16* dybase = p.dy + (size_t)b * p.HW * p.C + c;
+  const size_t xstep = (size_t)p.R * xpitch, dstep = (size_t)p.R * p.C;
+  const __nv_bfloat16* const xg0 = xbase + (size_t)(p0 + row) * xpitch;
+  uint4* const sl = slab + threadIdx.x;
 
   float P[8], Qx[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { P[k] = 0.f; Qx[k] = 0.f; }
-  if (active) {
-    for (int pix = p0 + row; pix < p1; pix += U * p.R) {
-      uint4 vx[U], vd[U];
+  {
+    const __nv_bfloat16* xg = xg0;
+    const __nv_bfloat16* dg = p.dy + (size_t)b * p.HW * p.C + c + (size_t)(p0 + row) * p.C;
+    uint4* s_ = sl;
+    auto one = [&](const uint4& vx, const uint4& vd, uint4* dst) {
+      float f[8], d[8];
+      unpack_u4(vx, f); unpack_u4(vd, d);
 #pragma unroll
-      for (int j = 0; j < U; ++j)
-        if (pix + j * p.R < p1) {
-          vx[j] = __ldg(reinterpret_cast<const uint4*>(xbase + (size_t)(pix + j * p.R) * xpitch));
-          vd[j] = __ldg(reinterpret_cast<const uint4*>(dybase + (size_t)(pix + j * p.R) * p.C));
+      for (int k = 0; k < 8; ++k) {
+        float du = d[k];
+        if (SILU) {
+          const float h = fmaf(f[k], aGh[k], bHh[k]);
+          const float t = tanh_fast(h);
+          const float w = fmaf(h, fmaf(-t, t, 1.f), t);        // t + h*(1 - t^2)
+          du = d[k] * fmaf(0.5f, w, 0.5f);
         }
-#pragma unroll
-      for (int j = 0; j < U; ++j) {
-        if (pix + j * p.R < p1) {
-          float f[8], d[8];
-          vunpack<8>(vx[j], f); vunpack<8>(vd[j], d);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            float du = d[k];
-            if (p.silu) {
-              const float u = fmaf(f[k], aG[k], bH[k]);
-              const float sg = sigmoid_t(u);
-              du = d[k] * sg * fmaf(u, 1.f - sg, 1.f);
-            }
-            P[k] += du; Qx[k] = fmaf(du, f[k], Qx[k]);
-            d[k] = du;
-          }
-          uint4 raw;
-          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(d[2 * k], d[2 * k + 1]);
-          slab[(size_t)(pix + j * p.R - p0) * p.nvec + vec] = raw;
-        }
+        P[k] += du; Qx[k] = fmaf(du, f[k], Qx[k]);
+        d[k] = du;
       }
+      *dst = pack_u4(d);
+    };
+    int i = 0;
+    for (; i + 2 <= nit; i += 2) {
+      const uint4 vx0 = __ldg(reinterpret_cast<const uint4*>(xg)), vd0 = __ldg(reinterpret_cast<const uint4*>(dg));
+      const uint4 vx1 = __ldg(reinterpret_cast<const uint4*>(xg + xstep)), vd1 = __ldg(reinterpret_cast<const uint4*>(dg + dstep));
+      one(vx0, vd0, s_); one(vx1, vd1, s_ + RN);
+      xg += 2 * xstep; dg += 2 * dstep; s_ += 2 * RN;
+    }
+    if (i < nit) {
+      const uint4 vx0 = __ldg(reinterpret_cast<const uint4*>(xg)), vd0 = __ldg(reinterpret_cast<const uint4*>(dg));
+      one(vx0, vd0, s_);
     }
   }
   if (p.nvec == 8) {
@@ -596,48 +636,59 @@ __global__ void __launch_bounds__(kResThreads, 3) gn_bwd_res_kernel(const GnPara
   if (!active) return;
 
   const float inv_n = 1.f / ((float)cpg * (float)p.HW);
-  float K2[8], K3[8];
+  float K1[8], K2[8], K3[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int ch = c + k, g = ch / cpg, lg = (cl + k) / cpg;
     const float m = p.mean[b * kGroups + g], rs = p.rstd[b * kGroups + g];
+    K1[k] = 2.f * aGh[k];
     K3[k] = rs * rs * gs[kGroups + lg] * inv_n;
     K2[k] = rs * gs[lg] * inv_n - m * K3[k];
   }
-  __nv_bfloat16* dxbase = in0 ? p.dx0 + (size_t)b * p.HW * p.C0 + c : p.dx1 + (size_t)b * p.HW * p.C1 + (c - p.C0);
-  const __nv_bfloat16* daddbase = p.dadd ? p.dadd + (size_t)b * p.HW * p.C + c : nullptr;
   const bool acc = (p.accumulate_dx >> (in0 ? 0 : 1)) & 1;
-  for (int pix = p0 + row; pix < p1; pix += U * p.R) {
-    uint4 vx[U], vo[U], va[U];
+  const bool hasadd = p.dadd != nullptr;
+  {
+    const __nv_bfloat16* xg = xg0;
+    __nv_bfloat16* og = (in0 ? p.dx0 + (size_t)b * p.HW * p.C0 + c : p.dx1 + (size_t)b * p.HW * p.C1 + (c - p.C0)) +
+                        (size_t)(p0 + row) * xpitch;
+    const __nv_bfloat16* ag = hasadd ? p.dadd + (size_t)b * p.HW * p.C + c + (size_t)(p0 + row) * p.C : nullptr;
+    const uint4* s_ = sl;
+    auto one = [&](const uint4& vx, const uint4& vdu, const uint4& vo, const uint4& va, __nv_bfloat16* dst) {
+      float f[8], d[8], o[8];
+      unpack_u4(vx, f); unpack_u4(vdu, d);
 #pragma unroll
-    for (int j = 0; j < U; ++j)
-      if (pix + j * p.R < p1) {
-        const size_t px = (size_t)(pix + j * p.R);
-        vx[j] = __ldg(reinterpret_cast<const uint4*>(xbase + px * xpitch));
-        if (acc) vo[j] = *reinterpret_cast<const uint4*>(dxbase + px * xpitch);
-        if (daddbase) va[j] = __ldg(reinterpret_cast<const uint4*>(daddbase + px * p.C));
+      for (int k = 0; k < 8; ++k) o[k] = fmaf(K1[k], d[k], -fmaf(f[k], K3[k], K2[k]));
+      if (acc) {
+        float t[8];
+        unpack_u4(vo, t);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] += t[k];
       }
+      if (hasadd) {
+        float t[8];
+        unpack_u4(va, t);
 #pragma unroll
-    for (int j = 0; j < U; ++j) {
-      if (pix + j * p.R < p1) {
-        float f[8], d[8], o[8];
-        vunpack<8>(vx[j], f);
-        vunpack<8>(slab[(size_t)(pix + j * p.R - p0) * p.nvec + vec], d);
-        if (acc) vunpack<8>(vo[j], o);
-        else {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) o[k] = 0.f;
-        }
-        if (daddbase) {
-          float a[8];
-          vunpack<8>(va[j], a);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) o[k] += a[k];
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] += fmaf(aG[k], d[k], -fmaf(f[k], K3[k], K2[k]));
-        vstore<8>(dxbase + (size_t)(pix + j * p.R) * xpitch, o);
+        for (int k = 0; k < 8; ++k) o[k] += t[k];
       }
+      *reinterpret_cast<uint4*>(dst) = pack_u4(o);
+    };
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    int i = 0;
+    for (; i + 2 <= nit; i += 2) {
+      const uint4 vx0 = __ldg(reinterpret_cast<const uint4*>(xg)), vx1 = __ldg(reinterpret_cast<const uint4*>(xg + xstep));
+      uint4 vo0 = z, vo1 = z, va0 = z, va1 = z;
+      if (acc) { vo0 = *reinterpret_cast<const uint4*>(og); vo1 = *reinterpret_cast<const uint4*>(og + xstep); }
+      if (hasadd) { va0 = __ldg(reinterpret_cast<const uint4*>(ag)); va1 = __ldg(reinterpret_cast<const uint4*>(ag + dstep)); }
+      one(vx0, s_[0], vo0, va0, og); one(vx1, s_[RN], vo1, va1, og + xstep);
+      xg += 2 * xstep; og += 2 * xstep; s_ += 2 * RN;
+      if (hasadd) ag += 2 * dstep;
+    }
+    if (i < nit) {
+      const uint4 vx0 = __ldg(reinterpret_cast<const uint4*>(xg));
+      uint4 vo0 = z, va0 = z;
+      if (acc) vo0 = *reinterpret_cast<const uint4*>(og);
+      if (hasadd) va0 = __ldg(reinterpret_cast<const uint4*>(ag));
+      one(vx0, s_[0], vo0, va0, og);
     }
   }
 }
@@ -743,7 +794,8 @@ extern "C" int cdae_gn_fwd(const void* x0, int C0, const void* x1, int C1, int B
   if (gn_res_config(p, kResElemsFwd, 8)) {
     const size_t per = (size_t)((HW + p.S - 1) / p.S);
     const size_t smem_res = per * p.CC * 2 + sizeof(float) * (2 * p.CC + 4 * kGroups);
-    return gn_res_launch<0>(gn_fwd_res_kernel, p, B, smem_res, (cudaStream_t)s, "gn_fwd_res_kernel");
+    return silu ? gn_res_launch<0>(gn_fwd_res_kernel<true>, p, B, smem_res, (cudaStream_t)s, "gn_fwd_res_kernel")
+                : gn_res_launch<1>(gn_fwd_res_kernel<false>, p, B, smem_res, (cudaStream_t)s, "gn_fwd_res_kernel");
   }
   int S;
   const bool wide = (C0 + C1) > 4 * kGnThreads;     // > 1024 channels: 8-channel vectors keep nvec <= 256
@@ -771,7 +823,8 @@ extern "C" int cdae_gn_bwd(const void* dy, const void* x0, int C0, const void* x
   if (gn_res_config(p, kResElemsBwd, 8)) {
     const size_t per = (size_t)((HW + p.S - 1) / p.S);
     const size_t smem_res = per * p.CC * 2 + sizeof(float) * (4 * p.CC + 2 * kGroups);
-    return gn_res_launch<1>(gn_bwd_res_kernel<2>, p, B, smem_res, (cudaStream_t)s, "gn_bwd_res_kernel");
+    return silu ? gn_res_launch<2>(gn_bwd_res_kernel<true>, p, B, smem_res, (cudaStream_t)s, "gn_bwd_res_kernel")
+                : gn_res_launch<3>(gn_bwd_res_kernel<false>, p, B, smem_res, (cudaStream_t)s, "gn_bwd_res_kernel");
   }
   int S;
   const bool wide = (C0 + C1) > 4 * kGnThreads;

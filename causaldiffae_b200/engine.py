@@ -457,6 +457,7 @@ class Engine:
         n, qkv, o, out = T(pl, (B, H, W, Cc)), T(pl, (B, H, W, 3 * Cc)), T(pl, (B, H, W, Cc)), T(pl, (B, H, W, Cc))
         st = (pl.alloc((B, 32), th.float32), pl.alloc((B, 32), th.float32))
         lse = pl.alloc((B, heads, Tn), th.float32)
+        dsum = pl.alloc((B, heads, Tn), th.float32) if pl.train else None
         pl.add_fwd(lambda: ops.gn_fwd(x.t, ab.norm.weight, ab.norm.bias, silu=False, out=n.t, mean=st[0], rstd=st[1]))
         self.plan_conv(pl, cwq, [n], qkv, 1)
         qv, ov = qkv.t.view(B, Tn, 3 * Cc), o.t.view(B, Tn, Cc)
@@ -469,7 +470,8 @@ class Engine:
                 fns += self.plan_conv_bwd(pl, cwp, [o], dout, 1)
                 dqkv = qkv.grad()
                 do = o.grad()
-                fns.append(lambda: ops.attn_bwd(qv, ov, do.view(B, Tn, Cc), lse, heads, dqkv=dqkv.view(B, Tn, 3 * Cc)))
+                fns.append(lambda: ops.attn_bwd(qv, ov, do.view(B, Tn, Cc), lse, heads, dqkv=dqkv.view(B, Tn, 3 * Cc),
+                                                dsum=dsum))
                 qkv.g_written = True
                 fns += self.plan_conv_bwd(pl, cwq, [n], dqkv, 1)
                 gw, gb = self._gparam(ab.norm.weight), self._gparam(ab.norm.bias)

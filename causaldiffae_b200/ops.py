@@ -287,10 +287,12 @@ def attn_fwd(qkv, heads, out=None, lse=None):
     return out, lse
 
 
-def attn_bwd(qkv, out, dout, lse, heads, dqkv=None):
+def attn_bwd(qkv, out, dout, lse, heads, dqkv=None, dsum=None):
+    """dsum: fp32 [B, heads, T] scratch (rowsum(dout*out)); pass a preallocated buffer on graph-captured paths."""
     _bf16c(qkv); _bf16c(out); _bf16c(dout)
     B, T, C3 = qkv.shape
     ch = C3 // 3 // heads
     dqkv = torch.empty_like(qkv) if dqkv is None else dqkv
-    check(_lib.lib().cdae_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), B, T, heads, ch, stream()))
+    dsum = torch.empty(B, heads, T, device=qkv.device, dtype=torch.float32) if dsum is None else _f32c(dsum)
+    check(_lib.lib().cdae_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dsum), ptr(dqkv), B, T, heads, ch, stream()))
     return dqkv

@@ -138,9 +138,10 @@ int cdae_wgrad(const cdae_wgrad_desc* d, cdae_stream s);
 /* ------------------------------------------------------------------ fused QKV attention            unet.py:239-253
  * qkv: [B, T, 3*C] bf16, head h at channels [h*3*ch, (h+1)*3*ch) = [q_h | k_h | v_h]; out [B, T, C] bf16 (head h at
  * h*ch); softmax in fp32, scale ch^-1/4 on q and k; lse [B, heads, T] fp32 saved for the backward (may be NULL).
- * backward: dqkv in the same interleaved layout (recomputes the probabilities from lse). ch: multiple of 16, <= 128. */
+ * backward: dqkv in the same interleaved layout (recomputes the probabilities from lse); dsum [B, heads, T] fp32 is
+ * caller-owned scratch (rowsum(dout*out), written by the dQ pass and read by the dK/dV pass). ch: multiple of 16, <= 128. */
 int cdae_attn_fwd(const void* qkv, void* out, float* lse, int B, int T, int heads, int ch, cdae_stream s);
-int cdae_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+int cdae_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* dsum, void* dqkv,
                   int B, int T, int heads, int ch, cdae_stream s);
 
 #ifdef __cplusplus
