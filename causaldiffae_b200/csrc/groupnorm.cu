@@ -9,7 +9,10 @@
 // cluster-barrier phases of one CTA overlap the streaming phases of the others.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+#include <map>
 #include <mutex>
+#include <tuple>
 
 #include "common.cuh"
 
@@ -24,7 +27,8 @@ struct GnParams {
   const __nv_bfloat16* x0; const __nv_bfloat16* x1;
   int C0, C1, C, HW, S;          // S = CTAs per unit (cluster size)
   int nvec, R;                   // channel vectors per pixel, pixel rows per pass
-  int CC, nchunk;                // resident kernels: channels per unit (whole groups, multiple of 8), units per sample
+  int CC, nchunk;                // pipelined kernels: channels per unit (whole groups, multiple of 8), units per sample
+  int per, nunits, ncl, v4, nvp;      // pixels per CTA slab, units, clusters in the persistent grid, 128-bit constant loads ok
   const float* gamma; const float* beta;
   const float* film; int film_ld, film_off;
   int silu;
@@ -322,35 +326,30 @@ __global__ void __launch_bounds__(kGnThreads, 3) gn_bwd_kernel(const GnParams p)
   }
 }
 
-// ------------------------------------------------------------------------------------------------ resident kernels
+// ------------------------------------------------------------------------------------------------ pipelined kernels
 // Work unit = (sample, chunk of CC channels holding whole groups); a cluster of S CTAs shares the unit, each CTA owning
-// HW/S pixels.  The CTA's slab is copied global -> SHARED MEMORY with cp.async (the whole slab is in flight at once:
-// memory-level parallelism does not cost registers) and stays there between the statistics pass and the apply pass,
-// so every tensor crosses HBM (and the L2 -> SM fabric, which on B200 is barely faster than HBM) exactly once:
-// forward 2 B read + 2 B written per element, backward 4 B read + 2 B written.  128-bit accesses, 8 channels per
-// thread; partial sums go warp shuffle -> shared atomics -> DSMEM across the cluster.  The backward overwrites the dy
-// slab with du = dy*silu'(u) (bf16): the sigmoid is evaluated once per element.
-constexpr int kResElemsFwd = 32768;     // 64 KB slab (x)
-constexpr int kResElemsBwd = 32768;     // 64 KB slab (du)
+// HW/S pixels (its "slab").  The kernels are PERSISTENT: a cluster walks units cid, cid + ncl, ... and every CTA keeps a
+// two-slab ring in shared memory - while it reduces / normalises the slab of unit i, the slab of unit i+1 is already
+// streaming in through cp.async (16 B per request, no registers held), and the stores of unit i-1 drain behind it.
+// ncu on the first (one unit per CTA, 64 KB slab) version showed why that matters: load, compute and store phases ran
+// back to back in every CTA of a wave, so HBM idled two thirds of the time (45 % of peak) although each tensor crossed
+// it only once.  Three such CTAs share an SM (64 KB + statistics each), so cluster barriers of one overlap the math
+// of the others.  Every tensor crosses HBM once: forward 2 B read + 2 B written per element, backward 4 B + 2 B.
+// Partial sums: registers -> warp shuffles -> per-warp rows in shared memory (plain stores, no atomics when the
+// vector count divides 32) -> DSMEM across the cluster (published in a parity-double-buffered block: ONE cluster
+// barrier per unit).  SiLU goes through h = u/2: silu(u) = h + h*tanh(h), silu'(u) = (1 + t + h*(1 - t^2))/2 with
+// t = tanh(h): one MUFU per element.
+constexpr int kPipeElems = 16384;       // 32 KB slab; two of them + statistics = 3 CTAs per SM
 constexpr int kResThreads = 256;
+constexpr int kResWarps = kResThreads / 32;
 
 __device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-// sigmoid(u) = 0.5*tanh(0.5u) + 0.5 : one MUFU op (the results are rounded to bf16 right after)
-__device__ __forceinline__ float sigmoid_t(float u) { return fmaf(0.5f, tanh_fast(0.5f * u), 0.5f); }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-}
-
-// sum v over the lanes that share (lane % 8) - valid when nvec == 8
-__device__ __forceinline__ float vec8_sum(float v) {
-  v += __shfl_xor_sync(0xffffffffu, v, 8);
-  v += __shfl_xor_sync(0xffffffffu, v, 16);
-  return v;
-}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 // bf16 pair -> two fp32 (one shift, one mask)
 __device__ __forceinline__ void unpack2(uint32_t u, float& lo, float& hi) {
@@ -368,373 +367,481 @@ __device__ __forceinline__ uint4 pack_u4(const float* f) {
   h = __floats2bfloat162_rn(f[6], f[7]); r.w = *reinterpret_cast<uint32_t*>(&h);
   return r;
 }
-
-// The inner loops are written for instruction count (the first version of these kernels was ISSUE bound: 21 / 42
-// thread instructions per element forward / backward, ncu r1): thread `tid` owns slab entries tid, tid + RN, ... (RN =
-// active threads), so every stream is a pointer that advances by a loop-invariant stride; SiLU is evaluated through
-// h = u/2: silu(u) = h + h*tanh(h) and silu'(u) = (1 + t + h*(1 - t^2))/2 with t = tanh(h) (one MUFU per element).
-// smem: bf16 slab[P][CC] | float chan[2][CC] | float gpart[2][32] | float gstat[2][32]
-template <bool SILU>
-__global__ void __launch_bounds__(kResThreads, 3) gn_fwd_res_kernel(const GnParams p) {
-  extern __shared__ __align__(16) unsigned char smraw[];
-  const int per = (p.HW + p.S - 1) / p.S;
-  uint4* slab = reinterpret_cast<uint4*>(smraw);
-  float* chan = reinterpret_cast<float*>(smraw + (size_t)per * p.CC * 2);
-  float* gpart = chan + 2 * p.CC;
-  float* gstat = gpart + 2 * kGroups;
-  cg::cluster_group cluster = cg::this_cluster();
-  const int unit = blockIdx.x / p.S, rank = blockIdx.x % p.S;
-  const int b = unit / p.nchunk, chunk = unit % p.nchunk;
-  const int vec = threadIdx.x % p.nvec, row = threadIdx.x / p.nvec;
-  const bool active = row < p.R;
-  const int cl = vec * 8, c = chunk * p.CC + cl;              // channel inside the chunk / absolute
-  const int p0 = rank * per, p1 = min(p.HW, p0 + per);
-  const int cpg = p.C / kGroups;
-  const int ng = p.CC / cpg;                                   // groups in this chunk
-  const int RN = p.R * p.nvec;
-  const int nit = active ? max(0, (p1 - p0 - row + p.R - 1) / p.R) : 0;   // pixels owned by this thread
-
-  const bool in0 = c < p.C0;
-  const __nv_bfloat16* xbase = in0 ? p.x0 + (size_t)b * p.HW * p.C0 + c : p.x1 + (size_t)b * p.HW * p.C1 + (c - p.C0);
-  const int xpitch = in0 ? p.C0 : p.C1;
-  uint4* const sl = slab + threadIdx.x;
-  {
-    const __nv_bfloat16* g = xbase + (size_t)(p0 + row) * xpitch;
-    const size_t gstep = (size_t)p.R * xpitch;
-    uint4* s_ = sl;
-    for (int i = 0; i < nit; ++i) { cp_async16(s_, g); s_ += RN; g += gstep; }
-  }
-  // per-channel affine constants do not depend on the statistics: fetch them while the slab is in flight
-  float Gk[8], Hk[8];
+// eight consecutive floats (two 128-bit loads when the address allows)
+__device__ __forceinline__ void load8f(const float* q, bool v4, float* o) {
+  if (v4) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(q)), b = __ldg(reinterpret_cast<const float4*>(q + 4));
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+  } else {
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int ch = active ? c + k : 0;
-    const float ga = p.gamma[ch], be = p.beta[ch];
-    float sc1 = 1.f, sh = 0.f;
-    if (p.film) { const float* fr = p.film + (size_t)b * p.film_ld + p.film_off; sc1 = 1.f + fr[ch]; sh = fr[p.C + ch]; }
-    Gk[k] = ga * sc1; Hk[k] = be * sc1 + sh;
-  }
-  for (int i = threadIdx.x; i < 2 * p.CC; i += blockDim.x) chan[i] = 0.f;
-  cp_async_wait_all();
-  __syncthreads();
-
-  float s[8], ss[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) { s[k] = 0.f; ss[k] = 0.f; }
-  {
-    const uint4* s_ = sl;
-#pragma unroll 4
-    for (int i = 0; i < nit; ++i) {
-      float f[8];
-      unpack_u4(*s_, f);
-      s_ += RN;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { s[k] += f[k]; ss[k] = fmaf(f[k], f[k], ss[k]); }
-    }
-  }
-  if (p.nvec == 8) {            // warp = 4 pixel rows x 8 vectors: fold the rows before touching shared memory
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { s[k] = vec8_sum(s[k]); ss[k] = vec8_sum(ss[k]); }
-    if ((threadIdx.x & 31) < 8) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { atomicAdd(&chan[cl + k], s[k]); atomicAdd(&chan[p.CC + cl + k], ss[k]); }
-    }
-  } else if (active) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { atomicAdd(&chan[cl + k], s[k]); atomicAdd(&chan[p.CC + cl + k], ss[k]); }
-  }
-  __syncthreads();
-  if (threadIdx.x < ng) {
-    float a = 0.f, q = 0.f;
-    for (int k = 0; k < cpg; ++k) { a += chan[threadIdx.x * cpg + k]; q += chan[p.CC + threadIdx.x * cpg + k]; }
-    gpart[threadIdx.x] = a; gpart[kGroups + threadIdx.x] = q;
-  }
-  cluster.sync();
-  if (threadIdx.x < ng) {
-    float a = 0.f, q = 0.f;
-    for (int r = 0; r < p.S; ++r) {
-      const float* rp = cluster.map_shared_rank(gpart, r);
-      a += rp[threadIdx.x]; q += rp[kGroups + threadIdx.x];
-    }
-    const float n = (float)cpg * (float)p.HW;
-    const float m = a / n;
-    const float var = fmaxf(q / n - m * m, 0.f);
-    const float rs = rsqrtf(var + 1e-5f);
-    gstat[threadIdx.x] = m; gstat[kGroups + threadIdx.x] = rs;
-    if (rank == 0) {
-      const int g = chunk * ng + threadIdx.x;
-      p.mean[b * kGroups + g] = m; p.rstd[b * kGroups + g] = rs;
-    }
-  }
-  cluster.sync();   // remote reads of gpart complete before any CTA may exit; also publishes gstat block-wide
-  if (!active) return;
-
-  float A[8], Bc[8];
-  const float half = SILU ? 0.5f : 1.f;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int g = (cl + k) / cpg;
-    const float m = gstat[g], rs = gstat[kGroups + g];
-    A[k] = half * rs * Gk[k];
-    Bc[k] = half * (Hk[k] - m * rs * Gk[k]);
-  }
-  {
-    __nv_bfloat16* y = p.y + (size_t)b * p.HW * p.C + c + (size_t)(p0 + row) * p.C;
-    const size_t ystep = (size_t)p.R * p.C;
-    const uint4* s_ = sl;
-#pragma unroll 2
-    for (int i = 0; i < nit; ++i) {
-      float f[8];
-      unpack_u4(*s_, f);
-      s_ += RN;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float h = fmaf(f[k], A[k], Bc[k]);
-        f[k] = SILU ? fmaf(h, tanh_fast(h), h) : h;
-      }
-      *reinterpret_cast<uint4*>(y) = pack_u4(f);
-      y += ystep;
-    }
+    for (int k = 0; k < 8; ++k) o[k] = __ldg(q + k);
   }
 }
 
-// smem: bf16 du slab[P][CC] | float chan[2][CC] | float tot[2][CC] | float gs[2][32]
+// Per-thread partial sums a[8], q[8] (channels cl..cl+7 of the chunk) -> wsum[warp][0][CC], wsum[warp][1][CC].
+// Lanes with equal (lane % nvp) own the same channels (nvp is a power of two): xor-shuffle them together and let the
+// first min(nvp, 32) lanes store - plain stores, no atomics.  When nvp > 32 a warp owns a fixed subset of the channels;
+// the rest of its row was zeroed once at kernel start.
+__device__ __forceinline__ void warp_partials(float* wsum, int CC, int nvp, bool active, int cl, float* a, float* q) {
+  float* wrow = wsum + (threadIdx.x >> 5) * 2 * CC;
+  for (int o = nvp; o < 32; o <<= 1) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a[k] += __shfl_xor_sync(0xffffffffu, a[k], o); q[k] += __shfl_xor_sync(0xffffffffu, q[k], o); }
+  }
+  if (active && (int)(threadIdx.x & 31) < nvp) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { wrow[cl + k] = a[k]; wrow[CC + cl + k] = q[k]; }
+  }
+}
+
+// Per-channel constants are computed ONCE per unit by the first CC threads and broadcast through shared memory (the
+// first pipelined version recomputed them in every thread: ~380 of ~1300 instructions per thread and unit, ncu r1).
+// smem: bf16 slab[2][per][CC] | float wsum[8][2][CC] | float gpart[2][2][32] | float ab[2][CC]
+template <bool SILU>
+__global__ void __launch_bounds__(kResThreads, 3) gn_fwd_pipe_kernel(const GnParams p) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int per = p.per;
+  const size_t slab_bytes = (size_t)per * p.CC * 2;
+  float* wsum = reinterpret_cast<float*>(smraw + 2 * slab_bytes);
+  float* gpart = wsum + kResWarps * 2 * p.CC;
+  float* ab = gpart + 4 * kGroups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int cid = blockIdx.x / p.S, rank = blockIdx.x % p.S;
+  const int vec = threadIdx.x % p.nvp, row = threadIdx.x / p.nvp;     // nvp = nvec rounded up to a power of two
+  const bool active = vec < p.nvec;
+  const int cl = active ? vec * 8 : 0;
+  const int p0 = rank * per, p1 = min(p.HW, p0 + per);
+  const int cpg = p.C / kGroups;
+  const int ng = p.CC / cpg;                                   // groups in a chunk
+  const int RN = p.R * p.nvec;
+  const int nit = active ? max(0, (p1 - p0 - row + p.R - 1) / p.R) : 0;   // pixels owned by this thread
+  const int sidx = row * p.nvec + vec;                                 // this thread's first slab entry (stride RN)
+  const float inv_n = 1.f / ((float)cpg * (float)p.HW);
+  const bool chan_thread = (int)threadIdx.x < p.CC;                    // owns channel threadIdx.x of the chunk
+  const int myg = chan_thread ? (int)threadIdx.x / cpg : 0;
+  const float half = SILU ? 0.5f : 1.f;
+
+  auto issue = [&](int u, int stage) {
+    const int b = u / p.nchunk, c = (u % p.nchunk) * p.CC + cl;
+    const bool in0 = c < p.C0;
+    const int xpitch = in0 ? p.C0 : p.C1;
+    const __nv_bfloat16* g = (in0 ? p.x0 + (size_t)b * p.HW * p.C0 + c : p.x1 + (size_t)b * p.HW * p.C1 + (c - p.C0)) +
+                             (size_t)(p0 + row) * xpitch;
+    const size_t gstep = (size_t)p.R * xpitch;
+    uint4* s_ = reinterpret_cast<uint4*>(smraw + stage * slab_bytes) + sidx;
+    for (int i = 0; i < nit; ++i) { cp_async16(s_, g); s_ += RN; g += gstep; }
+  };
+
+  for (int i = threadIdx.x; i < kResWarps * 2 * p.CC; i += blockDim.x) wsum[i] = 0.f;   // entries a warp never owns stay 0
+  __syncthreads();
+  if (cid < p.nunits) issue(cid, 0);
+  cp_async_commit();
+  int it = 0;
+  for (int u = cid; u < p.nunits; u += p.ncl, ++it) {
+    const int st = it & 1;
+    if (u + p.ncl < p.nunits) issue(u + p.ncl, st ^ 1);
+    cp_async_commit();
+    const int b = u / p.nchunk, chunk = u - b * p.nchunk;
+    // this thread's channel: affine constants that do not depend on the statistics (fetched while the slab is in flight)
+    float gk = 0.f, hk = 0.f;
+    if (chan_thread) {
+      const int ch = chunk * p.CC + threadIdx.x;
+      gk = __ldg(p.gamma + ch); hk = __ldg(p.beta + ch);
+      if (p.film) {
+        const float* fr = p.film + (size_t)b * p.film_ld + p.film_off;
+        const float sc = __ldg(fr + ch), sh = __ldg(fr + p.C + ch);
+        gk = fmaf(gk, sc, gk); hk = fmaf(hk, sc, hk) + sh;
+      }
+    }
+    cp_async_wait1();
+    __syncthreads();
+
+    const uint4* sl = reinterpret_cast<const uint4*>(smraw + st * slab_bytes) + sidx;
+    float s[8], ss[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s[k] = 0.f; ss[k] = 0.f; }
+    {
+      const uint4* s_ = sl;
+#pragma unroll 4
+      for (int i = 0; i < nit; ++i) {
+        float f[8];
+        unpack_u4(*s_, f);
+        s_ += RN;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s[k] += f[k]; ss[k] = fmaf(f[k], f[k], ss[k]); }
+      }
+    }
+    warp_partials(wsum, p.CC, p.nvp, active, cl, s, ss);
+    __syncthreads();
+    float* gp = gpart + st * 2 * kGroups;
+    if ((int)threadIdx.x < ng) {
+      float a = 0.f, q = 0.f;
+      for (int w = 0; w < kResWarps; ++w) {
+        const float* wr = wsum + w * 2 * p.CC + threadIdx.x * cpg;
+        for (int k = 0; k < cpg; ++k) { a += wr[k]; q += wr[p.CC + k]; }
+      }
+      gp[threadIdx.x] = a; gp[kGroups + threadIdx.x] = q;
+    }
+    if (p.S > 1) cluster.sync(); else __syncthreads();
+    if (chan_thread) {
+      float a = 0.f, q = 0.f;
+      if (p.S > 1) {
+        for (int r = 0; r < p.S; ++r) {
+          const float* rp = cluster.map_shared_rank(gp, r);
+          a += rp[myg]; q += rp[kGroups + myg];
+        }
+      } else { a = gp[myg]; q = gp[kGroups + myg]; }
+      const float m = a * inv_n;
+      const float var = fmaxf(q * inv_n - m * m, 0.f);
+      const float rs = rsqrtf(var + 1e-5f);
+      ab[threadIdx.x] = half * rs * gk;
+      ab[p.CC + threadIdx.x] = half * (hk - m * rs * gk);
+      if (rank == 0 && (int)threadIdx.x == myg * cpg) {
+        const int g = chunk * ng + myg;
+        p.mean[b * kGroups + g] = m; p.rstd[b * kGroups + g] = rs;
+      }
+    }
+    __syncthreads();
+
+    if (active) {
+      float A[8], Bc[8];
+      *reinterpret_cast<float4*>(A) = *reinterpret_cast<const float4*>(ab + cl);
+      *reinterpret_cast<float4*>(A + 4) = *reinterpret_cast<const float4*>(ab + cl + 4);
+      *reinterpret_cast<float4*>(Bc) = *reinterpret_cast<const float4*>(ab + p.CC + cl);
+      *reinterpret_cast<float4*>(Bc + 4) = *reinterpret_cast<const float4*>(ab + p.CC + cl + 4);
+      __nv_bfloat16* y = p.y + (size_t)b * p.HW * p.C + chunk * p.CC + cl + (size_t)(p0 + row) * p.C;
+      const size_t ystep = (size_t)p.R * p.C;
+      const uint4* s_ = sl;
+#pragma unroll 2
+      for (int i = 0; i < nit; ++i) {
+        float f[8];
+        unpack_u4(*s_, f);
+        s_ += RN;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float h = fmaf(f[k], A[k], Bc[k]);
+          f[k] = SILU ? fmaf(h, tanh_fast(h), h) : h;
+        }
+        *reinterpret_cast<uint4*>(y) = pack_u4(f);
+        y += ystep;
+      }
+    }
+    __syncthreads();      // slab st and ab are free for the next iteration
+  }
+  if (p.S > 1) cluster.sync();   // no CTA exits while a peer may still read its gpart
+}
+
+// smem: bf16 du slab[2][per][CC] | float wsum[8][2][CC] | float pub[2][2][CC] | float tot[2][CC] | float cst[6][CC]
 // With u = x*aG + bH (aG = rstd*G, bH = -mean*rstd*G + Hh), du = dy*silu'(u), P = sum du, Qx = sum du*x:
 //   Q = sum du*xhat = rstd*Qx - mean*rstd*P ;  dx = K1*du - K2' - x*K3'  with K1 = rstd*G, K3' = rstd^2*s2/n,
 //   K2' = rstd*s1/n - mean*rstd^2*s2/n.
-// x and dy are streamed through registers (two 128-bit loads per pixel per thread, two pixels in flight); du is kept in
-// shared memory, x is read again in the apply pass (an L2 hit: the same CTA streamed it microseconds earlier and the
-// in-flight footprint of all CTAs is a few tens of MB).
+// dy is prefetched into the ring (cp.async) and overwritten in place by du; x is streamed through registers in the
+// reduction pass and read again in the apply pass (an L2 hit: the same CTA touched it microseconds earlier).
+// cst rows: 0 aG/2 (aG when !SILU) | 1 bH/2 | 2 G (gamma*(1+scale)) | 3 K1 | 4 K2' | 5 K3'
 template <bool SILU>
-__global__ void __launch_bounds__(kResThreads, 3) gn_bwd_res_kernel(const GnParams p) {
+__global__ void __launch_bounds__(kResThreads, 3) gn_bwd_pipe_kernel(const GnParams p) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  const int per = (p.HW + p.S - 1) / p.S;
-  uint4* slab = reinterpret_cast<uint4*>(smraw);
-  float* chan = reinterpret_cast<float*>(smraw + (size_t)per * p.CC * 2);
-  float* tot = chan + 2 * p.CC;
-  float* gs = tot + 2 * p.CC;
+  const int per = p.per;
+  const size_t slab_bytes = (size_t)per * p.CC * 2;
+  float* wsum = reinterpret_cast<float*>(smraw + 2 * slab_bytes);
+  float* pub = wsum + kResWarps * 2 * p.CC;
+  float* tot = pub + 4 * p.CC;
+  float* cst = tot + 2 * p.CC;
   cg::cluster_group cluster = cg::this_cluster();
-  const int unit = blockIdx.x / p.S, rank = blockIdx.x % p.S;
-  const int b = unit / p.nchunk, chunk = unit % p.nchunk;
-  const int vec = threadIdx.x % p.nvec, row = threadIdx.x / p.nvec;
-  const bool active = row < p.R;
-  const int cl = vec * 8, c = chunk * p.CC + cl;
+  const int cid = blockIdx.x / p.S, rank = blockIdx.x % p.S;
+  const int vec = threadIdx.x % p.nvp, row = threadIdx.x / p.nvp;     // nvp = nvec rounded up to a power of two
+  const bool active = vec < p.nvec;
+  const int cl = active ? vec * 8 : 0;
   const int p0 = rank * per, p1 = min(p.HW, p0 + per);
   const int cpg = p.C / kGroups;
   const int ng = p.CC / cpg;
-  const int c0 = chunk * p.CC;
   const int RN = p.R * p.nvec;
   const int nit = active ? max(0, (p1 - p0 - row + p.R - 1) / p.R) : 0;
-
-  for (int i = threadIdx.x; i < 2 * p.CC; i += blockDim.x) chan[i] = 0.f;
-  __syncthreads();
-
-  float aGh[8], bHh[8];      // halved affine: h = u/2 = x*aGh + bHh
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int ch = active ? c + k : 0, g = ch / cpg;
-    const float m = p.mean[b * kGroups + g], rs = p.rstd[b * kGroups + g];
-    float sc1 = 1.f, sh = 0.f;
-    if (p.film) { const float* fr = p.film + (size_t)b * p.film_ld + p.film_off; sc1 = 1.f + fr[ch]; sh = fr[p.C + ch]; }
-    const float G = p.gamma[ch] * sc1, Hh = p.beta[ch] * sc1 + sh;
-    aGh[k] = 0.5f * rs * G; bHh[k] = 0.5f * (Hh - m * rs * G);
-  }
-  const bool in0 = c < p.C0;
-  const __nv_bfloat16* xbase = in0 ? p.x0 + (size_t)b * p.HW * p.C0 + c : p.x1 + (size_t)b * p.HW * p.C1 + (c - p.C0);
-  const int xpitch = in0 ? p.C0 : p.C1;
-  const size_t xstep = (size_t)p.R * xpitch, dstep = (size_t)p.R * p.C;
-  const __nv_bfloat16* const xg0 = xbase + (size_t)(p0 + row) * xpitch;
-  uint4* const sl = slab + threadIdx.x;
-
-  float P[8], Qx[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) { P[k] = 0.f; Qx[k] = 0.f; }
-  {
-    const __nv_bfloat16* xg = xg0;
-    const __nv_bfloat16* dg = p.dy + (size_t)b * p.HW * p.C + c + (size_t)(p0 + row) * p.C;
-    uint4* s_ = sl;
-    auto one = [&](const uint4& vx, const uint4& vd, uint4* dst) {
-      float f[8], d[8];
-      unpack_u4(vx, f); unpack_u4(vd, d);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float du = d[k];
-        if (SILU) {
-          const float h = fmaf(f[k], aGh[k], bHh[k]);
-          const float t = tanh_fast(h);
-          const float w = fmaf(h, fmaf(-t, t, 1.f), t);        // t + h*(1 - t^2)
-          du = d[k] * fmaf(0.5f, w, 0.5f);
-        }
-        P[k] += du; Qx[k] = fmaf(du, f[k], Qx[k]);
-        d[k] = du;
-      }
-      *dst = pack_u4(d);
-    };
-    int i = 0;
-    for (; i + 2 <= nit; i += 2) {
-      const uint4 vx0 = __ldg(reinterpret_cast<const uint4*>(xg)), vd0 = __ldg(reinterpret_cast<const uint4*>(dg));
-      const uint4 vx1 = __ldg(reinterpret_cast<const uint4*>(xg + xstep)), vd1 = __ldg(reinterpret_cast<const uint4*>(dg + dstep));
-      one(vx0, vd0, s_); one(vx1, vd1, s_ + RN);
-      xg += 2 * xstep; dg += 2 * dstep; s_ += 2 * RN;
-    }
-    if (i < nit) {
-      const uint4 vx0 = __ldg(reinterpret_cast<const uint4*>(xg)), vd0 = __ldg(reinterpret_cast<const uint4*>(dg));
-      one(vx0, vd0, s_);
-    }
-  }
-  if (p.nvec == 8) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { P[k] = vec8_sum(P[k]); Qx[k] = vec8_sum(Qx[k]); }
-    if ((threadIdx.x & 31) < 8) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { atomicAdd(&chan[cl + k], P[k]); atomicAdd(&chan[p.CC + cl + k], Qx[k]); }
-    }
-  } else if (active) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { atomicAdd(&chan[cl + k], P[k]); atomicAdd(&chan[p.CC + cl + k], Qx[k]); }
-  }
-  cluster.sync();
-  for (int i = threadIdx.x; i < 2 * p.CC; i += blockDim.x) {
-    float a = 0.f;
-    for (int r = 0; r < p.S; ++r) a += cluster.map_shared_rank(chan, r)[i];
-    tot[i] = a;
-  }
-  cluster.sync();
-  // tot[0][c] = P_c, tot[1][c] = sum du*x ; Q_c = rstd*(Qx_c - mean*P_c)
-  if (threadIdx.x < ng) {
-    const int g = chunk * ng + threadIdx.x;
-    const float m = p.mean[b * kGroups + g], rs = p.rstd[b * kGroups + g];
-    float s1 = 0.f, s2 = 0.f;
-    for (int k = 0; k < cpg; ++k) {
-      const int lc = threadIdx.x * cpg + k, ch = c0 + lc;
-      float kc = p.gamma[ch];
-      if (p.film) kc *= 1.f + p.film[(size_t)b * p.film_ld + p.film_off + ch];
-      const float Pc = tot[lc], Qc = rs * (tot[p.CC + lc] - m * Pc);
-      s1 += kc * Pc; s2 += kc * Qc;
-    }
-    gs[threadIdx.x] = s1; gs[kGroups + threadIdx.x] = s2;
-  }
-  if (rank == 0) {
-    for (int lc = threadIdx.x; lc < p.CC; lc += blockDim.x) {
-      const int ch = c0 + lc, g = ch / cpg;
-      const float m = p.mean[b * kGroups + g], rs = p.rstd[b * kGroups + g];
-      const float Pc = tot[lc], Qc = rs * (tot[p.CC + lc] - m * Pc);
-      float s1c = 1.f;
-      if (p.film) {
-        const size_t fo = (size_t)b * p.film_ld + p.film_off;
-        s1c = 1.f + p.film[fo + ch];
-        if (p.dfilm) {
-          p.dfilm[fo + ch] += p.gamma[ch] * Qc + p.beta[ch] * Pc;   // d scale  (columns owned by this layer & sample)
-          p.dfilm[fo + p.C + ch] += Pc;                              // d shift
-        }
-      }
-      if (p.dgamma) atomicAdd(p.dgamma + ch, s1c * Qc);
-      if (p.dbeta) atomicAdd(p.dbeta + ch, s1c * Pc);
-    }
-  }
-  __syncthreads();
-  if (!active) return;
-
+  const int sidx = row * p.nvec + vec;                                 // this thread's first slab entry (stride RN)
   const float inv_n = 1.f / ((float)cpg * (float)p.HW);
-  float K1[8], K2[8], K3[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int ch = c + k, g = ch / cpg, lg = (cl + k) / cpg;
-    const float m = p.mean[b * kGroups + g], rs = p.rstd[b * kGroups + g];
-    K1[k] = 2.f * aGh[k];
-    K3[k] = rs * rs * gs[kGroups + lg] * inv_n;
-    K2[k] = rs * gs[lg] * inv_n - m * K3[k];
-  }
-  const bool acc = (p.accumulate_dx >> (in0 ? 0 : 1)) & 1;
+  const size_t dstep = (size_t)p.R * p.C;
   const bool hasadd = p.dadd != nullptr;
-  {
-    const __nv_bfloat16* xg = xg0;
-    __nv_bfloat16* og = (in0 ? p.dx0 + (size_t)b * p.HW * p.C0 + c : p.dx1 + (size_t)b * p.HW * p.C1 + (c - p.C0)) +
-                        (size_t)(p0 + row) * xpitch;
-    const __nv_bfloat16* ag = hasadd ? p.dadd + (size_t)b * p.HW * p.C + c + (size_t)(p0 + row) * p.C : nullptr;
-    const uint4* s_ = sl;
-    auto one = [&](const uint4& vx, const uint4& vdu, const uint4& vo, const uint4& va, __nv_bfloat16* dst) {
-      float f[8], d[8], o[8];
-      unpack_u4(vx, f); unpack_u4(vdu, d);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = fmaf(K1[k], d[k], -fmaf(f[k], K3[k], K2[k]));
-      if (acc) {
-        float t[8];
-        unpack_u4(vo, t);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] += t[k];
+  const bool chan_thread = (int)threadIdx.x < p.CC;
+  const int myg = chan_thread ? (int)threadIdx.x / cpg : 0;
+  const float half = SILU ? 0.5f : 1.f;
+
+  auto issue = [&](int u, int stage) {
+    const int b = u / p.nchunk, c = (u % p.nchunk) * p.CC + cl;
+    const __nv_bfloat16* g = p.dy + (size_t)b * p.HW * p.C + c + (size_t)(p0 + row) * p.C;
+    uint4* s_ = reinterpret_cast<uint4*>(smraw + stage * slab_bytes) + sidx;
+    for (int i = 0; i < nit; ++i) { cp_async16(s_, g); s_ += RN; g += dstep; }
+  };
+
+  for (int i = threadIdx.x; i < kResWarps * 2 * p.CC; i += blockDim.x) wsum[i] = 0.f;   // entries a warp never owns stay 0
+  __syncthreads();
+  if (cid < p.nunits) issue(cid, 0);
+  cp_async_commit();
+  int it = 0;
+  for (int u = cid; u < p.nunits; u += p.ncl, ++it) {
+    const int st = it & 1;
+    if (u + p.ncl < p.nunits) issue(u + p.ncl, st ^ 1);
+    cp_async_commit();
+    const int b = u / p.nchunk, chunk = u - b * p.nchunk;
+    const int c0 = chunk * p.CC;
+    const int c = c0 + cl;
+    // this thread's channel
+    float G = 0.f, m = 0.f, rs = 0.f, sc1 = 1.f, ga = 0.f, be = 0.f;
+    if (chan_thread) {
+      const int ch = c0 + threadIdx.x;
+      ga = __ldg(p.gamma + ch); be = __ldg(p.beta + ch);
+      float sh = 0.f;
+      if (p.film) {
+        const float* fr = p.film + (size_t)b * p.film_ld + p.film_off;
+        sc1 = 1.f + __ldg(fr + ch); sh = __ldg(fr + p.C + ch);
       }
-      if (hasadd) {
-        float t[8];
-        unpack_u4(va, t);
+      G = ga * sc1;
+      const float Hh = be * sc1 + sh;
+      const int g = chunk * ng + myg;
+      m = p.mean[b * kGroups + g]; rs = p.rstd[b * kGroups + g];
+      cst[threadIdx.x] = half * rs * G;
+      cst[p.CC + threadIdx.x] = half * (Hh - m * rs * G);
+      cst[2 * p.CC + threadIdx.x] = G;
+    }
+    const bool in0 = c < p.C0;
+    const int xpitch = in0 ? p.C0 : p.C1;
+    const size_t xstep = (size_t)p.R * xpitch;
+    const __nv_bfloat16* const xg0 = (in0 ? p.x0 + (size_t)b * p.HW * p.C0 + c : p.x1 + (size_t)b * p.HW * p.C1 + (c - p.C0)) +
+                                     (size_t)(p0 + row) * xpitch;
+    uint4* const sl = reinterpret_cast<uint4*>(smraw + st * slab_bytes) + sidx;
+
+    // the first x loads go out before the wait: they do not depend on the ring
+    uint4 vxa = make_uint4(0u, 0u, 0u, 0u), vxb = vxa;
+    if (nit > 0) vxa = __ldg(reinterpret_cast<const uint4*>(xg0));
+    if (nit > 1) vxb = __ldg(reinterpret_cast<const uint4*>(xg0 + xstep));
+    cp_async_wait1();
+    __syncthreads();
+    float P[8], Qx[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] += t[k];
+    for (int k = 0; k < 8; ++k) { P[k] = 0.f; Qx[k] = 0.f; }
+    if (active) {
+      float aGh[8], bHh[8];      // halved affine: h = u/2 = x*aGh + bHh
+      if (SILU) {
+        *reinterpret_cast<float4*>(aGh) = *reinterpret_cast<const float4*>(cst + cl);
+        *reinterpret_cast<float4*>(aGh + 4) = *reinterpret_cast<const float4*>(cst + cl + 4);
+        *reinterpret_cast<float4*>(bHh) = *reinterpret_cast<const float4*>(cst + p.CC + cl);
+        *reinterpret_cast<float4*>(bHh + 4) = *reinterpret_cast<const float4*>(cst + p.CC + cl + 4);
       }
-      *reinterpret_cast<uint4*>(dst) = pack_u4(o);
-    };
-    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    int i = 0;
-    for (; i + 2 <= nit; i += 2) {
-      const uint4 vx0 = __ldg(reinterpret_cast<const uint4*>(xg)), vx1 = __ldg(reinterpret_cast<const uint4*>(xg + xstep));
-      uint4 vo0 = z, vo1 = z, va0 = z, va1 = z;
-      if (acc) { vo0 = *reinterpret_cast<const uint4*>(og); vo1 = *reinterpret_cast<const uint4*>(og + xstep); }
-      if (hasadd) { va0 = __ldg(reinterpret_cast<const uint4*>(ag)); va1 = __ldg(reinterpret_cast<const uint4*>(ag + dstep)); }
-      one(vx0, s_[0], vo0, va0, og); one(vx1, s_[RN], vo1, va1, og + xstep);
-      xg += 2 * xstep; og += 2 * xstep; s_ += 2 * RN;
-      if (hasadd) ag += 2 * dstep;
+      const __nv_bfloat16* xg = xg0 + 2 * xstep;
+      uint4* s_ = sl;
+      auto one = [&](const uint4& vx, uint4* dst) {
+        float f[8], d[8];
+        unpack_u4(vx, f); unpack_u4(*dst, d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float du = d[k];
+          if (SILU) {
+            const float h = fmaf(f[k], aGh[k], bHh[k]);
+            const float t = tanh_fast(h);
+            const float w = fmaf(h, fmaf(-t, t, 1.f), t);        // t + h*(1 - t^2)
+            du = d[k] * fmaf(0.5f, w, 0.5f);
+          }
+          P[k] += du; Qx[k] = fmaf(du, f[k], Qx[k]);
+          d[k] = du;
+        }
+        if (SILU) *dst = pack_u4(d);
+      };
+      int i = 0;
+      for (; i + 2 <= nit; i += 2) {       // software pipeline: the loads of pixels i+2, i+3 fly while i, i+1 are reduced
+        uint4 nxa = vxa, nxb = vxb;
+        if (i + 2 < nit) nxa = __ldg(reinterpret_cast<const uint4*>(xg));
+        if (i + 3 < nit) nxb = __ldg(reinterpret_cast<const uint4*>(xg + xstep));
+        one(vxa, s_); one(vxb, s_ + RN);
+        vxa = nxa; vxb = nxb;
+        xg += 2 * xstep; s_ += 2 * RN;
+      }
+      if (i < nit) one(vxa, s_);
     }
-    if (i < nit) {
-      const uint4 vx0 = __ldg(reinterpret_cast<const uint4*>(xg));
-      uint4 vo0 = z, va0 = z;
-      if (acc) vo0 = *reinterpret_cast<const uint4*>(og);
-      if (hasadd) va0 = __ldg(reinterpret_cast<const uint4*>(ag));
-      one(vx0, s_[0], vo0, va0, og);
+    warp_partials(wsum, p.CC, p.nvp, active, cl, P, Qx);
+    __syncthreads();
+    float* pb = pub + st * 2 * p.CC;
+    for (int i = threadIdx.x; i < 2 * p.CC; i += blockDim.x) {
+      float a = 0.f;
+      for (int w = 0; w < kResWarps; ++w) a += wsum[w * 2 * p.CC + i];
+      pb[i] = a;
     }
+    if (p.S > 1) cluster.sync(); else __syncthreads();
+    for (int i = threadIdx.x; i < 2 * p.CC; i += blockDim.x) {
+      float a = 0.f;
+      if (p.S > 1) { for (int r = 0; r < p.S; ++r) a += cluster.map_shared_rank(pb, r)[i]; }
+      else a = pb[i];
+      tot[i] = a;
+    }
+    __syncthreads();
+    // tot[0][c] = P_c, tot[1][c] = sum du*x ; Q_c = rstd*(Qx_c - mean*P_c); every channel thread folds its own group
+    if (chan_thread) {
+      float s1 = 0.f, s2 = 0.f;
+      for (int k = 0; k < cpg; ++k) {
+        const int lc = myg * cpg + k;
+        const float kc = cst[2 * p.CC + lc];
+        const float Pc = tot[lc], Qc = rs * (tot[p.CC + lc] - m * Pc);
+        s1 = fmaf(kc, Pc, s1); s2 = fmaf(kc, Qc, s2);
+      }
+      const float K3 = rs * rs * s2 * inv_n;
+      cst[3 * p.CC + threadIdx.x] = rs * G;
+      cst[4 * p.CC + threadIdx.x] = rs * s1 * inv_n - m * K3;
+      cst[5 * p.CC + threadIdx.x] = K3;
+      if (rank == 0) {
+        const int ch = c0 + threadIdx.x;
+        const float Pc = tot[threadIdx.x], Qc = rs * (tot[p.CC + threadIdx.x] - m * Pc);
+        if (p.film && p.dfilm) {
+          const size_t fo = (size_t)b * p.film_ld + p.film_off;
+          p.dfilm[fo + ch] += ga * Qc + be * Pc;        // d scale  (columns owned by this layer & sample)
+          p.dfilm[fo + p.C + ch] += Pc;                 // d shift
+        }
+        if (p.dgamma) atomicAdd(p.dgamma + ch, sc1 * Qc);
+        if (p.dbeta) atomicAdd(p.dbeta + ch, sc1 * Pc);
+      }
+    }
+    __syncthreads();
+
+    if (active) {
+      float K1[8], K2[8], K3[8];
+      *reinterpret_cast<float4*>(K1) = *reinterpret_cast<const float4*>(cst + 3 * p.CC + cl);
+      *reinterpret_cast<float4*>(K1 + 4) = *reinterpret_cast<const float4*>(cst + 3 * p.CC + cl + 4);
+      *reinterpret_cast<float4*>(K2) = *reinterpret_cast<const float4*>(cst + 4 * p.CC + cl);
+      *reinterpret_cast<float4*>(K2 + 4) = *reinterpret_cast<const float4*>(cst + 4 * p.CC + cl + 4);
+      *reinterpret_cast<float4*>(K3) = *reinterpret_cast<const float4*>(cst + 5 * p.CC + cl);
+      *reinterpret_cast<float4*>(K3 + 4) = *reinterpret_cast<const float4*>(cst + 5 * p.CC + cl + 4);
+      const bool acc = (p.accumulate_dx >> (in0 ? 0 : 1)) & 1;
+      const __nv_bfloat16* xg = xg0;
+      __nv_bfloat16* og = (in0 ? p.dx0 + (size_t)b * p.HW * p.C0 + c : p.dx1 + (size_t)b * p.HW * p.C1 + (c - p.C0)) +
+                          (size_t)(p0 + row) * xpitch;
+      const __nv_bfloat16* ag = hasadd ? p.dadd + (size_t)b * p.HW * p.C + c + (size_t)(p0 + row) * p.C : nullptr;
+      const uint4* s_ = sl;
+      auto one = [&](const uint4& vx, const uint4& vdu, const uint4& vo, const uint4& va, __nv_bfloat16* dst) {
+        float f[8], d[8], o[8];
+        unpack_u4(vx, f); unpack_u4(vdu, d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = fmaf(K1[k], d[k], -fmaf(f[k], K3[k], K2[k]));
+        if (acc) {
+          float t[8];
+          unpack_u4(vo, t);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] += t[k];
+        }
+        if (hasadd) {
+          float t[8];
+          unpack_u4(va, t);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] += t[k];
+        }
+        *reinterpret_cast<uint4*>(dst) = pack_u4(o);
+      };
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      int i = 0;
+      for (; i + 2 <= nit; i += 2) {
+        const uint4 vx0 = __ldg(reinterpret_cast<const uint4*>(xg)), vx1 = __ldg(reinterpret_cast<const uint4*>(xg + xstep));
+        uint4 vo0 = z, vo1 = z, va0 = z, va1 = z;
+        if (acc) { vo0 = *reinterpret_cast<const uint4*>(og); vo1 = *reinterpret_cast<const uint4*>(og + xstep); }
+        if (hasadd) { va0 = __ldg(reinterpret_cast<const uint4*>(ag)); va1 = __ldg(reinterpret_cast<const uint4*>(ag + dstep)); }
+        one(vx0, s_[0], vo0, va0, og); one(vx1, s_[RN], vo1, va1, og + xstep);
+        xg += 2 * xstep; og += 2 * xstep; s_ += 2 * RN;
+        if (hasadd) ag += 2 * dstep;
+      }
+      if (i < nit) {
+        const uint4 vx0 = __ldg(reinterpret_cast<const uint4*>(xg));
+        uint4 vo0 = z, va0 = z;
+        if (acc) vo0 = *reinterpret_cast<const uint4*>(og);
+        if (hasadd) va0 = __ldg(reinterpret_cast<const uint4*>(ag));
+        one(vx0, s_[0], vo0, va0, og);
+      }
+    }
+    __syncthreads();      // slab st, tot and cst are free for the next iteration
   }
+  if (p.S > 1) cluster.sync();   // no CTA exits while a peer may still read its published sums
 }
 
-// pick the unit decomposition of the resident kernels; returns false when the sample does not fit (huge images)
-static bool gn_res_config(GnParams& p, int max_elems, int max_cluster) {
+static inline size_t gn_pipe_smem(const GnParams& p, bool bwd) {
+  const size_t slabs = 2 * (size_t)p.per * p.CC * 2;
+  const size_t stats = bwd ? sizeof(float) * ((size_t)kResWarps * 2 * p.CC + 4 * p.CC + 2 * p.CC + 6 * p.CC)
+                           : sizeof(float) * ((size_t)kResWarps * 2 * p.CC + 4 * kGroups + 2 * p.CC);
+  return slabs + stats;
+}
+
+// How many clusters of S CTAs (kResThreads threads, `smem` dynamic bytes) can be resident at once.  The persistent grid
+// must not exceed it: a cluster that is not co-resident would only start after another one has finished ALL its units.
+static int gn_max_clusters(const void* kernel, int S, size_t smem) {
+  static std::mutex mu;
+  static std::map<std::tuple<const void*, int, size_t>, int> cache;
+  const size_t key_smem = (smem + 1023) / 1024 * 1024;
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_tuple(kernel, S, key_smem);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(kNumSMs * 4 / S * S));
+  cfg.blockDim = dim3((unsigned)kResThreads);
+  cfg.dynamicSmemBytes = key_smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)S; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    n = kNumSMs / S / 2;                            // conservative guess: one CTA per SM, half the chip
+    if (n < 1) n = 1;
+  }
+  cache[key] = n;
+  return n;
+}
+
+static inline int pow2_ceil_i(int v) { int q = 1; while (q < v) q <<= 1; return q; }
+
+// Pick (CC, S) for the pipelined kernels by a small cost model (rounds of the persistent grid x work per round, with
+// penalties for cluster barriers, rows that are not whole 32 B sectors and idle lanes).  False: shape does not fit.
+static bool gn_pipe_config(GnParams& p, int B, bool bwd, const void* kernel) {
   p.C = p.C0 + p.C1;
   if (p.C % kGroups || p.C0 % 8 || p.C1 % 8) return false;
   const int cpg = p.C / kGroups;
   int base = cpg;                                   // lcm(8, cpg)
   while (base % 8) base += cpg;
-  // candidates: multiples of lcm(8, cpg) that divide C.  Prefer the smallest one with >= 128 B rows whose unit fits a
-  // cluster; otherwise the largest narrower one that fits.
-  auto fits = [&](int m, int* S_out) {
-    if (m / 8 > kResThreads || m / cpg > kGroups) return false;
+  double best = 1e30;
+  int bestCC = 0, bestS = 1, bestNcl = 1;
+  for (int m = base; m <= p.C; m += base) {
+    const int nvec = m / 8, nvp = pow2_ceil_i(nvec);
+    if (p.C % m || nvp > kResThreads / 4 || m / cpg > kGroups) continue;       // >= 4 pixel rows per pass
     int S = 1;
-    while (S < max_cluster && (int64_t)((p.HW + S - 1) / S) * m > max_elems) S <<= 1;
-    *S_out = S;
-    return (int64_t)((p.HW + S - 1) / S) * m <= max_elems;
-  };
-  int CC = 0, S = 1;
-  for (int m = base; m <= p.C && !CC; m += base)
-    if (p.C % m == 0 && m >= 64 && fits(m, &S)) CC = m;
-  if (!CC)
-    for (int m = base; m < 64 && m <= p.C; m += base)
-      if (p.C % m == 0 && fits(m, &S)) CC = m;       // keeps the largest
-  if (!CC) return false;
-  fits(CC, &S);
-  p.CC = CC; p.nchunk = p.C / CC; p.S = S;
-  p.nvec = CC / 8; p.R = kResThreads / p.nvec;
+    while (S <= 8 && (int64_t)((p.HW + S - 1) / S) * m > kPipeElems) S <<= 1;
+    if (S > 8) continue;
+    const int per = (p.HW + S - 1) / S;
+    GnParams t = p; t.CC = m; t.per = per;
+    const size_t smem = gn_pipe_smem(t, bwd);
+    if (smem > 200 * 1024) continue;
+    const int64_t units = (int64_t)B * (p.C / m);
+    int64_t ncl = gn_max_clusters(kernel, S, smem);
+    if (ncl > units) ncl = units;
+    const int64_t rounds = (units + ncl - 1) / ncl;
+    double cost = (double)rounds * ((double)per * m + 3000.0 + (S > 1 ? 3000.0 : 0.0));
+    cost *= (double)nvp / nvec;
+    if ((m * 2) % 32) cost *= 1.3;
+    if (m * 2 < 64) cost *= 1.25;
+    if (cost < best) { best = cost; bestCC = m; bestS = S; bestNcl = (int)ncl; }
+  }
+  if (!bestCC) return false;
+  p.CC = bestCC; p.nchunk = p.C / bestCC; p.S = bestS; p.ncl = bestNcl;
+  p.per = (p.HW + bestS - 1) / bestS;
+  p.nunits = B * p.nchunk;
+  p.nvec = bestCC / 8; p.nvp = pow2_ceil_i(p.nvec); p.R = kResThreads / p.nvp;
+  static const bool dbg = getenv("CDAE_GN_DEBUG") != nullptr;
+  if (dbg) fprintf(stderr, "gn %s B%d C%d HW%d: CC %d S %d per %d units %d clusters %d smem %zu\n", bwd ? "bwd" : "fwd", B, p.C, p.HW,
+                   p.CC, p.S, p.per, p.nunits, p.ncl, gn_pipe_smem(p, bwd));
   return true;
 }
 
-template <int TAG, typename K>
-static int gn_res_launch(K kernel, const GnParams& p, int B, size_t smem, cudaStream_t st, const char* name) {
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-  });
-  if (attr_err != cudaSuccess) { set_error("%s attributes: %s", name, cudaGetErrorString(attr_err)); return CDAE_ERR_CUDA; }
+template <typename K>
+static int gn_pipe_launch(K kernel, const GnParams& p, size_t smem, cudaStream_t st, const char* name) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)(B * p.nchunk * p.S));
-  cfg.blockDim = dim3((unsigned)((p.nvec * p.R + 31) / 32 * 32));
+  cfg.gridDim = dim3((unsigned)(p.ncl * p.S));
+  cfg.blockDim = dim3((unsigned)kResThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute at[1];
@@ -745,6 +852,8 @@ static int gn_res_launch(K kernel, const GnParams& p, int B, size_t smem, cudaSt
   if (e != cudaSuccess) { set_error("%s: %s", name, cudaGetErrorString(e)); return CDAE_ERR_CUDA; }
   return CDAE_OK;
 }
+
+static inline bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
 
 template <int V>
 static int gn_config(GnParams& p, int* S_out) {
@@ -791,11 +900,12 @@ extern "C" int cdae_gn_fwd(const void* x0, int C0, const void* x1, int C1, int B
   p.x0 = (const __nv_bfloat16*)x0; p.x1 = (const __nv_bfloat16*)x1; p.C0 = C0; p.C1 = C1; p.HW = HW;
   p.gamma = gamma; p.beta = beta; p.film = film; p.film_ld = film_ld; p.film_off = film_off; p.silu = silu;
   p.y = (__nv_bfloat16*)y; p.mean = mean; p.rstd = rstd;
-  if (gn_res_config(p, kResElemsFwd, 8)) {
-    const size_t per = (size_t)((HW + p.S - 1) / p.S);
-    const size_t smem_res = per * p.CC * 2 + sizeof(float) * (2 * p.CC + 4 * kGroups);
-    return silu ? gn_res_launch<0>(gn_fwd_res_kernel<true>, p, B, smem_res, (cudaStream_t)s, "gn_fwd_res_kernel")
-                : gn_res_launch<1>(gn_fwd_res_kernel<false>, p, B, smem_res, (cudaStream_t)s, "gn_fwd_res_kernel");
+  {
+    auto kern = silu ? gn_fwd_pipe_kernel<true> : gn_fwd_pipe_kernel<false>;
+    if (gn_pipe_config(p, B, false, reinterpret_cast<const void*>(kern))) {
+      p.v4 = aligned16(gamma) && aligned16(beta) && (!film || (aligned16(film) && film_ld % 4 == 0 && film_off % 4 == 0 && p.C % 4 == 0));
+      return gn_pipe_launch(kern, p, gn_pipe_smem(p, false), (cudaStream_t)s, "gn_fwd_pipe_kernel");
+    }
   }
   int S;
   const bool wide = (C0 + C1) > 4 * kGnThreads;     // > 1024 channels: 8-channel vectors keep nvec <= 256
@@ -820,11 +930,12 @@ extern "C" int cdae_gn_bwd(const void* dy, const void* x0, int C0, const void* x
   p.dy = (const __nv_bfloat16*)dy; p.dadd = (const __nv_bfloat16*)dadd; p.dx0 = (__nv_bfloat16*)dx0; p.dx1 = (__nv_bfloat16*)dx1;
   p.accumulate_dx = accumulate_dx;
   p.dgamma = dgamma; p.dbeta = dbeta; p.dfilm = dfilm;
-  if (gn_res_config(p, kResElemsBwd, 8)) {
-    const size_t per = (size_t)((HW + p.S - 1) / p.S);
-    const size_t smem_res = per * p.CC * 2 + sizeof(float) * (4 * p.CC + 2 * kGroups);
-    return silu ? gn_res_launch<2>(gn_bwd_res_kernel<true>, p, B, smem_res, (cudaStream_t)s, "gn_bwd_res_kernel")
-                : gn_res_launch<3>(gn_bwd_res_kernel<false>, p, B, smem_res, (cudaStream_t)s, "gn_bwd_res_kernel");
+  {
+    auto kern = silu ? gn_bwd_pipe_kernel<true> : gn_bwd_pipe_kernel<false>;
+    if (gn_pipe_config(p, B, true, reinterpret_cast<const void*>(kern))) {
+      p.v4 = aligned16(gamma) && aligned16(beta) && (!film || (aligned16(film) && film_ld % 4 == 0 && film_off % 4 == 0 && p.C % 4 == 0));
+      return gn_pipe_launch(kern, p, gn_pipe_smem(p, true), (cudaStream_t)s, "gn_bwd_pipe_kernel");
+    }
   }
   int S;
   const bool wide = (C0 + C1) > 4 * kGnThreads;
