@@ -296,3 +296,23 @@ def attn_bwd(qkv, out, dout, lse, heads, dqkv=None, dsum=None):
     dsum = torch.empty(B, heads, T, device=qkv.device, dtype=torch.float32) if dsum is None else _f32c(dsum)
     check(_lib.lib().cdae_attn_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dsum), ptr(dqkv), B, T, heads, ch, stream()))
     return dqkv
+
+
+# ------------------------------------------------------------------ causal DAG mask layer
+def dag_fwd(u, A, param_ptrs, n, d, D):
+    """ref nn.py:290-312 in one launch. u fp32 [B, n*d]; A fp32 [n, n]; param_ptrs: device int64 [4n] -> z_post [B, n*d]"""
+    _f32c(u); _f32c(A)
+    B = u.shape[0]
+    z = torch.empty_like(u)
+    check(_lib.lib().cdae_dag_fwd(ptr(u), ptr(A), ptr(param_ptrs), ptr(z), B, n, d, D, stream()))
+    return z
+
+
+def dag_bwd(u, A, param_ptrs, dz, grad_ptrs, ws, n, d, D):
+    """-> du; parameter gradients are accumulated through grad_ptrs (device int64 [4n]); ws: zeroed fp32 [B, n*d] scratch"""
+    _f32c(u); _f32c(A); _f32c(dz); _f32c(ws)
+    B = u.shape[0]
+    du = torch.empty_like(u)
+    check(_lib.lib().cdae_dag_bwd(ptr(u), ptr(A), ptr(param_ptrs), ptr(dz), ptr(grad_ptrs), ptr(ws), ptr(du), B, n, d, D,
+                                  stream()))
+    return du

@@ -263,8 +263,7 @@ class UNetModel(nn.Module):
                 mu, var = self.rep_emb.encode(x_start)
                 if self.causal_modeling:
                     At = self._adjacency(A, mu.device)
-                    z_pre = self.causal_mask.causal_masking(mu, At)
-                    z_post = self.causal_mask.nonlinearity_add_back_noise(mu, z_pre)
+                    z_post = self.causal_mask(mu, At)      # causal_masking + nonlinearity_add_back_noise, fused
                     z = reparameterize(z_post, var * 0.001)
                 else:
                     z = reparameterize(mu, var * 0.001)

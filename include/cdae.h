@@ -144,6 +144,17 @@ int cdae_attn_fwd(const void* qkv, void* out, float* lse, int B, int T, int head
 int cdae_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* dsum, void* dqkv,
                   int B, int T, int heads, int ch, cdae_stream s);
 
+/* ------------------------------------------------------------------ causal DAG mask layer   nn.py:225-240,290-312; unet.py:571-583
+ * z_pre[b,i,:] = sum_j A[j,i] u[b,j,:];  z_post[b,i,:] = W2_i leaky_relu(W1_i z_pre[b,i,:] + b1_i) + b2_i + u[b,i,:]
+ * u, z_post, dzpost, du: fp32 [B, n, d]; A: fp32 [n, n] row-major; params / grads: DEVICE arrays of 4n pointers
+ * {W1_i [D,d], b1_i [D], W2_i [d,D], b2_i [d]} (the reference keeps one MLP per causal variable).  n <= 8.
+ * backward: recomputes the hidden layer; parameter gradients are ACCUMULATED (+=) into grads; dzp_ws is a caller-owned
+ * fp32 [B, n, d] workspace that must be zero on entry and is left zero on exit; d in {64, 128, 256}, D % 32 == 0. */
+int cdae_dag_fwd(const float* u, const float* A, const void* const* params, float* zpost, int B, int n, int d, int D,
+                 cdae_stream s);
+int cdae_dag_bwd(const float* u, const float* A, const void* const* params, const float* dzpost, void* const* grads,
+                 float* dzp_ws, float* du, int B, int n, int d, int D, cdae_stream s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -311,3 +311,32 @@ def test_attention_fwd_bwd(B, T, heads, ch):
     got = dqkv.float().permute(0, 2, 1).reshape(B * heads, 3 * ch, T)
     for name, sl in (("dq", slice(0, ch)), ("dk", slice(ch, 2 * ch)), ("dv", slice(2 * ch, 3 * ch))):
         assert relerr(got[:, sl], ref_in.grad[:, sl]) < 2e-2, name
+
+
+# ------------------------------------------------------------------ causal DAG mask layer (fused) vs the two reference methods
+@pytest.mark.parametrize("B,n,latent", [(64, 4, 512), (5, 2, 512), (33, 4, 256)])
+def test_dag_layer_fwd_bwd(B, n, latent):
+    from causaldiffae_b200.nn import CausalModeling
+    torch.manual_seed(B + n)
+    mod = CausalModeling(latent_dim=latent, num_var=n).to(dev())
+    A = torch.triu(torch.ones(n, n), diagonal=1).to(dev())
+    A[0, -1] = 0.0
+    u = torch.randn(B, latent, device=dev(), requires_grad=True)
+    dz = torch.randn(B, latent, device=dev())
+    # reference composition (ref nn.py:290-312) through plain torch autograd
+    ref = mod.nonlinearity_add_back_noise(u, mod.causal_masking(u, A))
+    ref.backward(dz)
+    gref = [p.grad.clone() for p in mod._mlp_params()]
+    duref = u.grad.clone()
+    for p in mod._mlp_params():
+        p.grad = torch.full_like(p, 0.25)            # the kernel ACCUMULATES into existing gradients
+    u.grad = None
+    assert mod.fused_ok(u)
+    out = mod(u, A)
+    assert relerr(out, ref.detach()) < 1e-5
+    out.backward(dz)
+    assert relerr(u.grad, duref) < 1e-5
+    for p, g in zip(mod._mlp_params(), gref):
+        assert relerr(p.grad - 0.25, g) < 1e-4
+    # workspace is left zeroed for the next call
+    assert float(mod._workspace(u).abs().max()) == 0.0
