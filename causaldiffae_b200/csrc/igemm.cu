@@ -749,6 +749,7 @@ struct alignas(64) WgradKParams {
   int es, ksize, c0;
   int tiles_per_split;
   float* dw; int dw_ld, taps, ci_off, cin_real, cout;
+  float* dbias;        // fused bias gradient (column sums of dY) or nullptr
 };
 
 constexpr int kWgBoxBytes = 64 * 128;  // 64 pixels x 64 channels bf16
@@ -758,12 +759,14 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ Wgra
   constexpr int kABytes = 2 * kWgBoxBytes;            // 128 output channels
   constexpr int kBBytes = (BN / 64) * kWgBoxBytes;
   constexpr int kStageBytes = kABytes + kBBytes;
-  constexpr uint32_t kTmemCols = BN;
+  constexpr uint32_t kTmemCols = BN + 8 <= 128 ? 128 : BN + 8 <= 256 ? 256 : 512;   // + 8 columns for the bias gradient
   constexpr uint32_t kIdesc = make_idesc_bf16(128, BN, 1, 1);
+  constexpr uint32_t kIdescOnes = make_idesc_bf16(128, 8, 1, 1);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+  uint8_t* ones = smem + STAGES * kStageBytes;                      // 16 rows x 128 B of bf16 1.0
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ones + 2048);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = smem_u32(smem);
@@ -772,12 +775,14 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ Wgra
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
 
+  for (int i = threadIdx.x; i < 2048 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(tmem_full_bar, 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -786,6 +791,10 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ Wgra
   const int co0 = blockIdx.x * 128;
   const int ci_tiles = gridDim.y / p.taps;
   const int tap = blockIdx.y / ci_tiles, ci0 = (blockIdx.y % ci_tiles) * BN;
+  // The bias gradient (column sums of dY) rides along as an N = 8 MMA against a tile of ones.  Every (tap, ci) column of
+  // CTAs sees the same dY tiles, so pixel tile t is summed by column t % gridDim.y: the extra MMAs are spread evenly
+  // instead of making one column of CTAs the straggler of the launch.
+  const int bcols = gridDim.y, bcol = blockIdx.y;
   const int dh = p.ksize == 3 ? tap / 3 - 1 : 0, dw = p.ksize == 3 ? tap % 3 - 1 : 0;
   const int t_begin = blockIdx.z * p.tiles_per_split;
   int t_end = t_begin + p.tiles_per_split; if (t_end > p.ntiles) t_end = p.ntiles;
@@ -812,6 +821,7 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ Wgra
         }
       }
     } else if (warp == 1) {
+      int bias_started = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -825,6 +835,12 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ Wgra
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // K = 16 pixels = two 1024 B atoms = +128 in the >>4 address field
             umma_f16(tmem_base, adesc + 128 * k, bdesc + 128 * k, kIdesc, (kb | k) != 0);
+          if (p.dbias && (t_begin + kb) % bcols == bcol) {
+            const uint64_t odesc = smem_desc_mnmajor_sw128(smem_u32(ones), 0, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(tmem_base + BN, adesc + 128 * k, odesc, kIdescOnes, (bias_started | k) != 0);
+            bias_started = 1;
+          }
           umma_commit(empty_bar(s));
           if (kb == nkb - 1) umma_commit(tmem_full_bar);
         }
@@ -833,6 +849,7 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ Wgra
     } else {
       const int q = warp & 3;
       const int co = co0 + q * 32 + lane;
+      const bool do_bias = p.dbias != nullptr && t_begin + ((bcol - t_begin % bcols) + bcols) % bcols < t_end;
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
 #pragma unroll 1
@@ -855,6 +872,13 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ Wgra
           for (int j = 0; j < 32 && j < lim; ++j) atomicAdd(row + j, __uint_as_float(acc[j]));
         }
       }
+      if (do_bias) {
+        uint32_t acc[16];
+        __syncwarp();
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)BN, acc);   // columns 0..7 hold the same sum
+        tmem_ld_wait();
+        if (co < p.cout) atomicAdd(p.dbias + co, __uint_as_float(acc[0]));
+      }
       tc_fence_before();
     }
   }
@@ -864,7 +888,8 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ Wgra
 
 template <int BN, int STAGES>
 static int launch_wgrad(const WgradKParams& kp, dim3 grid, cudaStream_t st) {
-  constexpr int smem = STAGES * (2 * kWgBoxBytes + (BN / 64) * kWgBoxBytes) + 1024 + 256;
+  constexpr int smem = STAGES * (2 * kWgBoxBytes + (BN / 64) * kWgBoxBytes) + 2048 + 1024 + 256;
+  static_assert(smem <= 227 * 1024, "wgrad: shared memory budget");
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
@@ -919,7 +944,7 @@ __global__ void __launch_bounds__(192) wgrad3_kernel(const __grid_constant__ Wgr
   const int co0 = blockIdx.x * 128;
   const int ci_tiles = gridDim.y / 3;
   const int krow = blockIdx.y / ci_tiles, ci0 = (blockIdx.y % ci_tiles) * BN;     // kernel row 0..2 -> dh = krow - 1
-  const bool do_bias = p.dbias != nullptr && krow == 1 && ci0 == 0;
+  const int bcols = gridDim.y, bcol = blockIdx.y;       // bias gradient: pixel tile t is summed by column t % gridDim.y
   const int t_begin = blockIdx.z * p.tiles_per_split;
   int t_end = t_begin + p.tiles_per_split; if (t_end > p.ntiles) t_end = p.ntiles;
   const int nkb = t_end - t_begin;
@@ -957,6 +982,7 @@ __global__ void __launch_bounds__(192) wgrad3_kernel(const __grid_constant__ Wgr
         }
       }
     } else if (warp == 1) {
+      int bias_started = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -974,10 +1000,11 @@ __global__ void __launch_bounds__(192) wgrad3_kernel(const __grid_constant__ Wgr
             for (int k = 0; k < 4; ++k)   // K = 16 pixels = two image rows of the tile: +2 SBO steps per MMA
               umma_f16(tmem_base + tap * BN, adesc + 128 * k, bdesc + 160 * k, kIdesc, (kb | k) != 0);
           }
-          if (do_bias) {
+          if (p.dbias && (t_begin + kb) % bcols == bcol) {
             const uint64_t odesc = smem_desc_mnmajor_sw128(smem_u32(ones), 0, 1024);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16(tmem_base + 3 * BN, adesc + 128 * k, odesc, kIdescOnes, (kb | k) != 0);
+            for (int k = 0; k < 4; ++k) umma_f16(tmem_base + 3 * BN, adesc + 128 * k, odesc, kIdescOnes, (bias_started | k) != 0);
+            bias_started = 1;
           }
           umma_commit(empty_bar(s));
           if (kb == nkb - 1) umma_commit(tmem_full_bar);
@@ -987,6 +1014,7 @@ __global__ void __launch_bounds__(192) wgrad3_kernel(const __grid_constant__ Wgr
     } else {
       const int q = warp & 3;
       const int co = co0 + q * 32 + lane;
+      const bool do_bias = p.dbias != nullptr && t_begin + ((bcol - t_begin % bcols) + bcols) % bcols < t_end;
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
 #pragma unroll 1
@@ -1092,9 +1120,8 @@ extern "C" int cdae_wgrad(const cdae_wgrad_desc* d, cdae_stream s) {
   CDAE_CHECK_SHAPE(d->ldy % 8 == 0 && d->src_c % 8 == 0, "wgrad: pitches must be multiples of 8");
   static const bool no_w3 = getenv("CDAE_WGRAD_V1") != nullptr;
   // one-kernel-row kernel (N = 128 per tap): wins wherever the one-tap kernel cannot run its N = 256 tile
-  if (d->ksize == 3 && d->in_stride == 1 && d->H == d->OH && d->W == d->OW && !no_w3 && (d->cin % 256 != 0 || d->dbias))
+  if (d->ksize == 3 && d->in_stride == 1 && d->H == d->OH && d->W == d->OW && !no_w3 && d->cin % 256 != 0)
     return wgrad3(d, reinterpret_cast<cudaStream_t>(s));
-  CDAE_CHECK_SHAPE(!d->dbias, "wgrad: the fused bias gradient needs the 3x3 stride-1 kernel");
   WgradKParams kp;
   memset(&kp, 0, sizeof(kp));
   tile_geometry(64, d->OH, d->OW, &kp.bw, &kp.bh, &kp.bni);
@@ -1105,6 +1132,7 @@ extern "C" int cdae_wgrad(const cdae_wgrad_desc* d, cdae_stream s) {
   kp.es = d->in_stride; kp.ksize = d->ksize; kp.c0 = d->c0;
   kp.dw = d->dw; kp.dw_ld = d->dw_ld; kp.taps = d->ksize * d->ksize; kp.ci_off = d->ci_off;
   kp.cin_real = d->cin_real > 0 ? d->cin_real : d->cin; kp.cout = d->cout;
+  kp.dbias = d->dbias;
   {
     const uint64_t C = d->ldy;
     uint64_t dims[4] = {C, (uint64_t)d->OW, (uint64_t)d->OH, (uint64_t)d->N};

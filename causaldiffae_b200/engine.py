@@ -346,8 +346,8 @@ class Engine:
         """gradients of out = conv(concat(srcs)): bias, weight, and data (into srcs[i].grad()). dy: bf16 NHWC tensor."""
         fns = []
         gb, gw = self._gparam(cw.bias), self._gparam(cw.param)
-        # the bias gradient rides along in the one-kernel-row 3x3 weight-gradient kernel (used when Cin % 256 != 0)
-        fused_bias = ksize == 3 and stride == 1 and cw.cout % 8 == 0 and srcs[0].shape[3] % 256 != 0
+        # the bias gradient (column sums of dy) rides along in the weight-gradient kernel of the first source
+        fused_bias = cw.cout % 8 == 0
         if fused_bias:
             pass
         elif cw.cout % 8 == 0:
@@ -414,11 +414,11 @@ class Engine:
                 fns += self.plan_conv_bwd(pl, cw2, [a2], dout, 3)
                 if has_skip:
                     gsk_b, gsk_w = self._gparam(sk.bias), self._gparam(sk.param)
-                    fns.append(lambda: ops.colsum_(dout, gsk_b))
                     off = 0
                     for s in srcs_x:
                         c = s.shape[3]
-                        wd = ops.make_wgrad_desc(dout, s.t, gsk_w, cout, c, ksize=1, ci_off=off, dw_ld=cin)
+                        wd = ops.make_wgrad_desc(dout, s.t, gsk_w, cout, c, ksize=1, ci_off=off, dw_ld=cin,
+                                                 dbias=gsk_b if off == 0 else None)
                         fns.append(lambda wd=wd: ops.wgrad(wd))
                         acc, g = s.grad_acc(), s.grad()
                         segs, _ = ops.conv_segments([cout], 1)

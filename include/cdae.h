@@ -131,7 +131,7 @@ typedef struct {
   float* dw; int32_t dw_ld;                /* fp32 dW[co][tap][dw_ld] ; columns start at ci_off */
   int32_t ci_off, cin_real;                /* only ci < cin_real written */
   int32_t splits;                          /* split-K factor over pixel tiles (0: auto) */
-  float* dbias;                            /* fp32 [cout] += column sums of dy (bias gradient); 3x3 stride-1 only, or NULL */
+  float* dbias;                            /* fp32 [cout] += column sums of dy (the bias gradient, fused as an N=8 MMA against ones), or NULL */
 } cdae_wgrad_desc;
 int cdae_wgrad(const cdae_wgrad_desc* d, cdae_stream s);
 

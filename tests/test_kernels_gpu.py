@@ -267,7 +267,7 @@ def test_igemm_dgrad_matches_autograd():
 
 @pytest.mark.parametrize("N,H,cin,cout,ksize,stride", [(2, 32, 128, 128, 3, 1), (4, 8, 256, 128, 3, 1), (2, 16, 64, 64, 3, 1),
                                                        (3, 16, 192, 256, 1, 1), (2, 32, 128, 128, 3, 2), (8, 4, 128, 128, 3, 1),
-                                                       (2, 64, 64, 128, 3, 1), (3, 12, 128, 192, 3, 1)])
+                                                       (2, 64, 64, 128, 3, 1), (3, 12, 128, 192, 3, 1), (2, 16, 256, 256, 3, 1), (5, 8, 512, 64, 1, 1)])
 def test_wgrad_matches_autograd(N, H, cin, cout, ksize, stride):
     from causaldiffae_b200 import ops
     g = torch.Generator().manual_seed(H + cin)
@@ -277,7 +277,7 @@ def test_wgrad_matches_autograd(N, H, cin, cout, ksize, stride):
     dy = torch.randn(y.shape, generator=g).to(dev()).to(bf16).float()
     y.backward(dy)
     dw = torch.zeros(cout, ksize * ksize, cin, device=dev())
-    fused_bias = ksize == 3 and stride == 1          # the 3x3 stride-1 kernel also produces the bias gradient
+    fused_bias = True                                # every weight-gradient kernel also produces the bias gradient
     db = torch.full((cout,), 0.5, device=dev()) if fused_bias else None
     ops.wgrad(ops.make_wgrad_desc(nhwc(dy), nhwc(x), dw, cout, cin, ksize=ksize, in_stride=stride, dbias=db))
     ref = w.grad.permute(0, 2, 3, 1).reshape(cout, ksize * ksize, cin)
