@@ -183,9 +183,13 @@ def conv_roofline(peaks, B):
         flops = 2.0 * B * S * S * C * 9 * C
         out[name] = dict(ms=ms, tflops=flops / ms / 1e9, flops=flops)
     top = out["conv3x3_128c_64px"]
-    return {"bound": "tensor", "kernel": "igemm_kernel<128,3> (3x3 conv 128->128 @64x64, batch %d)" % B,
+    return {"bound": "tensor", "kernel": "igemm3_kernel<128,2,2,5,3> (3x3 conv 128->128 @64x64, batch %d)" % B,
             "achieved": top["tflops"], "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": top["tflops"] / peaks["tf_burst"],
-            "traffic": None, "peak_source": peaks["src"] + " bf16 burst", "flops_per_launch": top["flops"],
+            # dram__bytes_read + dram__bytes_write of this kernel and shape, ncu --set full (profiles/r1_ncu_igemm3_128c_summary.json):
+            # 67.5 MB read (= the input once; weights stay in L2) + 19.4 MB written before the kernel ends (the rest of the
+            # 67 MB output is still dirty in L2); algorithmic bytes are 134.5 MB, so nothing is re-read
+            "traffic": 86.83e6, "traffic_unit": "bytes/launch", "peak_source": peaks["src"] + " bf16 burst",
+            "flops_per_launch": top["flops"],
             "other_shapes": {k: round(v["tflops"], 1) for k, v in out.items()}}
 
 

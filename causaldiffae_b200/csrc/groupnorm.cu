@@ -822,7 +822,8 @@ static bool gn_pipe_config(GnParams& p, int B, bool bwd, const void* kernel) {
     double cost = (double)rounds * ((double)per * m + 3000.0 + (S > 1 ? 3000.0 : 0.0));
     cost *= (double)nvp / nvec;
     if ((m * 2) % 32) cost *= 1.3;
-    if (m * 2 < 64) cost *= 1.25;
+    static const int min_row = getenv("CDAE_GN_MIN_ROW") ? atoi(getenv("CDAE_GN_MIN_ROW")) : 64;
+    if (m * 2 < min_row) cost *= 1.25;
     if (cost < best) { best = cost; bestCC = m; bestS = S; bestNcl = (int)ncl; }
   }
   if (!bestCC) return false;

@@ -39,9 +39,10 @@ def main():
                 if u == "ns": x /= 1e3
                 if u == "ms": x *= 1e3
                 d[WANT[h]] = round(x, 3)
-        # any tensor-pipe metric the report carries
-        for h, v in zip(hdr, r):
-            if "tensor" in h and "pct" in h and h not in WANT:
+        for h, v in zip(hdr, r):     # tensor-pipe activity under whatever name this ncu version reports it
+            if h in ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+                     "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_uniform.sum",
+                     "smsp__inst_executed_pipe_tensor.sum", "sm__inst_executed_pipe_tensor.sum"):
                 try:
                     d[h] = round(float(v.replace(",", "")), 2)
                 except ValueError:
