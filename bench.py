@@ -307,15 +307,23 @@ def run_cuda(args):
         loop.run_step(x, dict(cond))
         last["loss"] = float(loop.last_loss)       # D2H read of the step's result
 
+    clocks = ClockSampler(local)
+    clocks.start()                  # nvidia-smi needs ~1 s before its first row (longer on an 8-GPU box): start it early
     for i in range(max(args.warmup, 3)):
         step_dev(i)
-    clocks = ClockSampler(local)
-    clocks.start()
+    t_wait = time.time()
+    while not clocks.rows and time.time() - t_wait < 8.0:      # keep the GPU under load until the sampler is live
+        step_dev(0)
+    clocks.rows.clear()
     ms_step = timed(step_dev, args.steps)
-    clk = clocks.stop()
     for i in range(3):
         step_host(i)
     ms_e2e = timed(step_host, args.steps)
+    if not clocks.rows:             # short runs: sample a little longer under the same load
+        t_wait = time.time()
+        while not clocks.rows and time.time() - t_wait < 3.0:
+            step_dev(0)
+    clk = clocks.stop()
 
     pl = model.engine.plan(B, True)
     launches_per_step = pl.n_fwd_launch + pl.n_bwd_launch + 6     # + q_sample, mse fwd/bwd, zero, pack, adam

@@ -367,6 +367,21 @@ __device__ __forceinline__ uint4 pack_u4(const float* f) {
   h = __floats2bfloat162_rn(f[6], f[7]); r.w = *reinterpret_cast<uint32_t*>(&h);
   return r;
 }
+// packed fp32 pairs (FADD2 / FFMA2, sm_100): the inner loops are issue bound, one instruction per TWO elements helps
+__device__ __forceinline__ void unpack_u4_2(const uint4& v, float2* f) {
+  unpack2(v.x, f[0].x, f[0].y); unpack2(v.y, f[1].x, f[1].y); unpack2(v.z, f[2].x, f[2].y); unpack2(v.w, f[3].x, f[3].y);
+}
+__device__ __forceinline__ uint4 pack_u4_2(const float2* f) {
+  uint4 r;
+  __nv_bfloat162 h;
+  h = __float22bfloat162_rn(f[0]); r.x = *reinterpret_cast<uint32_t*>(&h);
+  h = __float22bfloat162_rn(f[1]); r.y = *reinterpret_cast<uint32_t*>(&h);
+  h = __float22bfloat162_rn(f[2]); r.z = *reinterpret_cast<uint32_t*>(&h);
+  h = __float22bfloat162_rn(f[3]); r.w = *reinterpret_cast<uint32_t*>(&h);
+  return r;
+}
+__device__ __forceinline__ float2 tanh2(float2 h) { return make_float2(tanh_fast(h.x), tanh_fast(h.y)); }
+
 // eight consecutive floats (two 128-bit loads when the address allows)
 __device__ __forceinline__ void load8f(const float* q, bool v4, float* o) {
   if (v4) {
@@ -458,18 +473,21 @@ __global__ void __launch_bounds__(kResThreads, 3) gn_fwd_pipe_kernel(const GnPar
 
     const uint4* sl = reinterpret_cast<const uint4*>(smraw + st * slab_bytes) + sidx;
     float s[8], ss[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { s[k] = 0.f; ss[k] = 0.f; }
     {
+      float2 s2[4], q2[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { s2[k] = make_float2(0.f, 0.f); q2[k] = make_float2(0.f, 0.f); }
       const uint4* s_ = sl;
 #pragma unroll 4
       for (int i = 0; i < nit; ++i) {
-        float f[8];
-        unpack_u4(*s_, f);
+        float2 f[4];
+        unpack_u4_2(*s_, f);
         s_ += RN;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { s[k] += f[k]; ss[k] = fmaf(f[k], f[k], ss[k]); }
+        for (int k = 0; k < 4; ++k) { s2[k] = __fadd2_rn(s2[k], f[k]); q2[k] = __ffma2_rn(f[k], f[k], q2[k]); }
       }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { s[2 * k] = s2[k].x; s[2 * k + 1] = s2[k].y; ss[2 * k] = q2[k].x; ss[2 * k + 1] = q2[k].y; }
     }
     warp_partials(wsum, p.CC, p.nvp, active, cl, s, ss);
     __syncthreads();
@@ -504,25 +522,25 @@ __global__ void __launch_bounds__(kResThreads, 3) gn_fwd_pipe_kernel(const GnPar
     __syncthreads();
 
     if (active) {
-      float A[8], Bc[8];
+      float2 A[4], Bc[4];
       *reinterpret_cast<float4*>(A) = *reinterpret_cast<const float4*>(ab + cl);
-      *reinterpret_cast<float4*>(A + 4) = *reinterpret_cast<const float4*>(ab + cl + 4);
+      *reinterpret_cast<float4*>(A + 2) = *reinterpret_cast<const float4*>(ab + cl + 4);
       *reinterpret_cast<float4*>(Bc) = *reinterpret_cast<const float4*>(ab + p.CC + cl);
-      *reinterpret_cast<float4*>(Bc + 4) = *reinterpret_cast<const float4*>(ab + p.CC + cl + 4);
+      *reinterpret_cast<float4*>(Bc + 2) = *reinterpret_cast<const float4*>(ab + p.CC + cl + 4);
       __nv_bfloat16* y = p.y + (size_t)b * p.HW * p.C + chunk * p.CC + cl + (size_t)(p0 + row) * p.C;
       const size_t ystep = (size_t)p.R * p.C;
       const uint4* s_ = sl;
 #pragma unroll 2
       for (int i = 0; i < nit; ++i) {
-        float f[8];
-        unpack_u4(*s_, f);
+        float2 f[4];
+        unpack_u4_2(*s_, f);
         s_ += RN;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float h = fmaf(f[k], A[k], Bc[k]);
-          f[k] = SILU ? fmaf(h, tanh_fast(h), h) : h;
+        for (int k = 0; k < 4; ++k) {
+          const float2 h = __ffma2_rn(f[k], A[k], Bc[k]);
+          f[k] = SILU ? __ffma2_rn(h, tanh2(h), h) : h;
         }
-        *reinterpret_cast<uint4*>(y) = pack_u4(f);
+        *reinterpret_cast<uint4*>(y) = pack_u4_2(f);
         y += ystep;
       }
     }
@@ -537,7 +555,7 @@ __global__ void __launch_bounds__(kResThreads, 3) gn_fwd_pipe_kernel(const GnPar
 //   K2' = rstd*s1/n - mean*rstd^2*s2/n.
 // dy is prefetched into the ring (cp.async) and overwritten in place by du; x is streamed through registers in the
 // reduction pass and read again in the apply pass (an L2 hit: the same CTA touched it microseconds earlier).
-// cst rows: 0 aG/2 (aG when !SILU) | 1 bH/2 | 2 G (gamma*(1+scale)) | 3 K1 | 4 K2' | 5 K3'
+// cst rows: 0 aG/2 (aG when !SILU) | 1 bH/2 | 2 G (gamma*(1+scale)) | 3 K1 | 4 -K2' | 5 -K3'
 template <bool SILU>
 __global__ void __launch_bounds__(kResThreads, 3) gn_bwd_pipe_kernel(const GnParams p) {
   extern __shared__ __align__(16) unsigned char smraw[];
@@ -619,31 +637,34 @@ __global__ void __launch_bounds__(kResThreads, 3) gn_bwd_pipe_kernel(const GnPar
 #pragma unroll
     for (int k = 0; k < 8; ++k) { P[k] = 0.f; Qx[k] = 0.f; }
     if (active) {
-      float aGh[8], bHh[8];      // halved affine: h = u/2 = x*aGh + bHh
+      float2 aGh[4], bHh[4];      // halved affine: h = u/2 = x*aGh + bHh
       if (SILU) {
         *reinterpret_cast<float4*>(aGh) = *reinterpret_cast<const float4*>(cst + cl);
-        *reinterpret_cast<float4*>(aGh + 4) = *reinterpret_cast<const float4*>(cst + cl + 4);
+        *reinterpret_cast<float4*>(aGh + 2) = *reinterpret_cast<const float4*>(cst + cl + 4);
         *reinterpret_cast<float4*>(bHh) = *reinterpret_cast<const float4*>(cst + p.CC + cl);
-        *reinterpret_cast<float4*>(bHh + 4) = *reinterpret_cast<const float4*>(cst + p.CC + cl + 4);
+        *reinterpret_cast<float4*>(bHh + 2) = *reinterpret_cast<const float4*>(cst + p.CC + cl + 4);
       }
+      float2 P2[4], Q2[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { P2[k] = make_float2(0.f, 0.f); Q2[k] = make_float2(0.f, 0.f); }
+      const float2 kM1 = make_float2(-1.f, -1.f), kHalf = make_float2(0.5f, 0.5f);
       const __nv_bfloat16* xg = xg0 + 2 * xstep;
       uint4* s_ = sl;
       auto one = [&](const uint4& vx, uint4* dst) {
-        float f[8], d[8];
-        unpack_u4(vx, f); unpack_u4(*dst, d);
+        float2 f[4], d[4];
+        unpack_u4_2(vx, f); unpack_u4_2(*dst, d);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          float du = d[k];
+        for (int k = 0; k < 4; ++k) {
           if (SILU) {
-            const float h = fmaf(f[k], aGh[k], bHh[k]);
-            const float t = tanh_fast(h);
-            const float w = fmaf(h, fmaf(-t, t, 1.f), t);        // t + h*(1 - t^2)
-            du = d[k] * fmaf(0.5f, w, 0.5f);
+            const float2 h = __ffma2_rn(f[k], aGh[k], bHh[k]);
+            const float2 t = tanh2(h);
+            const float2 q = __ffma2_rn(t, t, kM1);                        // t^2 - 1
+            const float2 w = __ffma2_rn(__fmul2_rn(h, kM1), q, t);         // t + h*(1 - t^2)
+            d[k] = __fmul2_rn(d[k], __ffma2_rn(w, kHalf, kHalf));
           }
-          P[k] += du; Qx[k] = fmaf(du, f[k], Qx[k]);
-          d[k] = du;
+          P2[k] = __fadd2_rn(P2[k], d[k]); Q2[k] = __ffma2_rn(d[k], f[k], Q2[k]);
         }
-        if (SILU) *dst = pack_u4(d);
+        if (SILU) *dst = pack_u4_2(d);
       };
       int i = 0;
       for (; i + 2 <= nit; i += 2) {       // software pipeline: the loads of pixels i+2, i+3 fly while i, i+1 are reduced
@@ -655,6 +676,8 @@ __global__ void __launch_bounds__(kResThreads, 3) gn_bwd_pipe_kernel(const GnPar
         xg += 2 * xstep; s_ += 2 * RN;
       }
       if (i < nit) one(vxa, s_);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { P[2 * k] = P2[k].x; P[2 * k + 1] = P2[k].y; Qx[2 * k] = Q2[k].x; Qx[2 * k + 1] = Q2[k].y; }
     }
     warp_partials(wsum, p.CC, p.nvp, active, cl, P, Qx);
     __syncthreads();
@@ -683,8 +706,8 @@ __global__ void __launch_bounds__(kResThreads, 3) gn_bwd_pipe_kernel(const GnPar
       }
       const float K3 = rs * rs * s2 * inv_n;
       cst[3 * p.CC + threadIdx.x] = rs * G;
-      cst[4 * p.CC + threadIdx.x] = rs * s1 * inv_n - m * K3;
-      cst[5 * p.CC + threadIdx.x] = K3;
+      cst[4 * p.CC + threadIdx.x] = -(rs * s1 * inv_n - m * K3);     // stored negated: dx = K1*du + (x*(-K3') + (-K2'))
+      cst[5 * p.CC + threadIdx.x] = -K3;
       if (rank == 0) {
         const int ch = c0 + threadIdx.x;
         const float Pc = tot[threadIdx.x], Qc = rs * (tot[p.CC + threadIdx.x] - m * Pc);
@@ -700,13 +723,13 @@ __global__ void __launch_bounds__(kResThreads, 3) gn_bwd_pipe_kernel(const GnPar
     __syncthreads();
 
     if (active) {
-      float K1[8], K2[8], K3[8];
+      float2 K1[4], K2[4], K3[4];
       *reinterpret_cast<float4*>(K1) = *reinterpret_cast<const float4*>(cst + 3 * p.CC + cl);
-      *reinterpret_cast<float4*>(K1 + 4) = *reinterpret_cast<const float4*>(cst + 3 * p.CC + cl + 4);
+      *reinterpret_cast<float4*>(K1 + 2) = *reinterpret_cast<const float4*>(cst + 3 * p.CC + cl + 4);
       *reinterpret_cast<float4*>(K2) = *reinterpret_cast<const float4*>(cst + 4 * p.CC + cl);
-      *reinterpret_cast<float4*>(K2 + 4) = *reinterpret_cast<const float4*>(cst + 4 * p.CC + cl + 4);
+      *reinterpret_cast<float4*>(K2 + 2) = *reinterpret_cast<const float4*>(cst + 4 * p.CC + cl + 4);
       *reinterpret_cast<float4*>(K3) = *reinterpret_cast<const float4*>(cst + 5 * p.CC + cl);
-      *reinterpret_cast<float4*>(K3 + 4) = *reinterpret_cast<const float4*>(cst + 5 * p.CC + cl + 4);
+      *reinterpret_cast<float4*>(K3 + 2) = *reinterpret_cast<const float4*>(cst + 5 * p.CC + cl + 4);
       const bool acc = (p.accumulate_dx >> (in0 ? 0 : 1)) & 1;
       const __nv_bfloat16* xg = xg0;
       __nv_bfloat16* og = (in0 ? p.dx0 + (size_t)b * p.HW * p.C0 + c : p.dx1 + (size_t)b * p.HW * p.C1 + (c - p.C0)) +
@@ -714,23 +737,23 @@ __global__ void __launch_bounds__(kResThreads, 3) gn_bwd_pipe_kernel(const GnPar
       const __nv_bfloat16* ag = hasadd ? p.dadd + (size_t)b * p.HW * p.C + c + (size_t)(p0 + row) * p.C : nullptr;
       const uint4* s_ = sl;
       auto one = [&](const uint4& vx, const uint4& vdu, const uint4& vo, const uint4& va, __nv_bfloat16* dst) {
-        float f[8], d[8], o[8];
-        unpack_u4(vx, f); unpack_u4(vdu, d);
+        float2 f[4], d[4], o[4];
+        unpack_u4_2(vx, f); unpack_u4_2(vdu, d);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = fmaf(K1[k], d[k], -fmaf(f[k], K3[k], K2[k]));
+        for (int k = 0; k < 4; ++k) o[k] = __ffma2_rn(K1[k], d[k], __ffma2_rn(f[k], K3[k], K2[k]));   // K2, K3 are negated
         if (acc) {
-          float t[8];
-          unpack_u4(vo, t);
+          float2 t[4];
+          unpack_u4_2(vo, t);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) o[k] += t[k];
+          for (int k = 0; k < 4; ++k) o[k] = __fadd2_rn(o[k], t[k]);
         }
         if (hasadd) {
-          float t[8];
-          unpack_u4(va, t);
+          float2 t[4];
+          unpack_u4_2(va, t);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) o[k] += t[k];
+          for (int k = 0; k < 4; ++k) o[k] = __fadd2_rn(o[k], t[k]);
         }
-        *reinterpret_cast<uint4*>(dst) = pack_u4(o);
+        *reinterpret_cast<uint4*>(dst) = pack_u4_2(o);
       };
       const uint4 z = make_uint4(0u, 0u, 0u, 0u);
       int i = 0;

@@ -19,8 +19,7 @@ def encode(model, x, do_var=None, do_value=0.0, on="mu", A=None):
         mu[:, do_var * d:(do_var + 1) * d] = do_value
     if model.causal_modeling:
         At = th.as_tensor(A if A is not None else model.A, dtype=th.float32, device=mu.device)
-        z_pre = model.causal_mask.causal_masking(mu, At)
-        z_post = model.causal_mask.nonlinearity_add_back_noise(mu, z_pre)
+        z_post = model.causal_mask(mu, At)       # causal_masking + nonlinearity_add_back_noise (one fused kernel)
     else:
         z_post = mu
     if do_var is not None and on == "z_post":
