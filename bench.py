@@ -132,7 +132,7 @@ def cpu_baseline_sample(batch):
     from oracle import model as om, diffusion as od, schedules
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    Bs, n = 4, 3
+    Bs, n = 4, 16       # ~10 s of CPU work on the GPU box's host cores
     cfg = om.config_from_flags(**FLAGS, A=PENDULUM)
     sd = om.seeded_state_dict(cfg, seed=0)
     diff = od.Diffusion(steps=1000)
@@ -326,7 +326,7 @@ def run_cuda(args):
     clk = clocks.stop()
 
     pl = model.engine.plan(B, True)
-    launches_per_step = pl.n_fwd_launch + pl.n_bwd_launch + 6     # + q_sample, mse fwd/bwd, zero, pack, adam
+    launches_per_step = pl.n_fwd_launch + pl.n_bwd_launch + 9     # + q_sample, mse fwd/bwd, zero, pack, adam, DAG layer fwd/bwd/finish
     value = B * world / (ms_step / 1000)
     e2e = B * world / (ms_e2e / 1000)
     train_flops = 3 * FWD_GFLOP_PER_IMG * 1e9 * B
