@@ -31,7 +31,8 @@ class IgemmDesc(C.Structure):
                 ("sps", C.c_int32), ("ooh", C.c_int32), ("oow", C.c_int32),
                 ("bias", C.c_void_p), ("bias2", C.c_void_p),
                 ("resid", C.c_void_p), ("ldr", C.c_int32),
-                ("bn", C.c_int32)]
+                ("bn", C.c_int32),
+                ("stats", C.c_void_p)]
 
 
 class WgradDesc(C.Structure):
@@ -69,6 +70,7 @@ _SIGS = {
     "cdae_zero_insert2x": ([P, P, I32, I32, I32, I32, P], C.c_int),
     "cdae_colsum": ([P, P, I64, I32, I32, P], C.c_int),
     "cdae_gn_fwd": ([P, I32, P, I32, I32, I32, P, P, P, I32, I32, I32, P, P, P, P], C.c_int),
+    "cdae_gn_apply_fwd": ([P, I32, P, P, I32, P, I32, I32, P, P, P, I32, I32, I32, P, P, P, P], C.c_int),
     "cdae_gn_bwd": ([P, P, I32, P, I32, I32, I32, P, P, P, I32, I32, I32, P, P, P, P, P, I32, P, P, P, P], C.c_int),
     "cdae_igemm": ([C.POINTER(IgemmDesc), P], C.c_int),
     "cdae_wgrad": ([C.POINTER(WgradDesc), P], C.c_int),

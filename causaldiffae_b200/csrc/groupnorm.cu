@@ -779,6 +779,103 @@ __global__ void __launch_bounds__(kResThreads, 3) gn_bwd_pipe_kernel(const GnPar
   if (p.S > 1) cluster.sync();   // no CTA exits while a peer may still read its published sums
 }
 
+
+// ------------------------------------------------------------------------------------------------ streaming forward
+// When the producing convolution's epilogue has already accumulated per-(image, channel) sum / sum of squares
+// (cdae_igemm_desc.stats), the forward GroupNorm needs no reduction pass and nothing resident on chip: every CTA
+// rebuilds the group statistics of its sample from <= 1024 channel sums (an L2 hit), folds gamma / beta / FiLM into two
+// per-channel constants in shared memory and then streams its pixel range once: 128-bit loads, four rows in flight per
+// thread, packed FFMA2, one MUFU per element (tanh form of SiLU), 128-bit stores.  2 B read + 2 B written per element,
+// no clusters, no barriers in the streaming loop.
+struct GnApplyParams {
+  const __nv_bfloat16* x0; const __nv_bfloat16* x1;
+  const float* st0; const float* st1;      // fp32 [B][C0][2], [B][C1][2]
+  int C0, C1, C, HW;
+  const float* gamma; const float* beta; const float* film; int film_ld, film_off;
+  __nv_bfloat16* y; float* mean; float* rstd;
+  int ppc;                                  // pixels per CTA
+  int nvec, R;                              // 16 B vectors per pixel row; pixel rows per CTA pass (threads >= nvec*R idle)
+};
+constexpr int kApplyThreads = 256;
+constexpr int kApplyUnroll = 4;
+
+template <bool SILU>
+__global__ void __launch_bounds__(kApplyThreads, 4) gn_apply_fwd_kernel(const GnApplyParams p) {
+  extern __shared__ __align__(16) float sm_apply[];
+  float* cs = sm_apply;                 // [C] channel sums   -> later A (scale)
+  float* cq = sm_apply + p.C;           // [C] channel sumsq  -> later B (shift)
+  float* gm = sm_apply + 2 * p.C;       // [32] group mean
+  float* gr = gm + kGroups;             // [32] group rstd
+  const int b = blockIdx.y;
+  const int cpg = p.C / kGroups;
+  for (int c = threadIdx.x; c < p.C; c += kApplyThreads) {
+    const float2 v = c < p.C0 ? __ldg(reinterpret_cast<const float2*>(p.st0) + (size_t)b * p.C0 + c)
+                              : __ldg(reinterpret_cast<const float2*>(p.st1) + (size_t)b * p.C1 + (c - p.C0));
+    cs[c] = v.x; cq[c] = v.y;
+  }
+  __syncthreads();
+  if (threadIdx.x < kGroups) {
+    float a = 0.f, q = 0.f;
+    for (int k = 0; k < cpg; ++k) { a += cs[threadIdx.x * cpg + k]; q += cq[threadIdx.x * cpg + k]; }
+    const float inv_n = 1.f / ((float)cpg * (float)p.HW);
+    const float m = a * inv_n;
+    const float var = fmaxf(q * inv_n - m * m, 0.f);
+    const float rs = rsqrtf(var + 1e-5f);
+    gm[threadIdx.x] = m; gr[threadIdx.x] = rs;
+    if (blockIdx.x == 0) { p.mean[b * kGroups + threadIdx.x] = m; p.rstd[b * kGroups + threadIdx.x] = rs; }
+  }
+  __syncthreads();
+  const float half = SILU ? 0.5f : 1.f;
+  for (int c = threadIdx.x; c < p.C; c += kApplyThreads) {
+    float gk = __ldg(p.gamma + c), hk = __ldg(p.beta + c);
+    if (p.film) {
+      const float* fr = p.film + (size_t)b * p.film_ld + p.film_off;
+      const float sc = __ldg(fr + c), sh = __ldg(fr + p.C + c);
+      gk = fmaf(gk, sc, gk); hk = fmaf(hk, sc, hk) + sh;
+    }
+    const int g = c / cpg;
+    const float m = gm[g], rs = gr[g];
+    cs[c] = half * rs * gk;
+    cq[c] = half * (hk - m * rs * gk);
+  }
+  __syncthreads();
+  const int vec = threadIdx.x % p.nvec, row = threadIdx.x / p.nvec;
+  if (row >= p.R) return;
+  const int cl = vec * 8;
+  float2 A[4], Bc[4];
+  *reinterpret_cast<float4*>(A) = *reinterpret_cast<const float4*>(cs + cl);
+  *reinterpret_cast<float4*>(A + 2) = *reinterpret_cast<const float4*>(cs + cl + 4);
+  *reinterpret_cast<float4*>(Bc) = *reinterpret_cast<const float4*>(cq + cl);
+  *reinterpret_cast<float4*>(Bc + 2) = *reinterpret_cast<const float4*>(cq + cl + 4);
+  const bool in0 = cl < p.C0;
+  const int xpitch = in0 ? p.C0 : p.C1;
+  const __nv_bfloat16* xb = in0 ? p.x0 + (size_t)b * p.HW * p.C0 + cl : p.x1 + (size_t)b * p.HW * p.C1 + (cl - p.C0);
+  __nv_bfloat16* yb = p.y + (size_t)b * p.HW * p.C + cl;
+  const int p0 = blockIdx.x * p.ppc, p1 = min(p.HW, p0 + p.ppc);
+  for (int pix = p0 + row; pix < p1; pix += kApplyUnroll * p.R) {
+    uint4 v[kApplyUnroll];
+#pragma unroll
+    for (int k = 0; k < kApplyUnroll; ++k) {
+      const int pk = pix + k * p.R;
+      if (pk < p1) v[k] = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)pk * xpitch));
+    }
+#pragma unroll
+    for (int k = 0; k < kApplyUnroll; ++k) {
+      const int pk = pix + k * p.R;
+      if (pk < p1) {
+        float2 f[4];
+        unpack_u4_2(v[k], f);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 h = __ffma2_rn(f[e], A[e], Bc[e]);
+          f[e] = SILU ? __ffma2_rn(h, tanh2(h), h) : h;
+        }
+        *reinterpret_cast<uint4*>(yb + (size_t)pk * p.C) = pack_u4_2(f);
+      }
+    }
+  }
+}
+
 static inline size_t gn_pipe_smem(const GnParams& p, bool bwd) {
   const size_t slabs = 2 * (size_t)p.per * p.CC * 2;
   const size_t stats = bwd ? sizeof(float) * ((size_t)kResWarps * 2 * p.CC + 4 * p.CC + 2 * p.CC + 6 * p.CC)
@@ -938,6 +1035,39 @@ extern "C" int cdae_gn_fwd(const void* x0, int C0, const void* x1, int C1, int B
   const size_t smem = sizeof(float) * (2 * p.C + 4 * kGroups);
   if (wide) return gn_launch(gn_fwd_kernel<8, 4>, p, B, S, smem, (cudaStream_t)s, "gn_fwd_kernel");
   return gn_launch(gn_fwd_kernel<4, 4>, p, B, S, smem, (cudaStream_t)s, "gn_fwd_kernel");
+}
+
+extern "C" int cdae_gn_apply_fwd(const void* x0, int C0, const float* stats0, const void* x1, int C1, const float* stats1,
+                                 int B, int HW, const float* gamma, const float* beta, const float* film, int film_ld,
+                                 int film_off, int silu, void* y, float* mean, float* rstd, cdae_stream s) {
+  CDAE_CHECK_ARG(x0 && stats0 && gamma && beta && y && mean && rstd && (C1 == 0 || (x1 && stats1)), "gn_apply_fwd: null pointer");
+  if (B == 0 || HW == 0) return CDAE_OK;
+  GnApplyParams p;
+  memset(&p, 0, sizeof(p));
+  p.x0 = (const __nv_bfloat16*)x0; p.x1 = (const __nv_bfloat16*)x1; p.st0 = stats0; p.st1 = stats1;
+  p.C0 = C0; p.C1 = C1; p.C = C0 + C1; p.HW = HW;
+  p.gamma = gamma; p.beta = beta; p.film = film; p.film_ld = film_ld; p.film_off = film_off;
+  p.y = (__nv_bfloat16*)y; p.mean = mean; p.rstd = rstd;
+  CDAE_CHECK_SHAPE(p.C % kGroups == 0 && C0 % 8 == 0 && C1 % 8 == 0, "gn_apply_fwd: C0=%d C1=%d (C %% 32, C0/C1 %% 8)", C0, C1);
+  CDAE_CHECK_SHAPE(p.C / 8 <= kApplyThreads, "gn_apply_fwd: C=%d too large", p.C);
+  CDAE_CHECK_ARG(aligned16(x0) && aligned16(y) && (!x1 || aligned16(x1)) && (reinterpret_cast<uintptr_t>(stats0) & 7) == 0 &&
+                 (!stats1 || (reinterpret_cast<uintptr_t>(stats1) & 7) == 0), "gn_apply_fwd: misaligned pointer");
+  CDAE_CHECK_SHAPE(B <= 65535, "gn_apply_fwd: batch %d too large", B);
+  p.nvec = p.C / 8;
+  p.R = kApplyThreads / p.nvec;
+  // ~48 KB of input per CTA (a multiple of the rows one pass covers), but enough CTAs to fill the chip twice
+  int ppc = (48 * 1024) / (p.C * 2);
+  ppc = ppc / (p.R * kApplyUnroll) * (p.R * kApplyUnroll);
+  if (ppc < p.R * kApplyUnroll) ppc = p.R * kApplyUnroll;
+  while (ppc > p.R * kApplyUnroll && (int64_t)B * ((HW + ppc - 1) / ppc) < 2 * 4 * kNumSMs) ppc -= p.R * kApplyUnroll;
+  if (ppc > HW) ppc = HW;
+  p.ppc = ppc;
+  dim3 grid((unsigned)((HW + ppc - 1) / ppc), (unsigned)B);
+  const size_t smem = sizeof(float) * (2 * (size_t)p.C + 2 * kGroups);
+  if (silu) gn_apply_fwd_kernel<true><<<grid, kApplyThreads, smem, (cudaStream_t)s>>>(p);
+  else gn_apply_fwd_kernel<false><<<grid, kApplyThreads, smem, (cudaStream_t)s>>>(p);
+  CDAE_CHECK_LAUNCH("gn_apply_fwd_kernel");
+  return CDAE_OK;
 }
 
 extern "C" int cdae_gn_bwd(const void* dy, const void* x0, int C0, const void* x1, int C1, int B, int HW,

@@ -75,6 +75,7 @@ struct alignas(64) IgemmKParams {
   void* out;
   const float* bias;
   const float* bias2;
+  float* stats;      // optional fp32 [Nimg][cout][2]: per-(image, channel) sum / sum of squares of the stored bf16 output
   int nboxes, ntn;   // number of 128-pixel boxes and of N tiles
   // halo kernel (3x3 stride 1): K is walked source-chunk-major; each 64-channel chunk brings ONE halo tile per box
   struct { int src, c0, nchunk, ntap, wk0; } hs[8];
@@ -98,6 +99,7 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmKParams& p, const EpiC
   constexpr int SLABW = BN < 64 ? BN : 64;                    // channels per output slab
   constexpr int kSlabStride = 128 * 128;                      // staging buffers are 16 KB apart (1024 B aligned)
   constexpr uint32_t kAccCols = MT * BN;
+  static_assert(NS >= 3, "the statistics pass reads slab i while slab i+1 is produced: buffer i must not be recycled before the next named barrier");
   const uint32_t tmem_base = cx.tmem_base, stg_base = cx.stg_base;
   const int total_tiles = cx.total_tiles, boxes_per_img = cx.boxes_per_img;
   auto tfull_bar = [&](int a) { return cx.tfull0 + 8u * a; };
@@ -124,6 +126,16 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmKParams& p, const EpiC
         if (box >= p.nboxes) break;
         const int w0 = (box % p.tilesW) * p.BW, h0 = ((box / p.tilesW) % p.tilesH) * p.BH;
         const int nn0 = (box / boxes_per_img) * p.BNI;
+        // GroupNorm statistics of the consumer (gn_apply_fwd_kernel) ride along: which of this warp's 32 pixel rows
+        // are real output pixels, and the image they belong to (BW*BH >= 32, checked on the host)
+        uint32_t vmask = 0;
+        int nimg = 0;
+        if (SLABW == 64 && p.stats != nullptr) {
+          const int pb = p.BW * p.BH;
+          const bool row_ok = (nn0 + r / pb < p.Nimg) && (h0 + (r / p.BW) % p.BH < p.OHt) && (w0 + r % p.BW < p.OWt);
+          vmask = __ballot_sync(0xffffffffu, row_ok);
+          nimg = nn0 + (q * 32) / pb;
+        }
 #pragma unroll 1
         for (int c = 0; c < BN; c += SLABW) {
           const int co0 = n0 + c;
@@ -177,6 +189,24 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmKParams& p, const EpiC
             bulk_commit();
             bulk_wait_read<NS - 2>();                 // every store but the newest NS-2 has finished reading smem
             if (sidx >= NS - 2) mbar_arrive(sfree_bar((sidx - (NS - 2)) % NS));
+          }
+          if (SLABW == 64 && vmask != 0) {
+            // column sums of the slab as stored (bf16): lane = channel pair, this warp's 32 rows; one 128-bit red
+            // per lane into stats[nimg][co0 + 2*lane .. +1][sum, sumsq].  The buffer is recycled no earlier than the
+            // named barrier of a later slab, i.e. after every thread has left this loop.
+            const uint32_t sb = stg_base + buf * kSlabStride + (uint32_t)(q * 32) * 128u + (uint32_t)((lane & 3) << 2);
+            const uint32_t cj = (uint32_t)(lane >> 2);
+            float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) {
+              uint32_t u = lds32(sb + (uint32_t)i * 128u + ((cj ^ (uint32_t)(i & 7)) << 4));
+              if (!((vmask >> i) & 1u)) u = 0u;
+              const float2 f = make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+              s2 = __fadd2_rn(s2, f);
+              q2 = __ffma2_rn(f, f, q2);
+            }
+            float* dst = p.stats + ((size_t)nimg * p.cout + co0 + 2 * lane) * 2;
+            atomicAdd(reinterpret_cast<float4*>(dst), make_float4(s2.x, q2.x, s2.y, q2.y));
           }
           ++sidx;
         }
@@ -656,6 +686,10 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
   kp.in_stride = es; kp.Nimg = d->N; kp.OHt = OHt; kp.OWt = OWt;
   kp.OH = d->OH; kp.OW = d->OW; kp.cout = d->cout; kp.out_mode = d->out_mode;
   kp.out = d->out; kp.bias = d->bias; kp.bias2 = d->bias2; kp.has_resid = d->resid != nullptr;
+  kp.stats = d->stats;
+  CDAE_CHECK_SHAPE(!d->stats || (kp.out_mode == 0 && d->cout % 64 == 0 && kp.BW * kp.BH >= 32 &&
+                                 (reinterpret_cast<uintptr_t>(d->stats) & 15) == 0),
+                   "igemm: channel statistics need NHWC output, cout %% 64 == 0 and >= 32 output pixels per image");
   CDAE_CHECK_SHAPE(kp.out_mode == 1 || (d->cout % 8 == 0 && d->ldo % 8 == 0), "igemm: NHWC output needs cout, ldo %% 8 == 0");
   CDAE_CHECK_SHAPE(kp.out_mode == 1 || (d->OH == OHt && d->OW == OWt), "igemm: output dims %dx%d do not match the tile grid %dx%d",
                    d->OH, d->OW, OHt, OWt);
@@ -680,6 +714,7 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
     else if (c >= 192 && c % 192 == 0 && (int64_t)nboxes * (c / 192) >= kNumSMs) bn = 192;
     else bn = c >= 128 ? 128 : c >= 64 ? 64 : c > 16 ? 32 : 16;
   }
+  CDAE_CHECK_SHAPE(!d->stats || bn >= 64, "igemm: channel statistics need an N tile of at least 64 (bn %d)", bn);
   const int ntn = (d->cout + bn - 1) / bn;
   if (bn <= 128 && (int64_t)((nboxes + 1) / 2) * ntn >= kNumSMs) mt = 2;
   {

@@ -73,6 +73,11 @@ __device__ __forceinline__ bf16x8 lds8(uint32_t addr) {
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr) : "memory");
   return *reinterpret_cast<bf16x8*>(&u);
 }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t u;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(addr) : "memory");
+  return u;
+}
 __device__ __forceinline__ void sts8(uint32_t addr, const bf16x8& v) {
   const uint4 u = *reinterpret_cast<const uint4*>(&v);
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");

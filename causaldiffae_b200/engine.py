@@ -25,6 +25,8 @@ from ._lib import PackEntry
 
 bf16 = th.bfloat16
 USE_GRAPHS = os.environ.get("CDAE_GRAPHS", "1") != "0"
+# GroupNorm statistics from the producing conv's epilogue + one streaming normalise pass (0: reduce inside the GN kernel)
+FUSED_GN_STATS = os.environ.get("CDAE_FUSED_GN_STATS", "1") != "0"
 
 
 def _round_up(v, m):
@@ -52,6 +54,7 @@ class T:
         self.t = plan.alloc(shape)
         self.g = None
         self.g_written = False
+        self.stats = None       # fp32 [B, C, 2] channel sums written by the producing conv's epilogue (GroupNorm input)
 
     def grad(self):
         if self.g is None:
@@ -74,11 +77,29 @@ class Plan:
         self.fwd_graph = self.bwd_graph = None
         self.runs = 0
         self.n_fwd_launch = self.n_bwd_launch = 0
+        # per-(image, channel) GroupNorm sums accumulated by conv epilogues: carved from a few big chunks that the
+        # first node of the forward graph zeroes
+        self.stat_chunks, self._stat_used = [], 0
+        self.add_fwd(self._zero_stats, 0)
 
     def alloc(self, shape, dtype=bf16):
         t = th.empty(shape, device=self.dev, dtype=dtype)
         self.bufs.append(t)
         return t
+
+    def alloc_stats(self, B, C):
+        n = B * C * 2
+        if not self.stat_chunks or self._stat_used + n > self.stat_chunks[-1].numel():
+            self.stat_chunks.append(th.zeros(max(n, 1 << 21), device=self.dev, dtype=th.float32))
+            self._stat_used = 0
+            self.n_fwd_launch += 1
+        v = self.stat_chunks[-1][self._stat_used:self._stat_used + n].view(B, C, 2)
+        self._stat_used += (n + 3) // 4 * 4
+        return v
+
+    def _zero_stats(self):
+        for c in self.stat_chunks:
+            ops.zero_(c)
 
     def add_fwd(self, fn, n=1):
         self.fwd.append(fn); self.n_fwd_launch += n
@@ -325,8 +346,9 @@ class Engine:
         return self.grad_of(p)
 
     def plan_conv(self, pl, cw, srcs, out, ksize, stride=1, resid=None, skip=None, skip_srcs=None, out_mode=0,
-                  need_dgrad=True):
-        """out = conv_ksize(concat(srcs)) + bias [+ resid] [+ conv1x1_skip(concat(skip_srcs)) + bias_skip]"""
+                  need_dgrad=True, stats=False):
+        """out = conv_ksize(concat(srcs)) + bias [+ resid] [+ conv1x1_skip(concat(skip_srcs)) + bias_skip]
+        stats: `out` feeds a GroupNorm - let the epilogue accumulate its per-(image, channel) sums (out.stats)."""
         chans = [s.shape[3] for s in srcs]
         segs, K = ops.conv_segments(chans, ksize)
         all_srcs = list(srcs)
@@ -336,9 +358,13 @@ class Engine:
             segs += ssegs
             all_srcs += list(skip_srcs)
             bias2 = skip.bias
+        st = None
+        if stats and FUSED_GN_STATS and out_mode == 0 and cw.cout % 64 == 0 and cw.cout == out.shape[3] and \
+                out.shape[1] * out.shape[2] >= 32:
+            st = out.stats = pl.alloc_stats(out.shape[0], cw.cout)
         d = ops.make_igemm_desc([s.t for s in all_srcs], segs, cw.fwd, out if out_mode == 1 else out.t, cw.cout,
                                 in_stride=stride, bias=cw.bias, bias2=bias2, resid=resid.t if resid is not None else None,
-                                out_mode=out_mode)
+                                out_mode=out_mode, stats=st)
         pl.add_fwd(lambda: ops.igemm(d))
         return chans
 
@@ -383,6 +409,18 @@ class Engine:
                 off += c
         return fns
 
+    def plan_gn_fwd(self, pl, x0, x1, gn, out, st, film=None, film_off=0, silu=True):
+        """out = [SiLU](FiLM(GroupNorm32(concat(x0, x1)))) (ref nn.py:430-437, unet.py:185-198); st = (mean, rstd) [B,32].
+        Streaming kernel when every source carries channel sums from its producer, reducing kernel otherwise."""
+        x1t = x1.t if x1 is not None else None
+        if x0.stats is not None and (x1 is None or x1.stats is not None):
+            s1 = x1.stats if x1 is not None else None
+            pl.add_fwd(lambda: ops.gn_apply_fwd(x0.t, x0.stats, gn.weight, gn.bias, x1=x1t, stats1=s1, film=film,
+                                                film_off=film_off, silu=silu, out=out.t, mean=st[0], rstd=st[1]))
+        else:
+            pl.add_fwd(lambda: ops.gn_fwd(x0.t, gn.weight, gn.bias, x1=x1t, film=film, film_off=film_off, silu=silu,
+                                          out=out.t, mean=st[0], rstd=st[1]))
+
     # ------------------------------------------------------------------ layer planners
     def plan_resblock(self, pl, rb, x0, x1, film, dfilm):
         B, H, W = x0.shape[:3]
@@ -397,15 +435,14 @@ class Engine:
         st1 = (pl.alloc((B, 32), th.float32), pl.alloc((B, 32), th.float32))
         st2 = (pl.alloc((B, 32), th.float32), pl.alloc((B, 32), th.float32))
         x1t = x1.t if x1 is not None else None
-        pl.add_fwd(lambda: ops.gn_fwd(x0.t, gn1.weight, gn1.bias, x1=x1t, silu=True, out=a1.t, mean=st1[0], rstd=st1[1]))
-        self.plan_conv(pl, cw1, [a1], h1, 3)
-        pl.add_fwd(lambda: ops.gn_fwd(h1.t, gn2.weight, gn2.bias, film=film, film_off=foff, silu=True, out=a2.t,
-                                      mean=st2[0], rstd=st2[1]))
+        self.plan_gn_fwd(pl, x0, x1, gn1, a1, st1)
+        self.plan_conv(pl, cw1, [a1], h1, 3, stats=True)
+        self.plan_gn_fwd(pl, h1, None, gn2, a2, st2, film=film, film_off=foff)
         srcs_x = [x0] + ([x1] if x1 is not None else [])
         if has_skip:
-            self.plan_conv(pl, cw2, [a2], out, 3, skip=sk, skip_srcs=srcs_x)
+            self.plan_conv(pl, cw2, [a2], out, 3, skip=sk, skip_srcs=srcs_x, stats=True)
         else:
-            self.plan_conv(pl, cw2, [a2], out, 3, resid=x0)
+            self.plan_conv(pl, cw2, [a2], out, 3, resid=x0, stats=True)
         if pl.train:
             def build_bwd():
                 fns = []
@@ -458,11 +495,11 @@ class Engine:
         st = (pl.alloc((B, 32), th.float32), pl.alloc((B, 32), th.float32))
         lse = pl.alloc((B, heads, Tn), th.float32)
         dsum = pl.alloc((B, heads, Tn), th.float32) if pl.train else None
-        pl.add_fwd(lambda: ops.gn_fwd(x.t, ab.norm.weight, ab.norm.bias, silu=False, out=n.t, mean=st[0], rstd=st[1]))
+        self.plan_gn_fwd(pl, x, None, ab.norm, n, st, silu=False)
         self.plan_conv(pl, cwq, [n], qkv, 1)
         qv, ov = qkv.t.view(B, Tn, 3 * Cc), o.t.view(B, Tn, Cc)
         pl.add_fwd(lambda: ops.attn_fwd(qv, heads, out=ov, lse=lse))
-        self.plan_conv(pl, cwp, [o], out, 1, resid=x)
+        self.plan_conv(pl, cwp, [o], out, 1, resid=x, stats=True)
         if pl.train:
             def build_bwd():
                 fns = []
@@ -488,7 +525,7 @@ class Engine:
         B, H, W, Cc = x.shape
         cw = self.convs[id(ds.op)]
         out = T(pl, (B, H // 2, W // 2, Cc))
-        self.plan_conv(pl, cw, [x], out, 3, stride=2)
+        self.plan_conv(pl, cw, [x], out, 3, stride=2, stats=True)
         if pl.train:
             pl.bwd_builders.append(lambda: self.plan_conv_bwd(pl, cw, [x], out.grad(), 3, stride=2))
         return out
@@ -498,7 +535,7 @@ class Engine:
         cw = self.convs[id(up.conv)]
         u, out = T(pl, (B, 2 * H, 2 * W, Cc)), T(pl, (B, 2 * H, 2 * W, Cc))
         pl.add_fwd(lambda: ops.upsample2x(x.t, out=u.t))
-        self.plan_conv(pl, cw, [u], out, 3)
+        self.plan_conv(pl, cw, [u], out, 3, stats=True)
         if pl.train:
             def build_bwd():
                 fns = self.plan_conv_bwd(pl, cw, [u], out.grad(), 3)
@@ -527,7 +564,7 @@ class Engine:
         stem = m.input_blocks[0][0]
         cws = self.convs[id(stem)]
         h = T(pl, (B, S, S, stem.out_channels))
-        self.plan_conv(pl, cws, [xin], h, 3)
+        self.plan_conv(pl, cws, [xin], h, 3, stats=True)
         if train:
             pl.bwd_builders.append(lambda h0=h: self.plan_conv_bwd(pl, cws, [xin], h0.grad(), 3, need_dgrad=False))
         hs = [h]
@@ -557,7 +594,7 @@ class Engine:
         cwo = self.convs[id(co)]
         a = T(pl, h.shape)
         sto = (pl.alloc((B, 32), th.float32), pl.alloc((B, 32), th.float32))
-        pl.add_fwd(lambda: ops.gn_fwd(h.t, gno.weight, gno.bias, silu=True, out=a.t, mean=sto[0], rstd=sto[1]))
+        self.plan_gn_fwd(pl, h, None, gno, a, sto)
         self.plan_conv(pl, cwo, [a], pl.eps, 3, out_mode=1)
         if train:
             pl.deps_in = pl.alloc((B, m.out_channels, S, S), th.float32)

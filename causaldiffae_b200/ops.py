@@ -149,6 +149,29 @@ def gn_fwd(x0, gamma, beta, x1=None, film=None, film_off=0, silu=True, out=None,
     return out, mean, rstd
 
 
+def gn_apply_fwd(x0, stats0, gamma, beta, x1=None, stats1=None, film=None, film_off=0, silu=True, out=None, mean=None,
+                 rstd=None):
+    """gn_fwd as ONE streaming pass: the per-(image, channel) sums stats0 [B,C0,2] (stats1 [B,C1,2]) were accumulated by
+    the convolutions that produced x0 (x1) (make_igemm_desc(stats=...))."""
+    _bf16c(x0); _f32c(stats0)
+    B = x0.shape[0]
+    C0 = x0.shape[-1]
+    HW = x0.numel() // (B * C0)
+    assert tuple(stats0.shape) == (B, C0, 2)
+    C1 = 0
+    if x1 is not None:
+        _bf16c(x1); _f32c(stats1); C1 = x1.shape[-1]
+        assert tuple(stats1.shape) == (B, C1, 2)
+    Ct = C0 + C1
+    out = torch.empty(*x0.shape[:-1], Ct, device=x0.device, dtype=bf16) if out is None else out
+    mean = torch.empty(B, 32, device=x0.device, dtype=torch.float32) if mean is None else mean
+    rstd = torch.empty(B, 32, device=x0.device, dtype=torch.float32) if rstd is None else rstd
+    check(_lib.lib().cdae_gn_apply_fwd(ptr(x0), C0, ptr(stats0), ptr(x1), C1, ptr(stats1), B, HW, ptr(gamma), ptr(beta),
+                                       ptr(film), film.shape[1] if film is not None else 0, film_off, int(silu), ptr(out),
+                                       ptr(mean), ptr(rstd), stream()))
+    return out, mean, rstd
+
+
 def gn_bwd(dy, x0, gamma, beta, mean, rstd, x1=None, film=None, film_off=0, silu=True, dx0=None, dx1=None,
            accumulate_dx=0, dgamma=None, dbeta=None, dfilm=None, dadd=None):
     """accumulate_dx: bit0 -> add into dx0, bit1 -> add into dx1 (True == both); dadd: extra bf16 [B,HW,C] gradient."""
@@ -189,8 +212,10 @@ def conv_segments(chans, ksize=3, transposed=False, wk0=0, src0=0):
 
 
 def make_igemm_desc(srcs, segs, wgt, out, cout, in_stride=1, bias=None, resid=None, out_mode=0, sps=1, ooh=0, oow=0,
-                    bn=0, out_hw=None, bias2=None):
-    """Fill a cdae_igemm_desc.  srcs: bf16 [N,H,W,C]; wgt: bf16 [rows, K]; out: bf16 NHWC or fp32 NCHW (out_mode 1)."""
+                    bn=0, out_hw=None, bias2=None, stats=None):
+    """Fill a cdae_igemm_desc.  srcs: bf16 [N,H,W,C]; wgt: bf16 [rows, K]; out: bf16 NHWC or fp32 NCHW (out_mode 1).
+    stats: optional fp32 [N, cout, 2] that the epilogue ACCUMULATES per-(image, channel) sum / sum of squares of the
+    stored output into (zero it first) - the GroupNorm statistics of the consumer, see gn_apply_fwd."""
     d = IgemmDesc()
     N, H, W = srcs[0].shape[:3]
     for i, s in enumerate(srcs):
@@ -219,7 +244,11 @@ def make_igemm_desc(srcs, segs, wgt, out, cout, in_stride=1, bias=None, resid=No
     d.resid = ptr(resid)
     d.ldr = resid.shape[-1] if resid is not None else 0
     d.bn = bn
-    d._keep = (srcs, wgt, out, bias, bias2, resid)   # keep tensors alive as long as the descriptor
+    if stats is not None:
+        _f32c(stats)
+        assert out_mode == 0 and tuple(stats.shape) == (N, cout, 2)
+    d.stats = ptr(stats)
+    d._keep = (srcs, wgt, out, bias, bias2, resid, stats)   # keep tensors alive as long as the descriptor
     return d
 
 

@@ -88,6 +88,12 @@ int cdae_colsum(const void* x_bf16, float* out, int64_t rows, int C, int ld, cda
 int cdae_gn_fwd(const void* x0, int C0, const void* x1, int C1, int B, int HW,
                 const float* gamma, const float* beta, const float* film, int film_ld, int film_off,
                 int silu, void* y, float* mean, float* rstd, cdae_stream s);
+/* same forward when the producing convolutions already accumulated the per-(image, channel) sums (cdae_igemm_desc.stats):
+ * stats0 fp32 [B][C0][2], stats1 fp32 [B][C1][2] = {sum, sum of squares} over the HW pixels.  One streaming pass
+ * (2 B read + 2 B written per element), no reduction; mean/rstd [B,32] are still written for the backward. */
+int cdae_gn_apply_fwd(const void* x0, int C0, const float* stats0, const void* x1, int C1, const float* stats1,
+                      int B, int HW, const float* gamma, const float* beta, const float* film, int film_ld, int film_off,
+                      int silu, void* y, float* mean, float* rstd, cdae_stream s);
 /* backward: dx split into dx0/dx1; accumulate_dx bit0/bit1: add to the existing contents of dx0/dx1;
  * dadd: optional bf16 [B,HW,C] tensor added to dx (identity-skip gradient of a ResBlock, unet.py:198);
  * dgamma/dbeta (+=, fp32), dfilm (+= into [B, film_ld] at the same columns) */
@@ -117,6 +123,10 @@ typedef struct {
   const float* bias2;                      /* second fp32 [cout] bias (fused 1x1 skip conv) or NULL */
   const void* resid; int32_t ldr;          /* bf16 tensor added in the epilogue (same pixel indexing as out) or NULL */
   int32_t bn;                              /* N tile: 16, 32, 64, 128 or 256 (0: auto) */
+  float* stats;                            /* optional fp32 [N][cout][2] (16 B aligned), ACCUMULATED (+=): per-(image, channel)
+                                              sum and sum of squares of the bf16 output as stored - the GroupNorm statistics of
+                                              the consumer (cdae_gn_apply_fwd), produced by the conv epilogue so that the norm
+                                              becomes one streaming pass.  Needs out_mode 0, cout % 64 == 0, OH*OW >= 32. */
 } cdae_igemm_desc;
 int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s);
 

@@ -293,6 +293,88 @@ def test_wgrad_matches_autograd(N, H, cin, cout, ksize, stride):
 
 
 # ------------------------------------------------------------------ attention
+# ------------------------------------------------------------------ GroupNorm statistics from the conv epilogue + streaming GN
+@pytest.mark.parametrize("N,H,chans,cout,ksize,stride,resid", [
+    (2, 64, [64], 128, 3, 1, False),          # halo kernel, N tile 128 (two slabs per tile)
+    (3, 32, [128], 256, 3, 1, True),          # residual epilogue, N tile 256
+    (5, 8, [256], 256, 3, 1, False),          # two images per 128-pixel box, ragged batch
+    (2, 32, [128], 128, 3, 2, False),         # stride-2 (Downsample)
+    (2, 16, [192], 64, 1, 1, True),           # 1x1 conv, cout 64
+    (2, 48, [64, 128], 192, 3, 1, True),      # non-power-of-two image: partial boxes must be masked out of the sums
+    (3, 24, [64], 64, 3, 1, False),           # tap-streaming kernel with partial boxes
+    (67, 16, [128], 128, 3, 1, True),         # many boxes (MT = 2 tail)
+])
+def test_igemm_channel_stats(N, H, chans, cout, ksize, stride, resid):
+    """cdae_igemm_desc.stats: per-(image, channel) sum / sum of squares of the bf16 output, accumulated by the epilogue"""
+    from causaldiffae_b200 import ops
+    g = torch.Generator().manual_seed(H * 7 + cout)
+    cin = sum(chans)
+    x = torch.randn(N, cin, H, H, generator=g).to(dev()).to(bf16)
+    w = (torch.randn(cout, cin, ksize, ksize, generator=g) * (cin * ksize * ksize) ** -0.5).to(dev()).to(bf16).float()
+    b = torch.randn(cout, generator=g).to(dev())
+    OH = (H + stride - 1) // stride
+    r = torch.randn(N, OH, OH, cout, generator=g).to(dev()).to(bf16) if resid else None
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    xs, off = [], 0
+    for c in chans:
+        xs.append(xn[..., off:off + c].contiguous()); off += c
+    segs, _ = ops.conv_segments(chans, ksize)
+    out = torch.full((N, OH, OH, cout), float("nan"), device=dev(), dtype=bf16)
+    stats = torch.zeros(N, cout, 2, device=dev())
+    d = ops.make_igemm_desc(xs, segs, pack_ohwi(w), out, cout, in_stride=stride, bias=b, resid=r, stats=stats)
+    ops.igemm(d)
+    o = out.double()
+    ref = torch.stack([o.sum(dim=(1, 2)), (o * o).sum(dim=(1, 2))], dim=-1)
+    assert bool(torch.isfinite(stats).all())
+    np.testing.assert_allclose(stats.double().cpu().numpy(), ref.cpu().numpy(), rtol=2e-4, atol=2e-3 * OH)
+    ops.igemm(d)    # accumulates
+    np.testing.assert_allclose(stats.double().cpu().numpy(), 2 * ref.cpu().numpy(), rtol=2e-4, atol=4e-3 * OH)
+
+
+def test_igemm_channel_stats_rejects_unsupported():
+    from causaldiffae_b200 import ops
+    from causaldiffae_b200._lib import CdaeError
+    x = torch.randn(2, 4, 4, 64, device=dev()).to(bf16)          # 16 pixels per image: a warp's rows span two images
+    w = torch.randn(64, 9 * 64, device=dev()).to(bf16)
+    segs, _ = ops.conv_segments([64], 3)
+    d = ops.make_igemm_desc([x], segs, w, torch.empty(2, 4, 4, 64, device=dev(), dtype=bf16), 64,
+                            stats=torch.zeros(2, 64, 2, device=dev()))
+    with pytest.raises(CdaeError):
+        ops.igemm(d)
+
+
+@pytest.mark.parametrize("C0,C1,HW,film,silu,B", [(128, 0, 64 * 64, True, True, 3), (64, 0, 16 * 16, False, True, 2),
+                                                  (512, 384, 8 * 8, False, True, 3), (256, 128, 32 * 32, True, True, 2),
+                                                  (384, 0, 16 * 16, False, False, 5), (384, 256, 16 * 16, True, True, 2),
+                                                  (512, 512, 8 * 8, False, True, 70), (128, 128, 48 * 48, False, True, 2)])
+def test_groupnorm_apply_fwd_matches_reducing_kernel_and_torch(C0, C1, HW, film, silu, B):
+    from causaldiffae_b200 import ops
+    g = torch.Generator().manual_seed(C0 + 3 * C1 + HW)
+    Ct = C0 + C1
+    S = int(HW ** 0.5)
+    x = (torch.randn(B, Ct, S, S, generator=g) * 1.5 + 0.3).to(dev()).to(bf16).float()
+    gamma = (1 + 0.2 * torch.randn(Ct, generator=g)).to(dev())
+    beta = (0.2 * torch.randn(Ct, generator=g)).to(dev())
+    film_t = (0.3 * torch.randn(B, 2 * Ct + 32, generator=g)).to(dev()) if film else None
+    foff = 16
+    u = F.group_norm(x, 32, gamma, beta, eps=1e-5)
+    if film:
+        u = u * (1 + film_t[:, foff:foff + Ct, None, None]) + film_t[:, foff + Ct:foff + 2 * Ct, None, None]
+    yref = u * torch.sigmoid(u) if silu else u
+    x_nhwc = nhwc(x)
+    x0 = x_nhwc[..., :C0].contiguous()
+    x1 = x_nhwc[..., C0:].contiguous() if C1 else None
+    st = torch.stack([x.sum(dim=(2, 3)), (x * x).sum(dim=(2, 3))], dim=-1)          # [B, Ct, 2]
+    st0 = st[:, :C0].contiguous()
+    st1 = st[:, C0:].contiguous() if C1 else None
+    y, mean, rstd = ops.gn_apply_fwd(x0, st0, gamma, beta, x1=x1, stats1=st1, film=film_t, film_off=foff, silu=silu)
+    assert relerr(nchw(y), yref) < 6e-3
+    y2, mean2, rstd2 = ops.gn_fwd(x0, gamma, beta, x1=x1, film=film_t, film_off=foff, silu=silu)
+    np.testing.assert_allclose(mean.cpu().numpy(), mean2.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(rstd.cpu().numpy(), rstd2.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    assert relerr(y.float(), y2.float()) < 4e-3
+
+
 @pytest.mark.parametrize("B,T,heads,ch", [(2, 256, 4, 96), (3, 64, 4, 128), (2, 16, 4, 32), (1, 784, 2, 64), (2, 100, 1, 48)])
 def test_attention_fwd_bwd(B, T, heads, ch):
     from causaldiffae_b200 import ops

@@ -42,6 +42,7 @@ def timeit(fns, iters=12):
 
 def main():
     only = sys.argv[1] if len(sys.argv) > 1 else ""
+    with_stats = "stats" in sys.argv[2:]     # also accumulate the GroupNorm channel sums in the epilogue
     g = torch.Generator(device=dev).manual_seed(0)
     if only in ("", "fwd"):
         for case in FWD:
@@ -57,13 +58,14 @@ def main():
                 out = torch.empty(N, cout, OH, OH, device=dev) if mode1 else torch.empty(N, OH, OH, cout, device=dev, dtype=bf16)
                 r = torch.randn(N, OH, OH, cout, device=dev, generator=g).to(bf16) if resid else None
                 segs, K = ops.conv_segments(chans, ks)
+                stt = torch.zeros(N, cout, 2, device=dev) if (with_stats and not mode1 and cout % 64 == 0) else None
                 d = ops.make_igemm_desc(xs, segs, w, out, cout, in_stride=st, bias=bias, resid=r, bn=bn,
-                                        out_mode=1 if mode1 else 0)
+                                        out_mode=1 if mode1 else 0, stats=stt)
                 fns.append(lambda d=d: ops.igemm(d))
             ms = timeit(fns)
             fl = 2.0 * N * OH * OH * cout * ks * ks * cin
             byts = 2.0 * N * (H * H * cin + OH * OH * cout * (2 if resid else 1))
-            print(f"igemm N{N} {H}x{H} cin{chans} cout{cout} k{ks} s{st} resid{int(resid)} bn{bn}: {ms*1e3:8.1f} us "
+            print(f"igemm{'+stats' if with_stats else ''} N{N} {H}x{H} cin{chans} cout{cout} k{ks} s{st} resid{int(resid)} bn{bn}: {ms*1e3:8.1f} us "
                   f"{fl/ms/1e9:7.1f} TF/s ({fl/ms/1e9/PEAK:5.1%} of measured peak)  {byts/ms/1e6:6.0f} GB/s algorithmic", flush=True)
     if only in ("", "wgrad"):
         for (N, H, cin, cout, ks) in WG:
