@@ -77,6 +77,7 @@ _SIGS = {
     "cdae_attn_fwd": ([P, P, P, I32, I32, I32, I32, P], C.c_int),
     "cdae_attn_bwd": ([P, P, P, P, P, P, I32, I32, I32, I32, P], C.c_int),
     "cdae_dag_fwd": ([P, P, P, P, I32, I32, I32, I32, P], C.c_int),
+    "cdae_gather_images": ([P, P, P, P, P, I32, I32, I32, I32, I32, I32, P], C.c_int),
     "cdae_dag_bwd": ([P, P, P, P, P, P, P, I32, I32, I32, I32, P], C.c_int),
 }
 # entry points that later files add; absent symbols are only an error when called

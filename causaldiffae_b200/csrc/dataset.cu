@@ -1,0 +1,74 @@
+// Batch assembly for an HBM-resident dataset (the step BEFORE the hot path, ref improved_diffusion/image_datasets.py).
+// The reference decodes one image at a time in a DataLoader worker (PIL -> ToTensor -> collate).  Here the decoded
+// dataset lives in HBM once (uint8 NHWC, 180 GB is plenty for every dataset the reference ships) and a training batch
+// is ONE gather launch: out[b, c, h, w] = images[idx[b], h, w, c] / 255 (fp32 NCHW, the exact ToTensor arithmetic:
+// IEEE division by 255, so batches are bit-identical to the reference's; mode 1: u / 127.5 - 1 as ImageDataset does),
+// labels gathered alongside.
+// HBM bound: C bytes read + 4*C bytes written per pixel.
+#include "common.cuh"
+
+namespace cdae {
+
+template <int C>
+__global__ void __launch_bounds__(256) gather_images_kernel(const uint8_t* __restrict__ images, const float* __restrict__ labels,
+                                                            const int64_t* __restrict__ idx, float* __restrict__ out,
+                                                            float* __restrict__ out_lab, int HW, int L, int mode) {
+  const int b = blockIdx.y;
+  const int64_t img = idx[b];
+  if (blockIdx.x == 0 && labels != nullptr) {
+    for (int l = threadIdx.x; l < L; l += blockDim.x) out_lab[(int64_t)b * L + l] = labels[img * L + l];
+  }
+  const int nq = HW >> 2;                        // HW % 4 == 0 (checked on the host): four pixels per thread
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(images + img * (int64_t)HW * C);
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+    uint32_t w[C];
+    if (C == 4) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + q);
+      w[0] = v.x; w[1 % C] = v.y; w[2 % C] = v.z; w[3 % C] = v.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < C; ++k) w[k] = __ldg(src + (int64_t)q * C + k);
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      float f[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int j = p * C + c;                 // byte index inside the 4*C byte group
+        const float u = (float)((w[j >> 2] >> ((j & 3) * 8)) & 0xffu);
+        f[p] = mode == 0 ? __fdiv_rn(u, 255.f) : __fsub_rn(__fdiv_rn(u, 127.5f), 1.f);
+      }
+      *reinterpret_cast<float4*>(out + ((int64_t)b * C + c) * HW + 4 * (int64_t)q) = make_float4(f[0], f[1], f[2], f[3]);
+    }
+  }
+}
+
+}  // namespace cdae
+using namespace cdae;
+
+extern "C" int cdae_gather_images(const void* images_u8, const float* labels, const int64_t* idx, float* out,
+                                  float* out_labels, int B, int H, int W, int C, int L, int mode, cdae_stream s) {
+  CDAE_CHECK_ARG(images_u8 && idx && out && (L == 0 || (labels && out_labels)), "gather_images: null pointer");
+  if (B == 0) return CDAE_OK;
+  const int HW = H * W;
+  CDAE_CHECK_SHAPE(C >= 1 && C <= 4, "gather_images: %d channels (1..4 supported)", C);
+  CDAE_CHECK_SHAPE(HW % 4 == 0 && HW > 0, "gather_images: H*W=%d must be a multiple of 4", HW);
+  CDAE_CHECK_ARG(mode == 0 || mode == 1, "gather_images: mode %d", mode);
+  CDAE_CHECK_SHAPE(B <= 65535, "gather_images: batch %d too large", B);
+  CDAE_CHECK_ARG((reinterpret_cast<uintptr_t>(images_u8) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                 "gather_images: images/out must be 16 B aligned");
+  const int nq = HW / 4;
+  dim3 grid((unsigned)((nq + 255) / 256), (unsigned)B);
+  if (grid.x > 64) grid.x = 64;
+  cudaStream_t st = (cudaStream_t)s;
+  const uint8_t* im = (const uint8_t*)images_u8;
+  const float* lab = L > 0 ? labels : nullptr;
+  switch (C) {
+    case 1: gather_images_kernel<1><<<grid, 256, 0, st>>>(im, lab, idx, out, out_labels, HW, L, mode); break;
+    case 2: gather_images_kernel<2><<<grid, 256, 0, st>>>(im, lab, idx, out, out_labels, HW, L, mode); break;
+    case 3: gather_images_kernel<3><<<grid, 256, 0, st>>>(im, lab, idx, out, out_labels, HW, L, mode); break;
+    default: gather_images_kernel<4><<<grid, 256, 0, st>>>(im, lab, idx, out, out_labels, HW, L, mode); break;
+  }
+  CDAE_CHECK_LAUNCH("gather_images_kernel");
+  return CDAE_OK;
+}

@@ -800,7 +800,7 @@ constexpr int kApplyThreads = 256;
 constexpr int kApplyUnroll = 4;
 
 template <bool SILU>
-__global__ void __launch_bounds__(kApplyThreads, 4) gn_apply_fwd_kernel(const GnApplyParams p) {
+__global__ void __launch_bounds__(kApplyThreads, 3) gn_apply_fwd_kernel(const GnApplyParams p) {
   extern __shared__ __align__(16) float sm_apply[];
   float* cs = sm_apply;                 // [C] channel sums   -> later A (scale)
   float* cq = sm_apply + p.C;           // [C] channel sumsq  -> later B (shift)
@@ -808,10 +808,29 @@ __global__ void __launch_bounds__(kApplyThreads, 4) gn_apply_fwd_kernel(const Gn
   float* gr = gm + kGroups;             // [32] group rstd
   const int b = blockIdx.y;
   const int cpg = p.C / kGroups;
+  // streaming geometry first: the first rows are requested BEFORE the statistics prologue, so that their DRAM latency
+  // hides the three dependent L2 round trips (channel sums -> group statistics -> per-channel constants)
+  const int vec = threadIdx.x % p.nvec, row = threadIdx.x / p.nvec;
+  const bool active = row < p.R;
+  const int cl = vec * 8;
+  const bool in0 = cl < p.C0;
+  const int xpitch = in0 ? p.C0 : p.C1;
+  const __nv_bfloat16* xb = in0 ? p.x0 + (size_t)b * p.HW * p.C0 + cl : p.x1 + (size_t)b * p.HW * p.C1 + (cl - p.C0);
+  __nv_bfloat16* yb = p.y + (size_t)b * p.HW * p.C + cl;
+  const int p0 = blockIdx.x * p.ppc, p1 = min(p.HW, p0 + p.ppc);
+  uint4 v[kApplyUnroll];
+  int pix = p0 + row;
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < kApplyUnroll; ++k) {
+      const int pk = pix + k * p.R;
+      if (pk < p1) v[k] = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)pk * xpitch));
+    }
+  }
   for (int c = threadIdx.x; c < p.C; c += kApplyThreads) {
-    const float2 v = c < p.C0 ? __ldg(reinterpret_cast<const float2*>(p.st0) + (size_t)b * p.C0 + c)
+    const float2 t = c < p.C0 ? __ldg(reinterpret_cast<const float2*>(p.st0) + (size_t)b * p.C0 + c)
                               : __ldg(reinterpret_cast<const float2*>(p.st1) + (size_t)b * p.C1 + (c - p.C0));
-    cs[c] = v.x; cq[c] = v.y;
+    cs[c] = t.x; cq[c] = t.y;
   }
   __syncthreads();
   if (threadIdx.x < kGroups) {
@@ -839,25 +858,20 @@ __global__ void __launch_bounds__(kApplyThreads, 4) gn_apply_fwd_kernel(const Gn
     cq[c] = half * (hk - m * rs * gk);
   }
   __syncthreads();
-  const int vec = threadIdx.x % p.nvec, row = threadIdx.x / p.nvec;
-  if (row >= p.R) return;
-  const int cl = vec * 8;
+  if (!active) return;
   float2 A[4], Bc[4];
   *reinterpret_cast<float4*>(A) = *reinterpret_cast<const float4*>(cs + cl);
   *reinterpret_cast<float4*>(A + 2) = *reinterpret_cast<const float4*>(cs + cl + 4);
   *reinterpret_cast<float4*>(Bc) = *reinterpret_cast<const float4*>(cq + cl);
   *reinterpret_cast<float4*>(Bc + 2) = *reinterpret_cast<const float4*>(cq + cl + 4);
-  const bool in0 = cl < p.C0;
-  const int xpitch = in0 ? p.C0 : p.C1;
-  const __nv_bfloat16* xb = in0 ? p.x0 + (size_t)b * p.HW * p.C0 + cl : p.x1 + (size_t)b * p.HW * p.C1 + (cl - p.C0);
-  __nv_bfloat16* yb = p.y + (size_t)b * p.HW * p.C + cl;
-  const int p0 = blockIdx.x * p.ppc, p1 = min(p.HW, p0 + p.ppc);
-  for (int pix = p0 + row; pix < p1; pix += kApplyUnroll * p.R) {
-    uint4 v[kApplyUnroll];
+  const int step = kApplyUnroll * p.R;
+  for (; pix < p1; pix += step) {
+    // rows of the NEXT batch are requested before this batch is normalised and stored
+    uint4 nx[kApplyUnroll];
 #pragma unroll
     for (int k = 0; k < kApplyUnroll; ++k) {
-      const int pk = pix + k * p.R;
-      if (pk < p1) v[k] = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)pk * xpitch));
+      const int pk = pix + step + k * p.R;
+      if (pk < p1) nx[k] = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)pk * xpitch));
     }
 #pragma unroll
     for (int k = 0; k < kApplyUnroll; ++k) {
@@ -873,6 +887,8 @@ __global__ void __launch_bounds__(kApplyThreads, 4) gn_apply_fwd_kernel(const Gn
         *reinterpret_cast<uint4*>(yb + (size_t)pk * p.C) = pack_u4_2(f);
       }
     }
+#pragma unroll
+    for (int k = 0; k < kApplyUnroll; ++k) v[k] = nx[k];
   }
 }
 
@@ -1059,7 +1075,7 @@ extern "C" int cdae_gn_apply_fwd(const void* x0, int C0, const float* stats0, co
   int ppc = (48 * 1024) / (p.C * 2);
   ppc = ppc / (p.R * kApplyUnroll) * (p.R * kApplyUnroll);
   if (ppc < p.R * kApplyUnroll) ppc = p.R * kApplyUnroll;
-  while (ppc > p.R * kApplyUnroll && (int64_t)B * ((HW + ppc - 1) / ppc) < 2 * 4 * kNumSMs) ppc -= p.R * kApplyUnroll;
+  while (ppc > p.R * kApplyUnroll && (int64_t)B * ((HW + ppc - 1) / ppc) < 2 * 3 * kNumSMs) ppc -= p.R * kApplyUnroll;
   if (ppc > HW) ppc = HW;
   p.ppc = ppc;
   dim3 grid((unsigned)((HW + ppc - 1) / ppc), (unsigned)B);

@@ -129,6 +129,23 @@ def colsum_(x2d, out, c=None):
     return out
 
 
+def gather_images(images_u8, idx, labels=None, mode=0, out=None, out_labels=None):
+    """batch assembly from an HBM-resident dataset (ref image_datasets.py __getitem__ + DataLoader collate):
+    images_u8 uint8 [n,H,W,C], idx int64 [B], labels fp32 [n,L] -> fp32 [B,C,H,W] = u8/255 (mode 1: u8/127.5-1), [B,L]"""
+    assert images_u8.is_cuda and images_u8.dtype == torch.uint8 and images_u8.is_contiguous() and images_u8.dim() == 4
+    assert idx.is_cuda and idx.dtype == torch.int64 and idx.is_contiguous()
+    n, H, W, Cc = images_u8.shape
+    B = idx.numel()
+    L = 0
+    if labels is not None:
+        _f32c(labels); L = labels.shape[1]
+        out_labels = torch.empty(B, L, device=idx.device, dtype=torch.float32) if out_labels is None else out_labels
+    out = torch.empty(B, Cc, H, W, device=idx.device, dtype=torch.float32) if out is None else out
+    check(_lib.lib().cdae_gather_images(ptr(images_u8), ptr(labels), ptr(idx), ptr(out), ptr(out_labels), B, H, W, Cc, L,
+                                        int(mode), stream()))
+    return out, out_labels
+
+
 # ------------------------------------------------------------------ GroupNorm32 (+FiLM)(+SiLU)
 def gn_fwd(x0, gamma, beta, x1=None, film=None, film_off=0, silu=True, out=None, mean=None, rstd=None):
     """ref nn.py:430-437 / unet.py:185-198.  x0 [B,H,W,C0] (+ x1 [B,H,W,C1] concatenated on channels)."""

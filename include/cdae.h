@@ -165,6 +165,15 @@ int cdae_dag_fwd(const float* u, const float* A, const void* const* params, floa
 int cdae_dag_bwd(const float* u, const float* A, const void* const* params, const float* dzpost, void* const* grads,
                  float* dzp_ws, float* du, int B, int n, int d, int D, cdae_stream s);
 
+/* ------------------------------------------------------------------ HBM-resident dataset batch assembly
+ * (the step before the hot path: image_datasets.py:141-183,241-296,344-392,411-483 = PIL decode + ToTensor + DataLoader
+ * collate per item).  images_u8: uint8 [n][H][W][C] resident in HBM (16 B aligned, image stride H*W*C a multiple of 4),
+ * labels: fp32 [n][L] (L may be 0), idx: int64 [B] row numbers.  out[b,c,h,w] = images[idx[b],h,w,c] / 255 (fp32 NCHW,
+ * IEEE division = torchvision ToTensor, bit-exact; mode 1: u / 127.5 - 1 = ImageDataset :171), out_labels[b,:] =
+ * labels[idx[b],:].  C in 1..4, H*W % 4 == 0. */
+int cdae_gather_images(const void* images_u8, const float* labels, const int64_t* idx, float* out, float* out_labels,
+                       int B, int H, int W, int C, int L, int mode, cdae_stream s);
+
 #ifdef __cplusplus
 }
 #endif
