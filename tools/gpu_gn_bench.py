@@ -16,6 +16,8 @@ SHAPES = [(128, 0, 4096, 8), (128, 0, 1024, 1), (256, 0, 1024, 6), (256, 0, 256,
           (512, 0, 64, 16), (512, 512, 64, 2), (512, 384, 64, 1), (512, 384, 256, 1), (384, 384, 256, 1), (384, 256, 256, 1),
           (384, 256, 1024, 1), (256, 256, 1024, 1), (256, 128, 1024, 1), (256, 128, 4096, 1), (128, 128, 4096, 2)]
 B = 64
+if 'first' in sys.argv[1:]:
+    SHAPES = SHAPES[:1]     # ncu captures: the 128-channel 64x64 layer only
 
 def timeit(fns, iters=12):
     for f in fns: f()

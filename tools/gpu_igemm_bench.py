@@ -45,7 +45,7 @@ def main():
     with_stats = "stats" in sys.argv[2:]     # also accumulate the GroupNorm channel sums in the epilogue
     g = torch.Generator(device=dev).manual_seed(0)
     if only in ("", "fwd"):
-        for case in FWD:
+        for case in (FWD[:1] if "first" in sys.argv[2:] else FWD):
             (N, H, chans, cout, ks, st, resid), bn = case[:7], (case[7] if len(case) > 7 else 0)
             cin = sum(chans)
             OH = H // st
