@@ -72,6 +72,7 @@ _SIGS = {
     "cdae_gn_fwd": ([P, I32, P, I32, I32, I32, P, P, P, I32, I32, I32, P, P, P, P], C.c_int),
     "cdae_gn_apply_fwd": ([P, I32, P, P, I32, P, I32, I32, P, P, P, I32, I32, I32, P, P, P, P], C.c_int),
     "cdae_gn_bwd": ([P, P, I32, P, I32, I32, I32, P, P, P, I32, I32, I32, P, P, P, P, P, I32, P, P, P, P], C.c_int),
+    "cdae_gn_bwd_stream": ([P, P, I32, P, I32, I32, I32, P, P, P, I32, I32, I32, P, P, P, P, P, I32, P, P, P, P, P], C.c_int),
     "cdae_igemm": ([C.POINTER(IgemmDesc), P], C.c_int),
     "cdae_wgrad": ([C.POINTER(WgradDesc), P], C.c_int),
     "cdae_attn_fwd": ([P, P, P, I32, I32, I32, I32, P], C.c_int),

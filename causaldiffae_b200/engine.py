@@ -27,6 +27,8 @@ bf16 = th.bfloat16
 USE_GRAPHS = os.environ.get("CDAE_GRAPHS", "1") != "0"
 # GroupNorm statistics from the producing conv's epilogue + one streaming normalise pass (0: reduce inside the GN kernel)
 FUSED_GN_STATS = os.environ.get("CDAE_FUSED_GN_STATS", "1") != "0"
+# GroupNorm backward as two streaming passes (reduce, then apply in reverse order: L2 reuse) instead of the resident kernel
+GN_BWD_STREAM = os.environ.get("CDAE_GN_BWD_STREAM", "1") != "0"
 
 
 def _round_up(v, m):
@@ -80,6 +82,7 @@ class Plan:
         # per-(image, channel) GroupNorm sums accumulated by conv epilogues: carved from a few big chunks that the
         # first node of the forward graph zeroes
         self.stat_chunks, self._stat_used = [], 0
+        self.bws_chunks, self._bws_used = [], 0
         self.add_fwd(self._zero_stats, 0)
 
     def alloc(self, shape, dtype=bf16):
@@ -99,6 +102,23 @@ class Plan:
 
     def _zero_stats(self):
         for c in self.stat_chunks:
+            ops.zero_(c)
+
+    def alloc_bwd_ws(self, B, C):
+        """zeroed-at-backward-start fp32 [B, 2, C] workspace of one streaming GroupNorm backward (None: resident kernel)"""
+        if not GN_BWD_STREAM:
+            return None
+        n = B * C * 2
+        if not self.bws_chunks or self._bws_used + n > self.bws_chunks[-1].numel():
+            self.bws_chunks.append(th.zeros(max(n, 1 << 21), device=self.dev, dtype=th.float32))
+            self._bws_used = 0
+        self.n_bwd_launch += 1                   # the streaming backward is two kernels
+        v = self.bws_chunks[-1][self._bws_used:self._bws_used + n].view(B, 2, C)
+        self._bws_used += (n + 3) // 4 * 4
+        return v
+
+    def _zero_bwd_ws(self):
+        for c in self.bws_chunks:
             ops.zero_(c)
 
     def add_fwd(self, fn, n=1):
@@ -465,8 +485,9 @@ class Engine:
                 # GN2 (+FiLM) backward -> dh1
                 ggn2w, ggn2b = self._gparam(gn2.weight), self._gparam(gn2.bias)
                 da2, dh1 = a2.grad(), h1.grad()
+                ws2 = pl.alloc_bwd_ws(B, cout)
                 fns.append(lambda: ops.gn_bwd(da2, h1.t, gn2.weight, gn2.bias, st2[0], st2[1], film=film, film_off=foff,
-                                              silu=True, dx0=dh1, dgamma=ggn2w, dbeta=ggn2b, dfilm=dfilm))
+                                              silu=True, dx0=dh1, dgamma=ggn2w, dbeta=ggn2b, dfilm=dfilm, ws=ws2))
                 h1.g_written = True
                 # conv1
                 fns += self.plan_conv_bwd(pl, cw1, [a1], dh1, 3)
@@ -479,9 +500,10 @@ class Engine:
                 dx1 = x1.grad() if x1 is not None else None
                 accmask = (1 if acc0 else 0) | (2 if acc1 else 0)
                 dadd = None if has_skip else dout
+                ws1 = pl.alloc_bwd_ws(B, cin)
                 fns.append(lambda: ops.gn_bwd(da1, x0.t, gn1.weight, gn1.bias, st1[0], st1[1], x1=x1t, silu=True,
                                               dx0=dx0, dx1=dx1, accumulate_dx=accmask, dgamma=ggn1w, dbeta=ggn1b,
-                                              dadd=dadd))
+                                              dadd=dadd, ws=ws1))
                 return fns
             pl.bwd_builders.append(build_bwd)
         return out
@@ -515,8 +537,9 @@ class Engine:
                 dn = n.grad()
                 acc = x.grad_acc()
                 dx = x.grad()
+                wsn = pl.alloc_bwd_ws(B, Cc)
                 fns.append(lambda: ops.gn_bwd(dn, x.t, ab.norm.weight, ab.norm.bias, st[0], st[1], silu=False, dx0=dx,
-                                              accumulate_dx=1 if acc else 0, dgamma=gw, dbeta=gb, dadd=dout))
+                                              accumulate_dx=1 if acc else 0, dgamma=gw, dbeta=gb, dadd=dout, ws=wsn))
                 return fns
             pl.bwd_builders.append(build_bwd)
         return out
@@ -607,8 +630,9 @@ class Engine:
                 gw, gb = self._gparam(gno.weight), self._gparam(gno.bias)
                 da = a.grad()
                 acc, dx = hfin.grad_acc(), hfin.grad()
+                wso = pl.alloc_bwd_ws(B, hfin.shape[3])
                 fns.append(lambda: ops.gn_bwd(da, hfin.t, gno.weight, gno.bias, sto[0], sto[1], silu=True, dx0=dx,
-                                              accumulate_dx=1 if acc else 0, dgamma=gw, dbeta=gb))
+                                              accumulate_dx=1 if acc else 0, dgamma=gw, dbeta=gb, ws=wso))
                 return fns
             pl.bwd_builders.append(build_out_bwd)
             # backward ops are built in REVERSE layer order so that "first producer writes, later ones accumulate"
@@ -616,6 +640,7 @@ class Engine:
             built = [b() for b in reversed(pl.bwd_builders)]
             for fns in reversed(built):
                 pl.add_bwd(fns)
+            pl.add_bwd([pl._zero_bwd_ws])        # layers replay last-to-first: this node opens the backward graph
         return pl
 
     def plan(self, B, train):

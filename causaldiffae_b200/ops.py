@@ -190,8 +190,9 @@ def gn_apply_fwd(x0, stats0, gamma, beta, x1=None, stats1=None, film=None, film_
 
 
 def gn_bwd(dy, x0, gamma, beta, mean, rstd, x1=None, film=None, film_off=0, silu=True, dx0=None, dx1=None,
-           accumulate_dx=0, dgamma=None, dbeta=None, dfilm=None, dadd=None):
-    """accumulate_dx: bit0 -> add into dx0, bit1 -> add into dx1 (True == both); dadd: extra bf16 [B,HW,C] gradient."""
+           accumulate_dx=0, dgamma=None, dbeta=None, dfilm=None, dadd=None, ws=None):
+    """accumulate_dx: bit0 -> add into dx0, bit1 -> add into dx1 (True == both); dadd: extra bf16 [B,HW,C] gradient.
+    ws: zeroed fp32 [B, 2, C] workspace -> the two-pass streaming kernels (cdae_gn_bwd_stream) instead of the resident one."""
     if accumulate_dx is True:
         accumulate_dx = 3
     _bf16c(dy); _bf16c(x0)
@@ -203,6 +204,14 @@ def gn_bwd(dy, x0, gamma, beta, mean, rstd, x1=None, film=None, film_off=0, silu
         _bf16c(x1); C1 = x1.shape[-1]
         dx1 = torch.empty_like(x1) if dx1 is None else dx1
     dx0 = torch.empty_like(x0) if dx0 is None else dx0
+    if ws is not None:
+        _f32c(ws)
+        assert ws.numel() == B * 2 * (C0 + C1)
+        check(_lib.lib().cdae_gn_bwd_stream(ptr(dy), ptr(x0), C0, ptr(x1), C1, B, HW, ptr(gamma), ptr(beta), ptr(film),
+                                            film.shape[1] if film is not None else 0, film_off, int(silu), ptr(mean),
+                                            ptr(rstd), ptr(dadd), ptr(dx0), ptr(dx1), int(accumulate_dx), ptr(dgamma),
+                                            ptr(dbeta), ptr(dfilm), ptr(ws), stream()))
+        return dx0, dx1
     check(_lib.lib().cdae_gn_bwd(ptr(dy), ptr(x0), C0, ptr(x1), C1, B, HW, ptr(gamma), ptr(beta), ptr(film),
                                  film.shape[1] if film is not None else 0, film_off, int(silu), ptr(mean), ptr(rstd),
                                  ptr(dadd), ptr(dx0), ptr(dx1), int(accumulate_dx), ptr(dgamma), ptr(dbeta), ptr(dfilm), stream()))

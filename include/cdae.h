@@ -102,6 +102,14 @@ int cdae_gn_bwd(const void* dy, const void* x0, int C0, const void* x1, int C1, 
                 const float* mean, const float* rstd, const void* dadd, void* dx0, void* dx1, int accumulate_dx,
                 float* dgamma, float* dbeta, float* dfilm, cdae_stream s);
 
+/* the same backward as two streaming passes (reduce: P_c = sum du, Qx_c = sum du*x per (sample, channel) into ws; apply:
+ * dx, walking the tensor in reverse so that the second read of dy / x hits the L2).  ws: caller-owned fp32 [B][2][C],
+ * ZERO on entry (it is accumulated into with red.add and left holding the sums). */
+int cdae_gn_bwd_stream(const void* dy, const void* x0, int C0, const void* x1, int C1, int B, int HW,
+                       const float* gamma, const float* beta, const float* film, int film_ld, int film_off, int silu,
+                       const float* mean, const float* rstd, const void* dadd, void* dx0, void* dx1, int accumulate_dx,
+                       float* dgamma, float* dbeta, float* dfilm, float* ws, cdae_stream s);
+
 /* ------------------------------------------------------------------ implicit-GEMM convolution on tcgen05/TMEM/TMA
  * Replaces aten::convolution (cuDNN) at unet.py:143-171 (ResBlock convs + 1x1 skip), :69-79, :97-105 (up/down),
  * :216-218 (attention qkv/proj Conv1d), :392, :498 and every nn.Linear that is GEMM shaped.

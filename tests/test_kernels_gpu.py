@@ -137,7 +137,8 @@ def test_layout_kernels():
 @pytest.mark.parametrize("C0,C1,HW,film,silu", [(128, 0, 64 * 64, True, True), (64, 0, 16 * 16, False, True),
                                                 (512, 384, 8 * 8, False, True), (256, 128, 32 * 32, True, True),
                                                 (384, 0, 16 * 16, False, False), (64, 64, 4 * 4, True, True)])
-def test_groupnorm_fwd_bwd(C0, C1, HW, film, silu):
+@pytest.mark.parametrize("stream", [False, True])
+def test_groupnorm_fwd_bwd(C0, C1, HW, film, silu, stream):
     from causaldiffae_b200 import ops
     g = torch.Generator().manual_seed(C0 + C1 + HW)
     B, Ct = 3, C0 + C1
@@ -162,8 +163,10 @@ def test_groupnorm_fwd_bwd(C0, C1, HW, film, silu):
     assert relerr(nchw(y), yref) < 6e-3
     dgamma, dbeta = torch.zeros(Ct, device=dev()), torch.zeros(Ct, device=dev())
     dfilm = torch.zeros_like(film_t) if film else None
+    # stream: the two-pass streaming kernels (cdae_gn_bwd_stream, zeroed workspace); else the resident cluster kernel
+    mkws = lambda: torch.zeros(B, 2, Ct, device=dev()) if stream else None
     dx0, dx1 = ops.gn_bwd(nhwc(dy), x0, gamma, beta, mean, rstd, x1=x1, film=film_t, film_off=foff, silu=silu,
-                          dgamma=dgamma, dbeta=dbeta, dfilm=dfilm)
+                          dgamma=dgamma, dbeta=dbeta, dfilm=dfilm, ws=mkws())
     dx = torch.cat([dx0, dx1], dim=-1) if C1 else dx0
     assert relerr(nchw(dx), xr.grad) < 8e-3
     assert relerr(dgamma, gr.grad) < 3e-3 and relerr(dbeta, br.grad) < 3e-3
@@ -173,9 +176,12 @@ def test_groupnorm_fwd_bwd(C0, C1, HW, film, silu):
     base = torch.randn_like(dx0.float()).to(bf16)
     acc0 = base.clone()
     acc1 = torch.zeros_like(dx1) if C1 else None
+    dadd = torch.randn(B, S, S, Ct, generator=g).to(dev()).to(bf16)
     ops.gn_bwd(nhwc(dy), x0, gamma, beta, mean, rstd, x1=x1, film=film_t, film_off=foff, silu=silu, dx0=acc0, dx1=acc1,
-               accumulate_dx=True)
-    assert relerr(acc0.float(), base.float() + dx0.float()) < 1e-2
+               accumulate_dx=True, dadd=dadd, ws=mkws())
+    assert relerr(acc0.float(), base.float() + dx0.float() + dadd[..., :C0].float()) < 1e-2
+    if C1:
+        assert relerr(acc1.float(), dx1.float() + dadd[..., C0:].float()) < 1e-2
 
 
 # ------------------------------------------------------------------ implicit GEMM (tcgen05)
