@@ -238,9 +238,37 @@ def hbm_kernels(peaks):
     gsq = torch.zeros(1, device=dev)
     ms = timeit([lambda a=a: ops.adam_ema(a[0], a[1], a[2], a[3], a[4], hyper, gsq) for a in sets])
     out["adam_ema"] = (36.0 * P, ms)
+    del sets
+    # GroupNorm32 + FiLM + SiLU on the heaviest cfg2 layer shape (concat 128+128 channels at 64x64, the per-GPU batch of
+    # the workload: 268 MB per tensor): streaming forward (4 B/elem) and the resident cluster backward (6 B/elem)
+    Bg, HW, C0, C1 = 64, 4096, 128, 128
+    Cg = C0 + C1
+    ng = Bg * HW * Cg
+    gam, bet = torch.randn(Cg, device=dev), torch.randn(Cg, device=dev)
+    film = torch.randn(Bg, 2 * Cg, device=dev) * 0.1
+    gsets = []
+    for _ in range(2):
+        x0 = torch.randn(Bg, HW, 1, C0, device=dev).to(torch.bfloat16)
+        x1 = torch.randn(Bg, HW, 1, C1, device=dev).to(torch.bfloat16)
+        st0 = torch.stack([x0.float().sum(dim=(1, 2)), (x0.float() ** 2).sum(dim=(1, 2))], dim=-1).contiguous()
+        st1 = torch.stack([x1.float().sum(dim=(1, 2)), (x1.float() ** 2).sum(dim=(1, 2))], dim=-1).contiguous()
+        gsets.append(dict(x0=x0, x1=x1, st0=st0, st1=st1, y=torch.empty(Bg, HW, 1, Cg, device=dev, dtype=torch.bfloat16),
+                          dy=torch.randn(Bg, HW, 1, Cg, device=dev).to(torch.bfloat16), dx0=torch.empty_like(x0),
+                          dx1=torch.empty_like(x1), mean=torch.empty(Bg, 32, device=dev), rstd=torch.empty(Bg, 32, device=dev),
+                          ))
+    ms = timeit([lambda a=a: ops.gn_apply_fwd(a["x0"], a["st0"], gam, bet, x1=a["x1"], stats1=a["st1"], film=film, silu=True,
+                                              out=a["y"], mean=a["mean"], rstd=a["rstd"]) for a in gsets])
+    out["groupnorm_fwd_stream"] = (4.0 * ng, ms)
+    dg, db, dfl = torch.zeros(Cg, device=dev), torch.zeros(Cg, device=dev), torch.zeros_like(film)
+
+    def gbwd(a):
+        ops.gn_bwd(a["dy"], a["x0"], gam, bet, a["mean"], a["rstd"], x1=a["x1"], film=film, silu=True, dx0=a["dx0"],
+                   dx1=a["dx1"], dgamma=dg, dbeta=db, dfilm=dfl)
+    ms = timeit([lambda a=a: gbwd(a) for a in gsets])
+    out["groupnorm_bwd"] = (6.0 * ng, ms)
     return {k: {"GB/s": round(b / ms / 1e6, 1), "frac": round(b / ms / 1e6 / peaks["hbm"], 3), "ms": round(ms, 4)}
             for k, (b, ms) in out.items()} | {"peak": peaks["hbm"], "peak_source": peaks["src"] + " hbm copy",
-                                              "sizes": "4096x3x64x64 fp32 tensors; 93.5 M-element arenas"}
+                                              "sizes": "4096x3x64x64 fp32 tensors; 93.5 M-element arenas; GroupNorm: 64x(128+128)x64x64 bf16"}
 
 
 # ---------------------------------------------------------------------------------------------- CUDA arm

@@ -27,8 +27,11 @@ bf16 = th.bfloat16
 USE_GRAPHS = os.environ.get("CDAE_GRAPHS", "1") != "0"
 # GroupNorm statistics from the producing conv's epilogue + one streaming normalise pass (0: reduce inside the GN kernel)
 FUSED_GN_STATS = os.environ.get("CDAE_FUSED_GN_STATS", "1") != "0"
-# GroupNorm backward as two streaming passes (reduce, then apply in reverse order: L2 reuse) instead of the resident kernel
-GN_BWD_STREAM = os.environ.get("CDAE_GN_BWD_STREAM", "1") != "0"
+# GroupNorm backward as two streaming passes (reduce, then apply in reverse order) instead of the resident cluster kernel.
+# Measured on B200 (profiles/r1_gn_bench_bwd_stream.log): SLOWER - 96 vs 80 us on the 128-channel 64x64 layer, 3123 vs
+# 3229 img/s for the whole step - the second read of dy / x does not hit L2 for the big layers and the two launches cost
+# more than the cluster barriers they avoid.  Kept as an opt-in (tests cover both), off by default.
+GN_BWD_STREAM = os.environ.get("CDAE_GN_BWD_STREAM", "0") != "0"
 
 
 def _round_up(v, m):
