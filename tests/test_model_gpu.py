@@ -15,6 +15,17 @@ CFG2S = dict(image_size=64, num_channels=64, num_res_blocks=1, class_cond=False,
              causal_modeling=True, in_channels=3, learn_sigma=False, rescale_timesteps=False,
              rescale_learned_sigmas=False, diffusion_steps=1000)
 PENDULUM = [[0, 0, 1, 1], [0, 0, 1, 1], [0, 0, 0, 0], [0, 0, 0, 0]]
+CIRCUIT = [[0, 1, 1, 1], [0, 0, 0, 1], [0, 0, 0, 1], [0, 0, 0, 0]]
+# the three configurations the reference ships launch lines for (scripts/{morhomnist,pendulum,circuit}/train_*_causaldae.sh):
+# same image sizes, input channels, variable counts, class / masking flags and attention placement; the width and the
+# number of res blocks are reduced so that the fp32 oracle stays cheap.  28 -> 14 -> 7 (odd sizes, attention at 28x28,
+# T = 784), 96 -> 48 -> 24 -> 12 (no attention, partial tiles), 128 -> ... -> 4 (six levels, attention at 16x16 / 8x8).
+_BASE = dict(rep_cond=True, causal_modeling=True, learn_sigma=False, rescale_timesteps=False, rescale_learned_sigmas=False,
+             diffusion_steps=1000)
+MNIST28 = dict(image_size=28, num_channels=64, num_res_blocks=1, class_cond=True, n_vars=2, in_channels=1, **_BASE)
+PEND96 = dict(image_size=96, num_channels=64, num_res_blocks=1, class_cond=False, n_vars=4, in_channels=4, **_BASE)
+CIRC128 = dict(image_size=128, num_channels=64, num_res_blocks=1, class_cond=False, n_vars=4, in_channels=3, **_BASE)
+SHIPPED = [(MNIST28, None), (PEND96, PENDULUM), (CIRC128, CIRCUIT)]
 
 
 def relerr(a, b):
@@ -44,11 +55,11 @@ def inputs(flags, B, seed=5):
                 w=torch.rand(B, generator=g) + 0.5)
 
 
-@pytest.mark.parametrize("flags,A", [(CFG1, None), (CFG2S, PENDULUM)])
+@pytest.mark.parametrize("flags,A", [(CFG1, None), (CFG2S, PENDULUM)] + SHIPPED)
 def test_eps_forward_given_z(flags, A):
     from oracle import model as om
     model, diff, cfg, sd, odiff = build(flags, A)
-    inp = inputs(flags, 4)
+    inp = inputs(flags, 4 if flags["image_size"] <= 64 else 3)
     model.eval()
     with torch.no_grad():
         x_t = odiff.q_sample(inp["x0"], inp["t"], inp["noise"])
@@ -91,12 +102,13 @@ def test_per_layer_teacher_forced():
             assert err <= 1e-2, (prefix, err)
 
 
-@pytest.mark.parametrize("flags,A,masking", [(CFG1, None, False), (CFG2S, PENDULUM, True)])
+@pytest.mark.parametrize("flags,A,masking", [(CFG1, None, False), (CFG2S, PENDULUM, True), (MNIST28, None, True),
+                                             (PEND96, PENDULUM, True), (CIRC128, CIRCUIT, True)])
 def test_training_losses_and_gradients(flags, A, masking):
     from oracle import model as om, diffusion as od
     flags = {**flags, "masking": masking}
     model, diff, cfg, sd, odiff = build(flags, A)
-    inp = inputs(flags, 4)
+    inp = inputs(flags, 4 if flags["image_size"] <= 64 else 3)
     diff.kl_weight = odiff.kl_weight = 0.3
     # oracle (CPU fp32 autograd)
     for n in om.trainable_names(cfg):
