@@ -9,5 +9,5 @@ timeout 1200 ncu --set full --clock-control none --import-source on -k regex:ige
     python bench.py --steps 2 --warmup 3 --no-ddim --no-cpu > gpurun_out/ncu_full_stdout.log 2>&1
 tail -3 gpurun_out/ncu_full_stdout.log
 # (3) eager PyTorch reference on the same GPU
-timeout 900 python tools/gpu_ref_eager.py 2>&1 | tail -3 | tee gpurun_out/ref_eager.log
+timeout 900 python tests/gpu_ref_eager.py 2>&1 | tail -3 | tee gpurun_out/ref_eager.log
 ls -la gpurun_out
