@@ -152,7 +152,7 @@ def gn_fwd(x0, gamma, beta, x1=None, film=None, film_off=0, silu=True, out=None,
     _bf16c(x0)
     B = x0.shape[0]
     C0 = x0.shape[-1]
-    HW = x0.numel() // (B * C0)
+    HW = x0[0].numel() // C0 if B else 0
     C1 = 0
     if x1 is not None:
         _bf16c(x1); C1 = x1.shape[-1]
@@ -173,7 +173,7 @@ def gn_apply_fwd(x0, stats0, gamma, beta, x1=None, stats1=None, film=None, film_
     _bf16c(x0); _f32c(stats0)
     B = x0.shape[0]
     C0 = x0.shape[-1]
-    HW = x0.numel() // (B * C0)
+    HW = x0[0].numel() // C0 if B else 0
     assert tuple(stats0.shape) == (B, C0, 2)
     C1 = 0
     if x1 is not None:
@@ -198,7 +198,7 @@ def gn_bwd(dy, x0, gamma, beta, mean, rstd, x1=None, film=None, film_off=0, silu
     _bf16c(dy); _bf16c(x0)
     B = x0.shape[0]
     C0 = x0.shape[-1]
-    HW = x0.numel() // (B * C0)
+    HW = x0[0].numel() // C0 if B else 0
     C1 = 0
     if x1 is not None:
         _bf16c(x1); C1 = x1.shape[-1]

@@ -428,3 +428,42 @@ def test_dag_layer_fwd_bwd(B, n, latent):
         assert relerr(p.grad - 0.25, g) < 1e-4
     # workspace is left zeroed for the next call
     assert float(mod._workspace(u).abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------ empty inputs
+def test_empty_batch_is_a_no_op_everywhere():
+    """a rank whose shard is empty (ragged sharding of interventions, shard_range with n < world) must be able to call
+    the whole path: every entry point accepts a zero batch, launches nothing and returns correctly shaped tensors"""
+    from causaldiffae_b200 import ops
+    d = dev()
+    z4 = torch.zeros(0, 3, 8, 8, device=d)
+    t0 = torch.zeros(0, dtype=torch.int64, device=d)
+    tab = torch.rand(10, device=d)
+    assert ops.q_sample(z4, z4, t0, tab, tab).shape == (0, 3, 8, 8)
+    mse, dp = ops.mse_loss(z4, z4, torch.zeros(0, device=d), want_grad=True)
+    assert mse.shape == (0,) and dp.shape == z4.shape
+    coef = torch.rand(5, 8, device=d)
+    out, x0 = ops.ddim_step(z4, z4, coef, torch.zeros(1, dtype=torch.int32, device=d), want_xstart=True)
+    assert out.shape == z4.shape and x0.shape == z4.shape
+    xb = torch.zeros(0, 8, 8, 64, device=d, dtype=bf16)
+    g, b = torch.ones(64, device=d), torch.zeros(64, device=d)
+    y, mean, rstd = ops.gn_fwd(xb, g, b)
+    assert y.shape == xb.shape and mean.shape == (0, 32)
+    y2, _, _ = ops.gn_apply_fwd(xb, torch.zeros(0, 64, 2, device=d), g, b)
+    assert y2.shape == xb.shape
+    dx0, _ = ops.gn_bwd(xb, xb, g, b, mean, rstd)
+    assert dx0.shape == xb.shape
+    w = torch.zeros(64, 9 * 64, device=d, dtype=bf16)
+    segs, _ = ops.conv_segments([64], 3)
+    o = torch.empty(0, 8, 8, 64, device=d, dtype=bf16)
+    ops.igemm(ops.make_igemm_desc([xb], segs, w, o, 64, stats=torch.zeros(0, 64, 2, device=d)))
+    dw = torch.zeros(64, 9, 64, device=d)
+    ops.wgrad(ops.make_wgrad_desc(o, xb, dw, 64, 64))
+    assert float(dw.abs().max()) == 0.0
+    qkv = torch.zeros(0, 16, 3 * 64, device=d, dtype=bf16)
+    ao, lse = ops.attn_fwd(qkv, 4)
+    assert ao.shape == (0, 16, 64)
+    im = torch.zeros(4, 8, 8, 3, dtype=torch.uint8, device=d)
+    gx, gl = ops.gather_images(im, t0, labels=torch.zeros(4, 2, device=d))
+    assert gx.shape == (0, 3, 8, 8) and gl.shape == (0, 2)
+    torch.cuda.synchronize()
