@@ -472,8 +472,8 @@ using namespace cdae;
   }
 
 extern "C" int cdae_attn_fwd(const void* qkv, void* out, float* lse, int B, int T, int heads, int ch, cdae_stream s) {
-  CDAE_CHECK_ARG(qkv && out, "attn_fwd: null pointer");
   if (B == 0 || T == 0) return CDAE_OK;
+  CDAE_CHECK_ARG(qkv && out, "attn_fwd: null pointer");
 #define CALL(N) (T <= 64 ? attn_fwd_launch<N, 4>(qkv, out, lse, B, T, heads, (cudaStream_t)s) \
                          : attn_fwd_launch<N, 8>(qkv, out, lse, B, T, heads, (cudaStream_t)s))
   CDAE_ATTN_DISPATCH(CALL)
@@ -482,8 +482,8 @@ extern "C" int cdae_attn_fwd(const void* qkv, void* out, float* lse, int B, int 
 
 extern "C" int cdae_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* dsum, void* dqkv,
                              int B, int T, int heads, int ch, cdae_stream s) {
-  CDAE_CHECK_ARG(qkv && out && dout && lse && dsum && dqkv, "attn_bwd: null pointer");
   if (B == 0 || T == 0) return CDAE_OK;
+  CDAE_CHECK_ARG(qkv && out && dout && lse && dsum && dqkv, "attn_bwd: null pointer");
 #define CALL(N) (T <= 64 ? attn_bwd_launch<N, 4>(qkv, out, dout, lse, dsum, dqkv, B, T, heads, (cudaStream_t)s) \
                          : attn_bwd_launch<N, 8>(qkv, out, dout, lse, dsum, dqkv, B, T, heads, (cudaStream_t)s))
   CDAE_ATTN_DISPATCH(CALL)

@@ -48,8 +48,8 @@ using namespace cdae;
 
 extern "C" int cdae_gather_images(const void* images_u8, const float* labels, const int64_t* idx, float* out,
                                   float* out_labels, int B, int H, int W, int C, int L, int mode, cdae_stream s) {
-  CDAE_CHECK_ARG(images_u8 && idx && out && (L == 0 || (labels && out_labels)), "gather_images: null pointer");
   if (B == 0) return CDAE_OK;
+  CDAE_CHECK_ARG(images_u8 && idx && out && (L == 0 || (labels && out_labels)), "gather_images: null pointer");
   const int HW = H * W;
   CDAE_CHECK_SHAPE(C >= 1 && C <= 4, "gather_images: %d channels (1..4 supported)", C);
   CDAE_CHECK_SHAPE(HW % 4 == 0 && HW > 0, "gather_images: H*W=%d must be a multiple of 4", HW);

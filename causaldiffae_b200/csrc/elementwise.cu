@@ -156,10 +156,10 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 
 extern "C" int cdae_q_sample(const float* x0, const float* noise, const int64_t* t, const float* sqrt_ac,
                              const float* sqrt_1mac, float* x_t, int64_t B, int64_t per_sample, cdae_stream s) {
+  if (B == 0) return CDAE_OK;
   CDAE_CHECK_ARG(x0 && noise && t && sqrt_ac && sqrt_1mac && x_t, "q_sample: null pointer");
   CDAE_CHECK_SHAPE(per_sample % 4 == 0 && aligned16(x0) && aligned16(noise) && aligned16(x_t),
                    "q_sample: per_sample %% 4 and 16-byte alignment required");
-  if (B == 0) return CDAE_OK;
   const int64_t nvec = B * per_sample / 4;
   q_sample_kernel<<<ew_grid(nvec), kEwThreads, 0, (cudaStream_t)s>>>((const float4*)x0, (const float4*)noise, t, sqrt_ac,
                                                                     sqrt_1mac, (float4*)x_t, nvec, per_sample / 4);
@@ -169,10 +169,10 @@ extern "C" int cdae_q_sample(const float* x0, const float* noise, const int64_t*
 
 extern "C" int cdae_mse_loss(const float* pred, const float* target, float* mse, const float* gscale, float* dpred,
                              int64_t B, int64_t per_sample, cdae_stream s) {
+  if (B == 0) return CDAE_OK;
   CDAE_CHECK_ARG(pred && target && mse, "mse_loss: null pointer");
   CDAE_CHECK_SHAPE(per_sample % 4 == 0 && aligned16(pred) && aligned16(target) && (!dpred || aligned16(dpred)),
                    "mse_loss: per_sample %% 4 and 16-byte alignment required");
-  if (B == 0) return CDAE_OK;
   mse_kernel<<<(unsigned)B, kEwThreads, 0, (cudaStream_t)s>>>((const float4*)pred, (const float4*)target, mse, gscale,
                                                                (float4*)dpred, per_sample / 4, 1.0f / (float)per_sample);
   CDAE_CHECK_LAUNCH("mse_kernel");
@@ -182,10 +182,10 @@ extern "C" int cdae_mse_loss(const float* pred, const float* target, float* mse,
 extern "C" int cdae_ddim_step(const float* x, const float* eps_c, const float* eps_u, float w, int use_w,
                               const float* coef_table, const int32_t* t_idx, int t_idx_stride, const float* noise,
                               float* x_prev, float* pred_xstart, int64_t B, int64_t per_sample, cdae_stream s) {
+  if (B == 0) return CDAE_OK;
   CDAE_CHECK_ARG(x && eps_c && coef_table && t_idx && x_prev && (!use_w || eps_u), "ddim_step: null pointer");
   CDAE_CHECK_SHAPE(per_sample % 4 == 0 && aligned16(x) && aligned16(eps_c) && aligned16(x_prev),
                    "ddim_step: per_sample %% 4 and 16-byte alignment required");
-  if (B == 0) return CDAE_OK;
   const int64_t nvec = B * per_sample / 4;
   ddim_kernel<<<ew_grid(nvec), kEwThreads, 0, (cudaStream_t)s>>>(
       (const float4*)x, (const float4*)eps_c, (const float4*)eps_u, w, use_w, coef_table, t_idx, t_idx_stride,
@@ -196,10 +196,10 @@ extern "C" int cdae_ddim_step(const float* x, const float* eps_c, const float* e
 
 extern "C" int cdae_adam_ema(float* p, const float* g, float* m, float* v, float* ema, const float* hyper,
                              float* gsq_out, int64_t n, cdae_stream s) {
+  if (n == 0) return CDAE_OK;
   CDAE_CHECK_ARG(p && g && m && v && hyper, "adam_ema: null pointer");
   CDAE_CHECK_SHAPE(n % 4 == 0 && aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v) && (!ema || aligned16(ema)),
                    "adam_ema: n %% 4 and 16-byte alignment required (pad the arena)");
-  if (n == 0) return CDAE_OK;
   adam_ema_kernel<<<ew_grid(n / 4), kEwThreads, 0, (cudaStream_t)s>>>((float4*)p, (const float4*)g, (float4*)m, (float4*)v,
                                                                      (float4*)ema, hyper, gsq_out, n / 4);
   CDAE_CHECK_LAUNCH("adam_ema_kernel");
@@ -207,9 +207,9 @@ extern "C" int cdae_adam_ema(float* p, const float* g, float* m, float* v, float
 }
 
 extern "C" int cdae_ema_update(float* ema, const float* p, float rate, int64_t n, cdae_stream s) {
+  if (n == 0) return CDAE_OK;
   CDAE_CHECK_ARG(ema && p, "ema_update: null pointer");
   CDAE_CHECK_SHAPE(n % 4 == 0 && aligned16(ema) && aligned16(p), "ema_update: n %% 4 and alignment");
-  if (n == 0) return CDAE_OK;
   ema_kernel<<<ew_grid(n / 4), kEwThreads, 0, (cudaStream_t)s>>>((float4*)ema, (const float4*)p, rate, n / 4);
   CDAE_CHECK_LAUNCH("ema_kernel");
   return CDAE_OK;

@@ -1288,8 +1288,8 @@ using namespace cdae;
 extern "C" int cdae_gn_fwd(const void* x0, int C0, const void* x1, int C1, int B, int HW, const float* gamma,
                            const float* beta, const float* film, int film_ld, int film_off, int silu, void* y,
                            float* mean, float* rstd, cdae_stream s) {
-  CDAE_CHECK_ARG(x0 && gamma && beta && y && mean && rstd && (C1 == 0 || x1), "gn_fwd: null pointer");
   if (B == 0) return CDAE_OK;
+  CDAE_CHECK_ARG(x0 && gamma && beta && y && mean && rstd && (C1 == 0 || x1), "gn_fwd: null pointer");
   GnParams p;
   memset(&p, 0, sizeof(p));
   p.x0 = (const __nv_bfloat16*)x0; p.x1 = (const __nv_bfloat16*)x1; p.C0 = C0; p.C1 = C1; p.HW = HW;
@@ -1314,8 +1314,8 @@ extern "C" int cdae_gn_fwd(const void* x0, int C0, const void* x1, int C1, int B
 extern "C" int cdae_gn_apply_fwd(const void* x0, int C0, const float* stats0, const void* x1, int C1, const float* stats1,
                                  int B, int HW, const float* gamma, const float* beta, const float* film, int film_ld,
                                  int film_off, int silu, void* y, float* mean, float* rstd, cdae_stream s) {
-  CDAE_CHECK_ARG(x0 && stats0 && gamma && beta && y && mean && rstd && (C1 == 0 || (x1 && stats1)), "gn_apply_fwd: null pointer");
   if (B == 0 || HW == 0) return CDAE_OK;
+  CDAE_CHECK_ARG(x0 && stats0 && gamma && beta && y && mean && rstd && (C1 == 0 || (x1 && stats1)), "gn_apply_fwd: null pointer");
   GnApplyParams p;
   memset(&p, 0, sizeof(p));
   p.x0 = (const __nv_bfloat16*)x0; p.x1 = (const __nv_bfloat16*)x1; p.st0 = stats0; p.st1 = stats1;
@@ -1348,8 +1348,8 @@ extern "C" int cdae_gn_bwd(const void* dy, const void* x0, int C0, const void* x
                            const float* gamma, const float* beta, const float* film, int film_ld, int film_off, int silu,
                            const float* mean, const float* rstd, const void* dadd, void* dx0, void* dx1, int accumulate_dx,
                            float* dgamma, float* dbeta, float* dfilm, cdae_stream s) {
-  CDAE_CHECK_ARG(dy && x0 && gamma && beta && mean && rstd && dx0 && (C1 == 0 || (x1 && dx1)), "gn_bwd: null pointer");
   if (B == 0) return CDAE_OK;
+  CDAE_CHECK_ARG(dy && x0 && gamma && beta && mean && rstd && dx0 && (C1 == 0 || (x1 && dx1)), "gn_bwd: null pointer");
   GnParams p;
   memset(&p, 0, sizeof(p));
   p.x0 = (const __nv_bfloat16*)x0; p.x1 = (const __nv_bfloat16*)x1; p.C0 = C0; p.C1 = C1; p.HW = HW;
@@ -1378,8 +1378,8 @@ extern "C" int cdae_gn_bwd_stream(const void* dy, const void* x0, int C0, const 
                                   const float* gamma, const float* beta, const float* film, int film_ld, int film_off,
                                   int silu, const float* mean, const float* rstd, const void* dadd, void* dx0, void* dx1,
                                   int accumulate_dx, float* dgamma, float* dbeta, float* dfilm, float* ws, cdae_stream s) {
-  CDAE_CHECK_ARG(dy && x0 && gamma && beta && mean && rstd && dx0 && ws && (C1 == 0 || (x1 && dx1)), "gn_bwd_stream: null pointer");
   if (B == 0 || HW == 0) return CDAE_OK;
+  CDAE_CHECK_ARG(dy && x0 && gamma && beta && mean && rstd && dx0 && ws && (C1 == 0 || (x1 && dx1)), "gn_bwd_stream: null pointer");
   GnBwdParams p;
   memset(&p, 0, sizeof(p));
   p.dy = (const __nv_bfloat16*)dy; p.x0 = (const __nv_bfloat16*)x0; p.x1 = (const __nv_bfloat16*)x1;

@@ -667,9 +667,9 @@ static bool halo_plan(const cdae_igemm_desc* d, IgemmKParams& kp) {
 using namespace cdae;
 
 extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
+  if (d && (d->N == 0 || d->H == 0 || d->W == 0)) return CDAE_OK;        // empty batch: nothing to compute
   CDAE_CHECK_ARG(d && d->out && d->wgt && d->nsrc >= 1 && d->nsrc <= 4, "igemm: bad descriptor");
   CDAE_CHECK_ARG(d->nseg >= 1 && d->nseg <= CDAE_MAX_SEG, "igemm: nseg %d out of range", d->nseg);
-  if (d->N == 0 || d->H == 0 || d->W == 0) return CDAE_OK;        // empty batch: nothing to compute
   CDAE_CHECK_SHAPE(d->in_stride == 1 || d->in_stride == 2, "igemm: in_stride %d", d->in_stride);
   CDAE_CHECK_SHAPE(d->wk % 8 == 0, "igemm: weight K %d must be a multiple of 8", d->wk);
   CDAE_CHECK_SHAPE((d->sps == 0 || d->sps == 1) && d->ooh == 0 && d->oow == 0, "igemm: strided output placement is not supported");
@@ -1150,8 +1150,8 @@ static int wgrad3(const cdae_wgrad_desc* d, cudaStream_t st) {
 }  // namespace cdae
 
 extern "C" int cdae_wgrad(const cdae_wgrad_desc* d, cdae_stream s) {
+  if (d && (d->N == 0 || d->OH == 0 || d->OW == 0)) return CDAE_OK;      // empty batch: dW += 0
   CDAE_CHECK_ARG(d && d->dy && d->src && d->dw, "wgrad: bad descriptor");
-  if (d->N == 0 || d->OH == 0 || d->OW == 0) return CDAE_OK;      // empty batch: dW += 0
   CDAE_CHECK_SHAPE(d->ksize == 1 || d->ksize == 3, "wgrad: ksize %d", d->ksize);
   CDAE_CHECK_SHAPE(d->in_stride == 1 || d->in_stride == 2, "wgrad: in_stride %d", d->in_stride);
   CDAE_CHECK_SHAPE(d->ldy % 8 == 0 && d->src_c % 8 == 0, "wgrad: pitches must be multiples of 8");

@@ -286,9 +286,9 @@ using namespace cdae;
 
 extern "C" int cdae_dag_fwd(const float* u, const float* A, const void* const* params, float* zpost, int B, int n, int d,
                             int D, cdae_stream s) {
+  if (B == 0) return CDAE_OK;
   CDAE_CHECK_ARG(u && A && params && zpost, "dag_fwd: null pointer");
   CDAE_CHECK_SHAPE(n >= 1 && n <= 8 && d % 4 == 0 && D % 4 == 0 && d >= 4 && D >= 4, "dag_fwd: n=%d d=%d D=%d unsupported", n, d, D);
-  if (B == 0) return CDAE_OK;
   const size_t smem = sizeof(float) * (size_t)kDagTB * (d + D);
   CDAE_CHECK_SHAPE(smem <= 48 * 1024, "dag_fwd: d + D = %d too large", d + D);
   dag_fwd_kernel<<<dim3(n, (B + kDagTB - 1) / kDagTB), kDagThreads, smem, (cudaStream_t)s>>>(
@@ -299,9 +299,9 @@ extern "C" int cdae_dag_fwd(const float* u, const float* A, const void* const* p
 
 extern "C" int cdae_dag_bwd(const float* u, const float* A, const void* const* params, const float* dzpost,
                             void* const* grads, float* dzp_ws, float* du, int B, int n, int d, int D, cdae_stream s) {
+  if (B == 0) return CDAE_OK;
   CDAE_CHECK_ARG(u && A && params && dzpost && grads && dzp_ws, "dag_bwd: null pointer");
   CDAE_CHECK_SHAPE(n >= 1 && n <= 8 && D % kDagHT == 0, "dag_bwd: n=%d D=%d unsupported", n, D);
-  if (B == 0) return CDAE_OK;
   const float* const* pp = reinterpret_cast<const float* const*>(params);
   float* const* gp = reinterpret_cast<float* const*>(grads);
   cudaStream_t st = (cudaStream_t)s;
