@@ -31,6 +31,21 @@ def _worker(rank, world, port, tmp, q):
     g = torch.full((8,), float(rank + 1))
     scale = dp_all_reduce_(g)
     assert scale == 1.0 / world and torch.equal(g * scale, torch.full((8,), 1.5))
+    # data path: load_data's dataset shard of this rank is the reference's rank-strided slice [rank:][::world]
+    from causaldiffae_b200 import image_datasets as ids
+    from tests.golden import dataset_fixture as fx
+    mm = os.path.join(tmp, "morphomnist")
+    if rank == 0:
+        fx.make_morphomnist(mm)
+    dist.barrier()
+    assert ids._rank_world() == (rank, world)
+    mine = ids.get_dataloader_morphomnist(mm, 2, "train", *ids._rank_world()).dataset
+    full = ids.MorphoMNISTLike(mm, columns=["thickness", "intensity"], train=True)
+    assert np.array_equal(mine.host_arrays()[0], full.host_arrays()[0][rank::world])
+    assert np.array_equal(mine.host_arrays()[1], full.host_arrays()[1][rank::world])
+    counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([len(mine)]))
+    assert sum(int(c) for c in counts) == len(full)                  # the shards partition the dataset
     # batch sharding of an intervention sweep: disjoint, ordered, covering
     lo, hi = shard_range(4097, rank, world)
     q.put((rank, lo, hi))
