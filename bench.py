@@ -445,7 +445,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch")
     ap.add_argument("--ref-batch", type=int, default=4, help="bounded per-step sample of the reference arm")
     ap.add_argument("--ddim-steps", type=int, default=50)
-    ap.add_argument("--ddim-batch", type=int, default=128)
+    ap.add_argument("--ddim-batch", type=int, default=512, help="interventions per GPU (BASELINE configs[3]: 4096 over 8 GPUs)")
     ap.add_argument("--no-ddim", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
