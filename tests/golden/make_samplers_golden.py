@@ -42,6 +42,19 @@ def main():
             for i in range(d.num_timesteps):        # DDIM inversion (encode) over the whole respaced chain
                 xs = d.ddim_reverse_sample(sc.stub_model, xs, torch.full((x.shape[0],), i, dtype=torch.long))["sample"]
             out[f"{name}/ddim_reverse_chain"] = xs.numpy()
+    # LossSecondMomentResampler (resample.py:122-156): the reference needs `np.int`, removed in numpy 1.24
+    if not hasattr(np, "int"):
+        np.int = int
+    d = ns.su.create_gaussian_diffusion(steps=sc.RESAMPLER["T"])
+    smp = ns.resample.LossSecondMomentResampler(d, history_per_term=sc.RESAMPLER["history"], uniform_prob=sc.RESAMPLER["uniform_prob"])
+    for r, (ts, losses) in enumerate(sc.resampler_batches()):
+        smp.update_with_all_losses(ts, losses)
+        if r in sc.RESAMPLER["check_rounds"]:
+            out[f"resampler/weights/{r}"] = np.asarray(smp.weights(), dtype=np.float64)
+            np.random.seed(100 + r)
+            t, w = smp.sample(16, torch.device("cpu"))
+            out[f"resampler/t/{r}"], out[f"resampler/w/{r}"] = t.numpy(), w.numpy()
+    out["resampler/history"] = smp._loss_history.copy()
     path = os.path.join(HERE, "samplers_v1.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path) // 1024, "KiB", len(out), "arrays")

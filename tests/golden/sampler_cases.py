@@ -26,3 +26,18 @@ def stub_model(x, t, **kwargs):
 
 def denoised_fn(v):
     return torch.tanh(v)
+
+
+RESAMPLER = dict(T=20, history=3, uniform_prob=0.01, check_rounds=(0, 5, 11, 12, 29))
+
+
+def resampler_batches(rounds=30, B=8):
+    """seeded (timesteps, losses) batches; early rounds leave some timesteps unseen (not warmed up), duplicates occur"""
+    g = torch.Generator().manual_seed(77)
+    for r in range(rounds):
+        hi = 12 if r < 4 else 20
+        ts = torch.randint(0, hi, (B,), generator=g).tolist()
+        if r >= 4:
+            ts[:4] = [(4 * r + k) % 20 for k in range(4)]      # sweep so that every timestep fills its history
+        losses = (torch.rand(B, generator=g) * (1 + 0.1 * r)).tolist()
+        yield ts, losses

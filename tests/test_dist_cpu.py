@@ -46,6 +46,15 @@ def _worker(rank, world, port, tmp, q):
     counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
     dist.all_gather(counts, torch.tensor([len(mine)]))
     assert sum(int(c) for c in counts) == len(full)                  # the shards partition the dataset
+    # loss-aware timestep resampling: ragged per-rank batches are gathered once, every rank ends with the same history
+    from causaldiffae_b200.resample import LossSecondMomentResampler
+    from types import SimpleNamespace
+    smp = LossSecondMomentResampler(SimpleNamespace(num_timesteps=6), history_per_term=2)
+    ts = [torch.tensor([0, 1, 2]), torch.tensor([3, 4, 5, 0, 1])][rank]
+    smp.update_with_local_losses(ts, ts.float() + 10.0 * (rank + 1))
+    expect = LossSecondMomentResampler(SimpleNamespace(num_timesteps=6), history_per_term=2)
+    expect.update_with_all_losses([0, 1, 2, 3, 4, 5, 0, 1], [10.0, 11.0, 12.0, 23.0, 24.0, 25.0, 20.0, 21.0])
+    assert np.array_equal(smp._loss_history, expect._loss_history) and np.array_equal(smp._loss_counts, expect._loss_counts)
     # batch sharding of an intervention sweep: disjoint, ordered, covering
     lo, hi = shard_range(4097, rank, world)
     q.put((rank, lo, hi))
