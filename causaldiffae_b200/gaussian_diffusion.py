@@ -397,5 +397,43 @@ class GaussianDiffusion:
         terms["loss"] = terms["mse"] + self.kl_weight * terms["kld_rep"] if rep_cond else terms["mse"]
         return terms
 
-    def calc_bpd_loop(self, *a, **k):
-        raise NotImplementedError("bits-per-dim evaluation needs learned sigmas (SURVEY Q18, next-row N4)")
+    # ------------------------------------------------------------------ variational bound (evaluation, ref :682-715, 862-935)
+    def _vb_terms_bpd(self, model, x_start, x_t, t, clip_denoised=True, model_kwargs=None):
+        """one term of the bound in bits/dim: decoder NLL at t == 0, KL(q(x_{t-1}|x_t,x_0) || p(x_{t-1}|x_t)) elsewhere"""
+        from .losses import normal_kl, discretized_gaussian_log_likelihood
+        from .nn import mean_flat
+        true_mean, _, true_logvar = self.q_posterior_mean_variance(x_start=x_start, x_t=x_t, t=t)
+        out = self.p_mean_variance(model, x_t, t, clip_denoised=clip_denoised, model_kwargs=model_kwargs)
+        kl = mean_flat(normal_kl(true_mean, true_logvar, out["mean"], out["log_variance"])) / np.log(2.0)
+        nll = -discretized_gaussian_log_likelihood(x_start, means=out["mean"], log_scales=0.5 * out["log_variance"])
+        nll = mean_flat(nll) / np.log(2.0)
+        return {"output": th.where(t == 0, nll, kl), "pred_xstart": out["pred_xstart"]}
+
+    def _prior_bpd(self, x_start):
+        """KL(q(x_T | x_0) || N(0, I)) in bits/dim (ref :862-878)"""
+        from .losses import normal_kl
+        from .nn import mean_flat
+        t = th.full((x_start.shape[0],), self.num_timesteps - 1, device=x_start.device, dtype=th.long)
+        qt_mean, _, qt_logvar = self.q_mean_variance(x_start, t)
+        return mean_flat(normal_kl(mean1=qt_mean, logvar1=qt_logvar, mean2=0.0, logvar2=0.0)) / np.log(2.0)
+
+    def calc_bpd_loop(self, model, x_start, clip_denoised=True, model_kwargs=None):
+        """whole bound, T -> 0 (ref :880-935): {"total_bpd" [N], "prior_bpd" [N], "vb" [N,T], "xstart_mse" [N,T], "mse" [N,T]}"""
+        from .nn import mean_flat
+        device, B = x_start.device, x_start.shape[0]
+        vb, xstart_mse, mse = [], [], []
+        steps = th.arange(self.num_timesteps, device=device, dtype=th.long)
+        for i in range(self.num_timesteps - 1, -1, -1):
+            t = steps[i:i + 1].expand(B)
+            noise = th.randn_like(x_start)
+            x_t = self.q_sample(x_start=x_start, t=t, noise=noise)
+            with th.no_grad():
+                out = self._vb_terms_bpd(model, x_start=x_start, x_t=x_t, t=t, clip_denoised=clip_denoised,
+                                         model_kwargs=model_kwargs)
+            vb.append(out["output"])
+            xstart_mse.append(mean_flat((out["pred_xstart"] - x_start) ** 2))
+            eps = self._predict_eps_from_xstart(x_t, t, out["pred_xstart"])
+            mse.append(mean_flat((eps - noise) ** 2))
+        vb, xstart_mse, mse = th.stack(vb, dim=1), th.stack(xstart_mse, dim=1), th.stack(mse, dim=1)
+        prior_bpd = self._prior_bpd(x_start)
+        return {"total_bpd": vb.sum(dim=1) + prior_bpd, "prior_bpd": prior_bpd, "vb": vb, "xstart_mse": xstart_mse, "mse": mse}

@@ -35,7 +35,14 @@ def main():
         out[f"{name}/q_post/mean"], out[f"{name}/q_post/var"], out[f"{name}/q_post/logvar"] = m.numpy(), v.numpy(), lv.numpy()
         m, v, lv = d.q_mean_variance(x, t)
         out[f"{name}/q_mv/mean"], out[f"{name}/q_mv/var"], out[f"{name}/q_mv/logvar"] = m.numpy(), v.numpy(), lv.numpy()
+        vbt = d._vb_terms_bpd(sc.stub_model, x * 0.5, x, t)
+        out[f"{name}/vb/output"], out[f"{name}/vb/pred_xstart"] = vbt["output"].numpy(), vbt["pred_xstart"].numpy()
+        out[f"{name}/prior_bpd"] = d._prior_bpd(x * 0.5).numpy()
         if d.num_timesteps <= 20:
+            torch.manual_seed(13)
+            bpd = d.calc_bpd_loop(sc.stub_model, x.clamp(-1, 1))
+            for k, v in bpd.items():
+                out[f"{name}/bpd/{k}"] = v.numpy()
             torch.manual_seed(12)
             out[f"{name}/p_sample_loop"] = d.p_sample_loop(sc.stub_model, tuple(x.shape), noise=x, device="cpu").numpy()
             xs = x
