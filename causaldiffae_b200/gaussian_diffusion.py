@@ -288,7 +288,7 @@ class GaussianDiffusion:
         eps_c, eps_u = self._model_eps(model, x, t, model_kwargs, w)
         noise = th.randn_like(x) if eta != 0.0 else None
         tab = self._ddim_table(x.device, eta, clip_denoised)
-        sample, x0 = ops.ddim_step(x.float().contiguous(), eps_c.float().contiguous(), tab, t.to(th.int32),
+        sample, x0 = ops.ddim_step(x.float().contiguous(), eps_c.float().contiguous(), tab, t.to(th.int32).contiguous(),
                                    eps_u=None if eps_u is None else eps_u.float().contiguous(), w=w, noise=noise,
                                    want_xstart=True)
         return {"sample": sample, "pred_xstart": x0}
@@ -422,9 +422,8 @@ class GaussianDiffusion:
         from .nn import mean_flat
         device, B = x_start.device, x_start.shape[0]
         vb, xstart_mse, mse = [], [], []
-        steps = th.arange(self.num_timesteps, device=device, dtype=th.long)
         for i in range(self.num_timesteps - 1, -1, -1):
-            t = steps[i:i + 1].expand(B)
+            t = th.full((B,), i, device=device, dtype=th.long)
             noise = th.randn_like(x_start)
             x_t = self.q_sample(x_start=x_start, t=t, noise=noise)
             with th.no_grad():

@@ -27,7 +27,8 @@ def _bf16c(t):
 def q_sample(x0, noise, t, sqrt_ac, sqrt_1mac, out=None):
     """ref gaussian_diffusion.py:201-222"""
     _f32c(x0); _f32c(noise); _f32c(sqrt_ac); _f32c(sqrt_1mac)
-    assert t.dtype == torch.int64 and t.is_cuda and x0.shape == noise.shape
+    assert t.dtype == torch.int64 and t.is_cuda and x0.shape == noise.shape and t.numel() == x0.shape[0]
+    t = t.contiguous()          # an expanded (stride-0) view would be read past its one element
     out = torch.empty_like(x0) if out is None else out
     B = x0.shape[0]
     if x0.numel() == 0:
