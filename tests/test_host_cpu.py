@@ -130,3 +130,27 @@ def test_no_cpu_fallback():
         model(x, torch.tensor([1, 2]))
     src = "".join(open(os.path.join(ROOT, "causaldiffae_b200", f)).read() for f in os.listdir(os.path.join(ROOT, "causaldiffae_b200")) if f.endswith(".py"))
     assert "import oracle" not in src and "from oracle" not in src, "the product must never import the oracle"
+
+
+def test_fp16_util_master_param_round_trip():
+    """ref fp16_util.py:27-76: one flat fp32 master parameter; gradients flatten in parameter order; zero_grad in place"""
+    from causaldiffae_b200 import fp16_util as fu
+    g = torch.Generator().manual_seed(0)
+    params = [torch.nn.Parameter(torch.randn(s, generator=g)) for s in ((3, 4), (5,), (2, 2, 2))]
+    master = fu.make_master_params(params)
+    assert len(master) == 1 and master[0].requires_grad and master[0].dtype == torch.float32
+    assert torch.equal(master[0].detach(), torch.cat([p.detach().reshape(-1) for p in params]))
+    for p in params:
+        p.grad = torch.randn(p.shape, generator=g)
+    fu.model_grads_to_master_grads(params, master)
+    assert torch.equal(master[0].grad, torch.cat([p.grad.reshape(-1) for p in params]))
+    with torch.no_grad():
+        master[0].mul_(2.0)
+    fu.master_params_to_model_params(params, master)
+    for p, u in zip(params, fu.unflatten_master_params(params, master)):
+        assert torch.equal(p.detach(), u) and u.shape == p.shape
+    grads = [p.grad for p in params]
+    fu.zero_grad(params)
+    assert all(p.grad is gr and float(gr.abs().sum()) == 0.0 for p, gr in zip(params, grads))    # zeroed in place, never None
+    lin = torch.nn.Linear(2, 2)
+    assert fu.convert_module_to_f16(lin) is lin and fu.convert_module_to_f32(lin) is lin and lin.weight.dtype == torch.float32
