@@ -154,3 +154,35 @@ def test_fp16_util_master_param_round_trip():
     assert all(p.grad is gr and float(gr.abs().sum()) == 0.0 for p, gr in zip(params, grads))    # zeroed in place, never None
     lin = torch.nn.Linear(2, 2)
     assert fu.convert_module_to_f16(lin) is lin and fu.convert_module_to_f32(lin) is lin and lin.weight.dtype == torch.float32
+
+
+def test_c_abi_error_convention_without_a_gpu():
+    """entry points return 0 / a negative cdae_status (never raise, never exit) and leave a message in
+    cdae_last_error(); argument and shape checks run before any CUDA call, zero-sized batches are accepted as no-ops."""
+    from causaldiffae_b200 import _lib
+    lib = _lib.load()
+    buf = ctypes.create_string_buffer(4096 + 64)
+    p = (ctypes.addressof(buf) + 63) // 64 * 64               # a 64 B aligned, never dereferenced pointer
+    OK, ERR_ARG, ERR_SHAPE = 0, -1, -2
+    # null pointers
+    assert lib.cdae_q_sample(None, p, p, p, p, p, 2, 64, None) == ERR_ARG
+    assert b"null" in lib.cdae_last_error().lower()
+    assert lib.cdae_gather_images(None, None, p, p, None, 2, 8, 8, 3, 0, 0, None) == ERR_ARG
+    # shapes the kernels do not support
+    assert lib.cdae_q_sample(p, p, p, p, p, p, 2, 63, None) == ERR_SHAPE                      # per_sample % 4
+    assert lib.cdae_gather_images(p, None, p, p, None, 2, 8, 8, 5, 0, 0, None) == ERR_SHAPE   # 5 channels
+    assert b"channels" in lib.cdae_last_error()
+    assert lib.cdae_gather_images(p, None, p, p, None, 2, 3, 3, 1, 0, 0, None) == ERR_SHAPE   # H*W % 4
+    assert lib.cdae_gn_apply_fwd(p, 40, p, None, 0, None, 2, 16, p, p, None, 0, 0, 1, p, p, p, None) == ERR_SHAPE   # C % 32
+    assert lib.cdae_gn_bwd_stream(p, p, 64, None, 0, 2, 16, p, p, None, 0, 0, 1, p, p, None, p, None, 0, None, None, None,
+                                  None, None) == ERR_ARG                                   # workspace missing
+    d = _lib.IgemmDesc()
+    d.out, d.wgt, d.nsrc, d.nseg, d.N, d.H, d.W = p, p, 1, 0, 1, 8, 8
+    assert lib.cdae_igemm(ctypes.byref(d), None) == ERR_ARG                                   # no K segments
+    assert b"nseg" in lib.cdae_last_error()
+    # zero-sized batches: accepted before any pointer check (empty torch tensors carry null pointers)
+    assert lib.cdae_q_sample(None, None, None, None, None, None, 0, 64, None) == OK
+    assert lib.cdae_gather_images(None, None, None, None, None, 0, 8, 8, 3, 0, 0, None) == OK
+    assert lib.cdae_gn_fwd(None, 64, None, 0, 0, 16, None, None, None, 0, 0, 1, None, None, None, None) == OK
+    d.N = 0
+    assert lib.cdae_igemm(ctypes.byref(d), None) == OK
