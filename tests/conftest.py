@@ -26,3 +26,9 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden():
     return np.load(os.path.join(ROOT, "tests", "golden", "golden_v1.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_shipped():
+    """reference outputs at the shipped image sizes (28 / 96 / 128 px), tests/golden/make_golden.py --shipped"""
+    return np.load(os.path.join(ROOT, "tests", "golden", "golden_v2_shipped.npz"))

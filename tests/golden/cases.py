@@ -42,6 +42,35 @@ MODEL_CASES = {
         grad_probe=["input_blocks.1.0.emb_layers.1.weight", "time_embed.0.weight"]),
 }
 
+CIRCUIT = [[0, 1, 1, 1], [0, 0, 0, 1], [0, 0, 0, 1], [0, 0, 0, 0]]
+
+# The image sizes of the reference's shipped launch lines (scripts/{morhomnist,pendulum,circuit}/train_*_causaldae.sh):
+# 28 px (three levels, odd 7x7 bottom, attention at 28x28), 96 px (RGBA, no attention level, the reference's own 6-conv
+# encoder), 128 px (six levels, attention at 16x16 / 8x8).  Narrow (32 channels, one res block) and small batches so
+# that the fixtures stay small (`sub`: image-shaped outputs are stored every sub-th pixel); stored in
+# golden_v2_shipped.npz by make_golden.py --shipped.
+SHIPPED_CASES = {
+    "mnist28": dict(
+        flags=dict(image_size=28, num_channels=32, num_res_blocks=1, class_cond=True, n_vars=2, in_channels=1,
+                   masking=True, **_COMMON),
+        A=None, B=2, wseed=6, iseed=21, rseed=31, kl_weight=0.3, respacing="ddim5", do_value=0.2,
+        ddim=[("w15", 1.5)], train_steps=0,
+        grad_probe=["out.2.weight", "input_blocks.1.1.qkv.weight", "rep_emb.fc_mu.bias", "label_emb.weight"]),
+    "pend96": dict(
+        flags=dict(image_size=96, num_channels=32, num_res_blocks=1, class_cond=False, n_vars=4, in_channels=4,
+                   masking=True, **_COMMON),
+        A=PENDULUM, B=2, sub=4, wseed=7, iseed=22, rseed=32, kl_weight=0.3, respacing="ddim5", do_value=-0.2,
+        ddim=[], train_steps=0,
+        grad_probe=["out.2.weight", "input_blocks.0.0.weight", "rep_emb.encoder.5.0.weight", "output_blocks.7.0.skip_connection.weight"]),
+    "circ128": dict(
+        flags=dict(image_size=128, num_channels=32, num_res_blocks=1, class_cond=False, n_vars=4, in_channels=3,
+                   **_COMMON),
+        A=CIRCUIT, B=2, sub=4, wseed=8, iseed=23, rseed=33, kl_weight=0.3, respacing="ddim5", do_value=0.4,
+        ddim=[], train_steps=0,
+        grad_probe=["out.2.weight", "middle_block.1.proj_out.weight", "rep_emb.encoder.5.0.weight", "causal_mask.nonlinearities.3.net.2.bias"]),
+}
+ALL_CASES = {**MODEL_CASES, **SHIPPED_CASES}
+
 
 def make_inputs(case):
     f = case["flags"]

@@ -72,10 +72,11 @@ def gen_model_case(ns, name, case, out):
     model.eval()
     with torch.no_grad():
         x_t = diff.q_sample(inp["x0"], inp["t"], inp["noise"])
-        out[f"{name}/x_t"] = x_t.numpy()
+        sub = case.get("sub", 1)
+        out[f"{name}/x_t"] = x_t.numpy()[..., ::sub, ::sub]
         zkw = {k: v for k, v in kw.items() if k == "y"}
         eps_z = model(x_t, torch.tensor(diff.timestep_map)[inp["t"]], z=inp["z"], **zkw)[0]
-        out[f"{name}/eps_given_z"] = eps_z.numpy()
+        out[f"{name}/eps_given_z"] = eps_z.numpy()[..., ::sub, ::sub]
         mu, var = model.rep_emb.encode(inp["x0"])
         out[f"{name}/enc_mu_eval"], out[f"{name}/enc_var_eval"] = mu.numpy(), var.numpy()
         At = torch.tensor(cfg.A, dtype=torch.float32)
@@ -138,6 +139,14 @@ def main():
     assert refshim.available(), "reference tree not present"
     ns = refshim.load()
     out = {}
+    if "--shipped" in sys.argv:       # the shipped image sizes (28 / 96 / 128 px) -> golden_v2_shipped.npz
+        for name, case in cases.SHIPPED_CASES.items():
+            gen_model_case(ns, name, case, out)
+            print("generated", name)
+        path = os.path.join(HERE, "golden_v2_shipped.npz")
+        np.savez_compressed(path, **out)
+        print(path, os.path.getsize(path) / 1e6, "MB", len(out), "arrays")
+        return
     gen_schedules(ns, out)
     for name, case in cases.MODEL_CASES.items():
         gen_model_case(ns, name, case, out)

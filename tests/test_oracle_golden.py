@@ -65,9 +65,10 @@ def _setup(case):
     return cfg, sd, cases.make_inputs(case)
 
 
-@pytest.mark.parametrize("name", list(cases.MODEL_CASES))
-def test_training_losses_and_grads(golden, name):
-    case = cases.MODEL_CASES[name]
+@pytest.mark.parametrize("name", list(cases.ALL_CASES))
+def test_training_losses_and_grads(golden, golden_shipped, name):
+    case = cases.ALL_CASES[name]
+    golden = golden_shipped if name in cases.SHIPPED_CASES else golden
     cfg, sd, inp = _setup(case)
     for n in om.trainable_names(cfg):
         sd[n].requires_grad_(True)
@@ -87,9 +88,10 @@ def test_training_losses_and_grads(golden, name):
         assert np.linalg.norm(got - ref) <= 1e-4 * np.linalg.norm(ref) + 1e-9, pn
 
 
-@pytest.mark.parametrize("name", list(cases.MODEL_CASES))
-def test_eval_paths(golden, name):
-    case = cases.MODEL_CASES[name]
+@pytest.mark.parametrize("name", list(cases.ALL_CASES))
+def test_eval_paths(golden, golden_shipped, name):
+    case = cases.ALL_CASES[name]
+    golden = golden_shipped if name in cases.SHIPPED_CASES else golden
     cfg, sd, inp = _setup(case)
     diff = od.Diffusion(steps=case["flags"]["diffusion_steps"])
     with torch.no_grad():
@@ -98,11 +100,12 @@ def test_eval_paths(golden, name):
         od.training_losses(diff, sd, cfg, inp["x0"], inp["t"], inp["noise"], y=inp["y"] if cfg.num_classes else None,
                            c=inp["c"])
         x_t = diff.q_sample(inp["x0"], inp["t"], inp["noise"])
-        np.testing.assert_allclose(x_t.numpy(), golden[f"{name}/x_t"], rtol=0, atol=1e-7)
+        sub = case.get("sub", 1)                  # large fixtures keep every sub-th pixel
+        np.testing.assert_allclose(x_t.numpy()[..., ::sub, ::sub], golden[f"{name}/x_t"], rtol=0, atol=1e-7)
         eps = om.unet_forward(sd, cfg, x_t, diff.model_timesteps(inp["t"]), y=inp["y"] if cfg.num_classes else None,
                               z=inp["z"], training=False)[0]
         ref = golden[f"{name}/eps_given_z"]
-        assert np.linalg.norm(eps.numpy() - ref) <= 2e-5 * np.linalg.norm(ref)
+        assert np.linalg.norm(eps.numpy()[..., ::sub, ::sub] - ref) <= 2e-5 * np.linalg.norm(ref)
         mu, var = om.encoder_encode(sd, cfg, inp["x0"], training=False)
         np.testing.assert_allclose(mu.numpy(), golden[f"{name}/enc_mu_eval"], rtol=1e-4, atol=1e-5)
         np.testing.assert_allclose(var.numpy(), golden[f"{name}/enc_var_eval"], rtol=1e-4, atol=1e-6)
@@ -110,9 +113,10 @@ def test_eval_paths(golden, name):
         np.testing.assert_allclose(zp.numpy(), golden[f"{name}/z_post_eval"], rtol=1e-4, atol=1e-5)
 
 
-@pytest.mark.parametrize("name,tag,w", [(n, t, w) for n, c in cases.MODEL_CASES.items() for t, w in c["ddim"]])
-def test_ddim_counterfactual(golden, name, tag, w):
-    case = cases.MODEL_CASES[name]
+@pytest.mark.parametrize("name,tag,w", [(n, t, w) for n, c in cases.ALL_CASES.items() for t, w in c["ddim"]])
+def test_ddim_counterfactual(golden, golden_shipped, name, tag, w):
+    case = cases.ALL_CASES[name]
+    golden = golden_shipped if name in cases.SHIPPED_CASES else golden
     cfg, sd, inp = _setup(case)
     d0 = od.Diffusion(steps=case["flags"]["diffusion_steps"])
     with torch.no_grad():
