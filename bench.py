@@ -446,11 +446,27 @@ def ddim_bench(model, world, dev, args):
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    model.train()
     peaks = load_peaks()
     tf = steps * FWD_GFLOP_PER_IMG * 1e9 * Bd / float(ms) / 1e9
-    return {"metric": f"ddim{steps}_counterfactual_img_per_s", "value": Bd * world / (float(ms) / 1000), "unit": "img/s",
-            "batch_per_gpu": Bd, "ms": float(ms), "tflops_per_gpu": tf, "frac_of_sustained_peak": tf / peaks["tf_sus"]}
+    res = {"metric": f"ddim{steps}_counterfactual_img_per_s", "value": Bd * world / (float(ms) / 1000), "unit": "img/s",
+           "batch_per_gpu": Bd, "ms": float(ms), "tflops_per_gpu": tf, "frac_of_sustained_peak": tf / peaks["tf_sus"]}
+    if world == 1:
+        # BASELINE configs[4]: classifier-free guided sampling (w = 1.5): two UNet forwards per DDIM step + the fused combine
+        try:
+            counterfactual(model, diff, x, do_var=0, do_value=0.2, w=1.5)
+            torch.cuda.synchronize()
+            e0.record()
+            counterfactual(model, diff, x, do_var=0, do_value=-0.35, w=1.5)
+            e1.record()
+            torch.cuda.synchronize()
+            gms = e0.elapsed_time(e1)
+            gtf = 2 * steps * FWD_GFLOP_PER_IMG * 1e9 * Bd / gms / 1e9
+            res["guided_w1.5"] = {"value": Bd / (gms / 1000), "unit": "img/s", "ms": gms, "tflops_per_gpu": gtf,
+                                  "frac_of_sustained_peak": gtf / peaks["tf_sus"]}
+        except Exception as ex:
+            res["guided_w1.5"] = {"error": repr(ex)}
+    model.train()
+    return res
 
 
 def main():
