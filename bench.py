@@ -251,9 +251,10 @@ def hbm_kernels(peaks):
     sets = [[torch.randn(P, device=dev) * 0.01 for _ in range(5)] for _ in range(2)]
     for s_ in sets:
         s_[3].abs_()
-    hyper = torch.tensor([1e-4, 0.9, 0.999, 1e-8, 0.0, 1e-4, 1.0, 0.9999, 1.0], device=dev)
+    hyper = torch.tensor([1e-4, 0.9, 0.999, 1e-8, 0.0, 0.9999, 1.0, 0.0], device=dev)
     gsq = torch.zeros(1, device=dev)
-    ms = timeit([lambda a=a: ops.adam_ema(a[0], a[1], a[2], a[3], a[4], hyper, gsq) for a in sets])
+    astep = torch.zeros(1, device=dev, dtype=torch.int64)
+    ms = timeit([lambda a=a: ops.adam_ema(a[0], a[1], a[2], a[3], a[4], hyper, astep, gsq) for a in sets])
     out["adam_ema"] = (36.0 * P, ms)
     del sets
     # GroupNorm32 + FiLM + SiLU on the heaviest cfg2 layer shape (concat 128+128 channels at 64x64, the per-GPU batch of

@@ -59,7 +59,9 @@ _SIGS = {
     "cdae_q_sample": ([P, P, P, P, P, P, I64, I64, P], C.c_int),
     "cdae_mse_loss": ([P, P, P, P, P, I64, I64, P], C.c_int),
     "cdae_ddim_step": ([P, P, P, F32, I32, P, P, I32, P, P, P, I64, I64, P], C.c_int),
-    "cdae_adam_ema": ([P, P, P, P, P, P, P, I64, P], C.c_int),
+    "cdae_adam_ema": ([P, P, I32, P, P, P, P, P, P, P, I64, P], C.c_int),
+    "cdae_sumsq": ([P, I32, P, I64, P], C.c_int),
+    "cdae_cast_bf16": ([P, P, I64, P], C.c_int),
     "cdae_ema_update": ([P, P, F32, I64, P], C.c_int),
     "cdae_zero": ([P, I64, P], C.c_int),
     "cdae_nchw_to_nhwc_pad": ([P, P, I32, I32, I32, I32, I32, P], C.c_int),

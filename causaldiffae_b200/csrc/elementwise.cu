@@ -93,17 +93,34 @@ __global__ void __launch_bounds__(kEwThreads) ddim_kernel(const float4* __restri
   }
 }
 
-// ---------------------------------------------------------------- AdamW + EMA + sum(g^2)  (ref train_util.py:292-303, nn.py:503-513)
-// hyper (device): {lr, beta1, beta2, eps, weight_decay, step_size = lr/bias_corr1, sqrt(bias_corr2), ema_rate, grad_scale}
-__global__ void __launch_bounds__(kEwThreads) adam_ema_kernel(float4* __restrict__ p, const float4* __restrict__ g,
+// ---------------------------------------------------------------- AdamW + EMA + sum(g^2)  (ref train_util.py:276-303, nn.py:503-513)
+// hyper (device): {lr, beta1, beta2, eps, weight_decay, ema_rate, grad_scale}; *step = optimizer steps taken so far (the
+// bias corrections are those of step + 1, evaluated in double like torch.optim.AdamW does on the host); guard (optional):
+// a device scalar that must be finite for the step to happen (sum of squared gradients, cdae_sumsq) - otherwise the whole
+// launch is a no-op, which is the "skip the step" of the reference's optimize_fp16.  G = float (fp32 gradient arena) or
+// __nv_bfloat16 (the all-reduced bf16 copy of it).
+__device__ __forceinline__ float4 ldg4(const float4* g, int64_t i) { return g[i]; }
+__device__ __forceinline__ float4 ldg4(const uint2* g, int64_t i) {
+  const uint2 u = g[i];
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                     __uint_as_float(u.y & 0xffff0000u));
+}
+
+template <typename GV>
+__global__ void __launch_bounds__(kEwThreads) adam_ema_kernel(float4* __restrict__ p, const GV* __restrict__ g,
                                                               float4* __restrict__ m, float4* __restrict__ v,
                                                               float4* __restrict__ ema, const float* __restrict__ hyper,
+                                                              const int64_t* __restrict__ step,
+                                                              const float* __restrict__ guard,
                                                               float* __restrict__ gsq_out, int64_t nvec) {
-  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], step_size = hyper[5],
-              bc2s = hyper[6], er = hyper[7], gscale = hyper[8];
+  if (guard && !isfinite(*guard)) return;
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], er = hyper[5], gscale = hyper[6];
+  const double t = (double)(*step + 1);
+  const float step_size = (float)((double)lr / (1.0 - pow((double)b1, t)));
+  const float bc2s = (float)sqrt(1.0 - pow((double)b2, t));
   float gsq = 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-    float4 pv = p[i], gv = g[i], mv = m[i], vv = v[i];
+    float4 pv = p[i], gv = ldg4(g, i), mv = m[i], vv = v[i];
     float pp[4] = {pv.x, pv.y, pv.z, pv.w}, gg[4] = {gv.x, gv.y, gv.z, gv.w}, mm[4] = {mv.x, mv.y, mv.z, mv.w},
           v2[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
@@ -132,10 +149,44 @@ __global__ void __launch_bounds__(kEwThreads) adam_ema_kernel(float4* __restrict
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = gsq;
     __syncthreads();
     if (threadIdx.x < 32) {
-      float t = threadIdx.x < kEwThreads / 32 ? red[threadIdx.x] : 0.f;
-      t = warp_sum(t);
-      if (threadIdx.x == 0) atomicAdd(gsq_out, t);
+      float t2 = threadIdx.x < kEwThreads / 32 ? red[threadIdx.x] : 0.f;
+      t2 = warp_sum(t2);
+      if (threadIdx.x == 0) atomicAdd(gsq_out, t2);
     }
+  }
+}
+
+// runs after the update: the step counter moves on unless the guard vetoed the step
+__global__ void adam_tick_kernel(int64_t* step, const float* guard) {
+  if (!(guard && !isfinite(*guard))) *step += 1;
+}
+
+// sum of squares of a flat fp32 buffer accumulated into *out (the non-finite-gradient guard; also a grad-norm probe)
+template <typename GV>
+__global__ void __launch_bounds__(kEwThreads) sumsq_kernel(const GV* __restrict__ g, float* __restrict__ out, int64_t nvec) {
+  float acc = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = ldg4(g, i);
+    acc += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+  }
+  __shared__ float red[kEwThreads / 32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < kEwThreads / 32 ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) atomicAdd(out, t);
+  }
+}
+
+// fp32 -> bf16 (round to nearest even) copy of a flat buffer: the gradient arena as it goes on the wire
+__global__ void __launch_bounds__(kEwThreads) cast_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst,
+                                                               int64_t nvec) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = src[i];
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
+    dst[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
   }
 }
 
@@ -194,15 +245,45 @@ extern "C" int cdae_ddim_step(const float* x, const float* eps_c, const float* e
   return CDAE_OK;
 }
 
-extern "C" int cdae_adam_ema(float* p, const float* g, float* m, float* v, float* ema, const float* hyper,
-                             float* gsq_out, int64_t n, cdae_stream s) {
+extern "C" int cdae_adam_ema(float* p, const void* g, int g_is_bf16, float* m, float* v, float* ema, const float* hyper,
+                             int64_t* step, const float* guard, float* gsq_out, int64_t n, cdae_stream s) {
   if (n == 0) return CDAE_OK;
-  CDAE_CHECK_ARG(p && g && m && v && hyper, "adam_ema: null pointer");
-  CDAE_CHECK_SHAPE(n % 4 == 0 && aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v) && (!ema || aligned16(ema)),
+  CDAE_CHECK_ARG(p && g && m && v && hyper && step, "adam_ema: null pointer");
+  CDAE_CHECK_SHAPE(n % 4 == 0 && aligned16(p) && aligned16(m) && aligned16(v) && (!ema || aligned16(ema)) &&
+                       (reinterpret_cast<uintptr_t>(g) & (g_is_bf16 ? 7 : 15)) == 0,
                    "adam_ema: n %% 4 and 16-byte alignment required (pad the arena)");
-  adam_ema_kernel<<<ew_grid(n / 4), kEwThreads, 0, (cudaStream_t)s>>>((float4*)p, (const float4*)g, (float4*)m, (float4*)v,
-                                                                     (float4*)ema, hyper, gsq_out, n / 4);
+  if (g_is_bf16)
+    adam_ema_kernel<uint2><<<ew_grid(n / 4), kEwThreads, 0, (cudaStream_t)s>>>((float4*)p, (const uint2*)g, (float4*)m,
+                                                                              (float4*)v, (float4*)ema, hyper, step, guard,
+                                                                              gsq_out, n / 4);
+  else
+    adam_ema_kernel<float4><<<ew_grid(n / 4), kEwThreads, 0, (cudaStream_t)s>>>((float4*)p, (const float4*)g, (float4*)m,
+                                                                               (float4*)v, (float4*)ema, hyper, step, guard,
+                                                                               gsq_out, n / 4);
   CDAE_CHECK_LAUNCH("adam_ema_kernel");
+  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)s>>>(step, guard);
+  CDAE_CHECK_LAUNCH("adam_tick_kernel");
+  return CDAE_OK;
+}
+
+extern "C" int cdae_sumsq(const void* g, int g_is_bf16, float* out, int64_t n, cdae_stream s) {
+  if (n == 0) return CDAE_OK;
+  CDAE_CHECK_ARG(g && out, "sumsq: null pointer");
+  CDAE_CHECK_SHAPE(n % 4 == 0 && (reinterpret_cast<uintptr_t>(g) & (g_is_bf16 ? 7 : 15)) == 0,
+                   "sumsq: n %% 4 and 16-byte alignment required");
+  if (g_is_bf16) sumsq_kernel<uint2><<<ew_grid(n / 4), kEwThreads, 0, (cudaStream_t)s>>>((const uint2*)g, out, n / 4);
+  else sumsq_kernel<float4><<<ew_grid(n / 4), kEwThreads, 0, (cudaStream_t)s>>>((const float4*)g, out, n / 4);
+  CDAE_CHECK_LAUNCH("sumsq_kernel");
+  return CDAE_OK;
+}
+
+extern "C" int cdae_cast_bf16(const float* src, void* dst_bf16, int64_t n, cdae_stream s) {
+  if (n == 0) return CDAE_OK;
+  CDAE_CHECK_ARG(src && dst_bf16, "cast_bf16: null pointer");
+  CDAE_CHECK_SHAPE(n % 4 == 0 && aligned16(src) && (reinterpret_cast<uintptr_t>(dst_bf16) & 7) == 0,
+                   "cast_bf16: n %% 4 and alignment required");
+  cast_bf16_kernel<<<ew_grid(n / 4), kEwThreads, 0, (cudaStream_t)s>>>((const float4*)src, (uint2*)dst_bf16, n / 4);
+  CDAE_CHECK_LAUNCH("cast_bf16_kernel");
   return CDAE_OK;
 }
 

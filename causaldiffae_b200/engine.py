@@ -81,6 +81,7 @@ class Plan:
         self.bufs = []
         self.fwd_graph = self.bwd_graph = None
         self.runs = 0
+        self.generation, self.pending = 0, False     # which forward the saved activations belong to / awaits backward
         self.n_fwd_launch = self.n_bwd_launch = 0
         # per-(image, channel) GroupNorm sums accumulated by conv epilogues: carved from a few big chunks that the
         # first node of the forward graph zeroes
@@ -258,6 +259,27 @@ class Engine:
         a0 = self.arena.data_ptr()
         return a0 <= p.data_ptr() < a0 + self.arena.numel() * 4
 
+    def owns_grad(self, g):
+        a0 = self.grad_arena.data_ptr()
+        return a0 <= g.data_ptr() < a0 + self.grad_arena.numel() * 4
+
+    def rebind_grads(self, discard=False):
+        """re-attach every Parameter's .grad to its view of the gradient arena (after zero_grad(set_to_none=True) or any
+        code that replaced .grad by a fresh tensor); a stray gradient is folded into the arena unless `discard`"""
+        for p, o, n, is_ohwi in self._views:
+            if p.grad is not None and self.owns_grad(p.grad):
+                continue
+            stray = p.grad
+            gflat = self.grad_arena[o:o + n]
+            if is_ohwi:
+                O, I, H, W = p.shape
+                p.grad = gflat.view(O, H, W, I).permute(0, 3, 1, 2)
+            else:
+                p.grad = gflat.view(p.shape)
+            if stray is not None and not discard:
+                with th.no_grad():
+                    p.grad.add_(stray)
+
     def grad_of(self, p):
         o, n = self.param_offsets[id(p)], p.numel()
         return self.grad_arena[o:o + n]
@@ -354,9 +376,16 @@ class Engine:
         self.n_pack = len(entries)
         self.pack_max = max(max(e.cout_pad, 1) * e.taps * e.cin_pad for e in entries)
 
+    def weights_version(self):
+        """Changes whenever the master weights were written through torch: the arena's own version counter plus the
+        counters of the Parameters re-homed into it (`p.data = arena.view(..)` gives each Parameter its OWN counter, so
+        load_state_dict / zero_module / a stock optimizer bump those and not the arena's).  Writes that bypass torch
+        (the fused optimizer kernel) set `dirty`."""
+        return (self.arena._version, sum(p._version for p, _, _, _ in self._views))
+
     def pack(self, force=False):
         """fp32 master arena -> bf16 operand copies (one launch). Re-run whenever the arena changed."""
-        ver = self.arena._version
+        ver = self.weights_version()
         if not (force or self.dirty or ver != self._packed_version):
             return
         ops.check(_lib.lib().cdae_pack_weights(self.arena.data_ptr(), self.bf16_arena.data_ptr(),
@@ -646,13 +675,27 @@ class Engine:
             pl.add_bwd([pl._zero_bwd_ws])        # layers replay last-to-first: this node opens the backward graph
         return pl
 
-    def plan(self, B, train):
+    MAX_PENDING = 2      # training plans of one batch size that may await their backward at the same time
+
+    def plan(self, B, train, fresh=False):
+        """The plan of (batch size, train|infer).  A training plan owns the activations its backward reads, so a second
+        grad-enabled forward before that backward (two model calls inside one loss, an evaluation forward without
+        no_grad) must not reuse it: `fresh=True` returns an instance that is not awaiting a backward, building up to
+        MAX_PENDING of them; beyond that the oldest one is recycled and its stale backward raises (generation check)."""
         key = (B, bool(train))
-        pl = self.plans.get(key)
-        if pl is None:
-            pl = self.build_plan(B, train)
-            self.plans[key] = pl
-        return pl
+        slots = self.plans.setdefault(key, [])
+        if not slots:
+            slots.append(self.build_plan(B, train))
+        if not (train and fresh):
+            return slots[0]
+        for pl in slots:
+            if not pl.pending:
+                return pl
+        if len(slots) < self.MAX_PENDING:
+            slots.append(self.build_plan(B, train))
+            return slots[-1]
+        slots.append(slots.pop(0))       # recycle the oldest: its generation moves on, a late backward fails loudly
+        return slots[-1]
 
     # ------------------------------------------------------------------ public entry: the torso as one autograd node
     def film(self, emb):
@@ -671,12 +714,14 @@ class _Torso(th.autograd.Function):
     @staticmethod
     def forward(ctx, eng, x, film, train):
         B = x.shape[0]
-        pl = eng.plan(B, train)
+        pl = eng.plan(B, train, fresh=True)
         eng.pack()
         pl.x_in.copy_(x)
         pl.film_in.copy_(film)
         pl.forward()
-        ctx.pl = pl
+        pl.generation += 1
+        pl.pending = bool(train)
+        ctx.pl, ctx.generation = pl, pl.generation
         return pl.eps.clone()
 
     @staticmethod
@@ -684,6 +729,10 @@ class _Torso(th.autograd.Function):
         pl = ctx.pl
         if not pl.train:
             raise _lib.CdaeError("backward through a torso forward that ran in inference mode")
+        if pl.generation != ctx.generation:
+            raise _lib.CdaeError("the saved activations of this torso forward were overwritten by later grad-enabled "
+                                 f"forwards of the same batch size (more than {Engine.MAX_PENDING} awaiting backward)")
+        pl.pending = False
         pl.deps_in.copy_(deps)
         pl.dfilm.zero_()
         pl.backward()
@@ -727,3 +776,60 @@ def run_layer(mod, x, emb=None):
         raise _lib.CdaeError(f"run_layer: unsupported module {type(mod)}")
     pl._run_fwd_eager()
     return out.t.float().permute(0, 3, 1, 2).contiguous()
+
+
+def _channel_stats(t_bf16):
+    """fp32 [B, C, 2] per-(image, channel) sum / sum of squares of an NHWC bf16 tensor: what the producing conv's epilogue
+    leaves behind inside the torso (standalone layer calls have no producer)"""
+    f = t_bf16.float()
+    return th.stack([f.sum(dim=(1, 2)), (f * f).sum(dim=(1, 2))], dim=-1).contiguous()
+
+
+def run_layer_train(mod, xs, emb=None, dout=None):
+    """Teacher-forced forward AND backward of ONE torso layer through the same planned kernels (and the same kernel
+    variants: statistics epilogue, streaming GroupNorm, two-source concat) the full torso launches.
+    xs: NCHW fp32 tensor, or a tuple (h, skip) for the skip-concatenated ResBlocks of the output path; dout: NCHW fp32
+    gradient of the layer output.  Returns (out, [dx per input], dfilm [B, film_width] | None), all fp32 NCHW; parameter
+    gradients are ACCUMULATED into the engine's gradient arena (read them through `param.grad`)."""
+    from .unet import ResBlock, AttentionBlock, Upsample, Downsample
+    root = getattr(mod, "_cdae_root", None)
+    if root is None:
+        raise _lib.CdaeError("standalone layer calls need model.engine to have been built (layers are bound to it)")
+    eng = root.engine
+    eng.pack()
+    xs = list(xs) if isinstance(xs, (tuple, list)) else [xs]
+    B, _, H, W = xs[0].shape
+    pl = Plan(eng, B, True)
+    pl.bwd_builders = []
+    tin = []
+    for x in xs:
+        t = T(pl, (B, H, W, x.shape[1]))
+        t.t.copy_(x.float().permute(0, 2, 3, 1))
+        if H * W >= 32 and x.shape[1] % 64 == 0 and FUSED_GN_STATS:
+            t.stats = _channel_stats(t.t)
+        tin.append(t)
+    film = dfilm = None
+    if isinstance(mod, ResBlock):
+        film = eng.film(emb).detach().contiguous()
+        dfilm = th.zeros_like(film)
+        out = eng.plan_resblock(pl, mod, tin[0], tin[1] if len(tin) > 1 else None, film, dfilm)
+    elif isinstance(mod, AttentionBlock):
+        out = eng.plan_attention(pl, mod, tin[0])
+    elif isinstance(mod, Upsample):
+        out = eng.plan_upsample(pl, mod, tin[0])
+    elif isinstance(mod, Downsample):
+        out = eng.plan_downsample(pl, mod, tin[0])
+    else:
+        raise _lib.CdaeError(f"run_layer_train: unsupported module {type(mod)}")
+    pl._run_fwd_eager()
+    res = out.t.float().permute(0, 3, 1, 2).contiguous()
+    if dout is None:
+        return res, None, None
+    built = [b() for b in reversed(pl.bwd_builders)]
+    out.grad().copy_(dout.float().permute(0, 2, 3, 1))
+    pl._zero_bwd_ws()
+    for fns in built:
+        for f in fns:
+            f()
+    dxs = [t.g.float().permute(0, 3, 1, 2).contiguous() for t in tin]
+    return res, dxs, dfilm

@@ -244,16 +244,18 @@ class CausalModeling(nn.Module):
             self.__dict__["_dag_ws"] = ws
         return ws
 
-    def fused_ok(self, u):
+    def fused_ok(self, u, A=None):
         ps = self._mlp_params()
         d = self.latent_dim // self.num_var
+        if A is not None and th.is_tensor(A) and A.requires_grad:
+            return False          # the fused backward does not produce dL/dA (learn=True): autograd path below
         return (u.is_cuda and self.num_var <= 8 and d in (64, 128, 256) and self.latent_dim % 32 == 0 and
                 all(p.is_cuda and p.dtype == th.float32 and p.is_contiguous() for p in ps))
 
     def forward(self, u, A):
         """z_post of the whole layer (ref unet.py:579-583 calls causal_masking + nonlinearity_add_back_noise): ONE fused
         kernel on the device; the two reference methods below stay for API users."""
-        if self.fused_ok(u):
+        if self.fused_ok(u, A):
             return _DagLayer.apply(self, u, A.to(device=u.device, dtype=th.float32))
         return self.nonlinearity_add_back_noise(u, self.causal_masking(u, A))
 

@@ -66,10 +66,26 @@ def ddim_step(x, eps_c, coef_table, t_idx, eps_u=None, w=None, noise=None, want_
     return out, x0
 
 
-def adam_ema(p, g, m, v, ema, hyper, gsq_out=None):
-    """ref train_util.py:292-303 + nn.py:503-513; flat fp32 arenas, hyper = device fp32[9]."""
+def adam_ema(p, g, m, v, ema, hyper, step, gsq_out=None, guard=None):
+    """ref train_util.py:276-303 + nn.py:503-513; flat fp32 arenas, hyper = device fp32[7] {lr, b1, b2, eps, wd, ema_rate,
+    grad_scale}, step = device int64[1] (incremented by the launch), g fp32 or bf16, guard = device fp32[1] or None."""
     n = p.numel()
-    check(_lib.lib().cdae_adam_ema(ptr(p), ptr(g), ptr(m), ptr(v), ptr(ema), ptr(hyper), ptr(gsq_out), n, stream()))
+    assert step.dtype == torch.int64 and g.numel() == n
+    check(_lib.lib().cdae_adam_ema(ptr(p), ptr(g), int(g.dtype == bf16), ptr(m), ptr(v), ptr(ema), ptr(hyper), ptr(step),
+                                   ptr(guard), ptr(gsq_out), n, stream()))
+
+
+def sumsq(g, out):
+    """out (fp32[1]) += sum(g^2); g fp32 or bf16"""
+    assert g.is_cuda and g.is_contiguous() and g.dtype in (torch.float32, bf16)
+    check(_lib.lib().cdae_sumsq(ptr(g), int(g.dtype == bf16), ptr(out), g.numel(), stream()))
+    return out
+
+
+def cast_bf16(src, out=None):
+    out = torch.empty(src.shape, device=src.device, dtype=bf16) if out is None else out
+    check(_lib.lib().cdae_cast_bf16(ptr(_f32c(src)), ptr(out), src.numel(), stream()))
+    return out
 
 
 def ema_update(ema, p, rate):

@@ -23,44 +23,69 @@ from .resample import LossAwareSampler, UniformSampler
 INITIAL_LOG_LOSS_SCALE = 20.0
 
 
-def adam_hyper(lr, step, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, ema_rate=0.9999, grad_scale=1.0):
-    """Host-side scalars of one AdamW step (torch.optim.AdamW semantics, ref train_util.py:94): the 9 floats the
-    fused kernel reads from device memory {lr, b1, b2, eps, wd, lr/bias_corr1, sqrt(bias_corr2), ema_rate, grad_scale}."""
-    bc1 = 1.0 - beta1 ** step
-    bc2 = 1.0 - beta2 ** step
-    return [lr, beta1, beta2, eps, weight_decay, lr / bc1, math.sqrt(bc2), ema_rate, grad_scale]
+def adam_hyper(lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, ema_rate=0.9999, grad_scale=1.0):
+    """Scalars of one AdamW step (torch.optim.AdamW semantics, ref train_util.py:94) as the fused kernel reads them from
+    device memory: {lr, b1, b2, eps, wd, ema_rate, grad_scale}.  The step counter lives on the device and the bias
+    corrections are evaluated there (in double, like torch does on the host)."""
+    return [lr, beta1, beta2, eps, weight_decay, ema_rate, grad_scale]
 
 
 class _FlatAdamW:
     """The optimizer object behind `TrainLoop.opt`: torch.optim.AdamW's surface (param_groups / state_dict / step)
-    over the flat arena, executed by the fused kernel."""
+    over the flat arena, executed by the fused kernel.  Nothing here synchronises with the host: the step counter, the
+    hyper-parameters and the non-finite-gradient guard are device scalars at fixed addresses (graph-replayable)."""
 
     def __init__(self, engine, lr, weight_decay, betas=(0.9, 0.999), eps=1e-8):
         self.engine = engine
         self.param_groups = [dict(lr=lr, weight_decay=weight_decay, betas=betas, eps=eps)]
         self.exp_avg = th.zeros_like(engine.arena)
         self.exp_avg_sq = th.zeros_like(engine.arena)
-        self.step_count = 0
-        self.gsq = th.zeros(1, device=engine.device)
+        dev = engine.device
+        self.step_dev = th.zeros(1, device=dev, dtype=th.int64)
+        self.hyper = th.zeros(8, device=dev)
+        self._hyper_host = None
+        self.gsq = th.zeros(1, device=dev)
+        self.guard = th.zeros(1, device=dev)
 
-    def step(self, ema=None, ema_rate=0.0, grad_scale=1.0):
+    @property
+    def step_count(self):
+        return int(self.step_dev.item())
+
+    def set_hyper(self, ema_rate=0.0, grad_scale=1.0):
+        """upload the hyper-parameters when they changed (lr annealing, a new world size); otherwise no copy at all"""
         g = self.param_groups[0]
-        self.step_count += 1
-        hyper = th.tensor(adam_hyper(g["lr"], self.step_count, g["betas"][0], g["betas"][1], g["eps"],
-                                     g["weight_decay"], ema_rate, grad_scale)).pin_memory().to(self.engine.device,
-                                                                                               non_blocking=True)
-        self.gsq.zero_()
-        ops.adam_ema(self.engine.arena, self.engine.grad_arena, self.exp_avg, self.exp_avg_sq, ema, hyper, self.gsq)
-        self.engine.dirty = True
+        vals = adam_hyper(g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], ema_rate, grad_scale) + [0.0]
+        if vals != self._hyper_host:
+            self.hyper.copy_(th.tensor(vals).pin_memory(), non_blocking=True)
+            self._hyper_host = vals
+
+    def step(self, ema=None, ema_rate=0.0, grad_scale=1.0, guarded=False, grads=None):
+        """grads: the (all-reduced) gradient buffer, fp32 or bf16 (default: the engine's fp32 gradient arena); guarded:
+        skip the whole step on the device when sum(g^2) is not finite (ref train_util.py:277-280)."""
+        self.set_hyper(ema_rate, grad_scale)
+        self.launch(ema, guarded, grads)
+
+    def launch(self, ema=None, guarded=False, grads=None):
+        e = self.engine
+        ops.zero_(self.gsq)
+        guard = None
+        g = e.grad_arena if grads is None else grads
+        if guarded:
+            ops.zero_(self.guard)
+            ops.sumsq(g, self.guard)
+            guard = self.guard
+        ops.adam_ema(e.arena, g, self.exp_avg, self.exp_avg_sq, ema, self.hyper, self.step_dev, self.gsq, guard)
+        e.dirty = True
 
     def state_dict(self):
         return dict(step=self.step_count, exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq,
                     param_groups=self.param_groups)
 
     def load_state_dict(self, sd):
-        self.step_count = int(sd["step"])
+        self.step_dev.fill_(int(sd["step"]))
         self.exp_avg.copy_(sd["exp_avg"]); self.exp_avg_sq.copy_(sd["exp_avg_sq"])
         self.param_groups = sd["param_groups"]
+        self._hyper_host = None
 
 
 class TrainLoop:
@@ -89,6 +114,7 @@ class TrainLoop:
         self.lg_loss_scale = INITIAL_LOG_LOSS_SCALE
         self.sync_cuda = th.cuda.is_available()
         self.log_quartiles = True
+        self.grad_wire_dtype = th.float32 if os.environ.get("CDAE_GRAD_WIRE", "bf16") == "fp32" else th.bfloat16
 
         if next(model.parameters()).device.type != "cuda":
             model.to(dist_util.dev())
@@ -119,7 +145,7 @@ class TrainLoop:
     def _load_ema_parameters(self, rate):
         ema = self.engine.arena.clone()
         main_checkpoint = find_resume_checkpoint() or self.resume_checkpoint
-        path = find_ema_checkpoint(main_checkpoint, self.resume_step, rate)
+        path = _rank0_decides(lambda: find_ema_checkpoint(main_checkpoint, self.resume_step, rate))
         if path:
             logger.log(f"loading EMA from checkpoint: {path}...")
             sd = dist_util.load_state_dict(path, map_location=dist_util.dev())
@@ -132,7 +158,7 @@ class TrainLoop:
     def _load_optimizer_state(self):
         main_checkpoint = find_resume_checkpoint() or self.resume_checkpoint
         path = os.path.join(os.path.dirname(main_checkpoint), f"opt{self.resume_step:06}.pt")
-        if os.path.exists(path):
+        if _rank0_decides(lambda: os.path.exists(path)):
             logger.log(f"loading optimizer state from checkpoint: {path}")
             self.opt.load_state_dict(dist_util.load_state_dict(path, map_location=dist_util.dev()))
 
@@ -191,19 +217,43 @@ class TrainLoop:
             self.last_loss = loss.detach()
             log_loss_dict(self.diffusion, t, {k: v * weights for k, v in losses.items()}, self.log_quartiles)
             loss.backward()
-        self._grad_scale = dp_all_reduce_(self.engine.grad_arena) if self.use_ddp else 1.0
+        self._grad_scale, self._reduced_grads = 1.0, None
+        if self.use_ddp:
+            self._grad_scale, self._reduced_grads = self._exchange_gradients()
+
+    def _exchange_gradients(self):
+        """ref train_util.py:107-126 (DDP mean).  bf16 on the wire (default): one cast pass over the arena, ONE NCCL sum
+        all-reduce of the 2-byte copy (187 MB instead of 374 MB at cfg2), and the fused optimizer reads that copy
+        directly; fp32 (CDAE_GRAD_WIRE=fp32): the all-reduce runs in place on the arena."""
+        if self.grad_wire_dtype == th.bfloat16:
+            if getattr(self, "_wire", None) is None:
+                self._wire = th.empty(self.engine.grad_arena.shape, device=self.engine.device, dtype=th.bfloat16)
+            ops.cast_bf16(self.engine.grad_arena, out=self._wire)
+            return dp_all_reduce_(self._wire), self._wire
+        return dp_all_reduce_(self.engine.grad_arena), None
 
     def optimize_fp16(self):
-        """bf16 tensor-core compute needs no loss scaling: same step as optimize_normal (ref train_util.py:276-290)."""
-        self.optimize_normal()
-        self.lg_loss_scale += self.fp16_scale_growth
+        """ref train_util.py:276-290.  The guard is kept, on the device: when any gradient is NaN/Inf the fused kernel
+        leaves parameters, moments, EMA and the step counter untouched and lg_loss_scale drops by one; otherwise the
+        step happens and lg_loss_scale grows by fp16_scale_growth.  bf16 tensor-core compute with fp32 accumulation
+        needs no loss scaling, so lg_loss_scale is bookkeeping (logged like the reference) and never multiplies the loss."""
+        self.optimize_normal(guarded=True)
+        ok = th.isfinite(self.opt.guard[0])
+        if not th.is_tensor(self.lg_loss_scale):
+            self.lg_loss_scale = th.full((), float(self.lg_loss_scale), device=self.engine.device)
+        self.lg_loss_scale = th.where(ok, self.lg_loss_scale + self.fp16_scale_growth, self.lg_loss_scale - 1)
 
-    def optimize_normal(self):
+    def optimize_normal(self, guarded=False):
         """ref train_util.py:292-297: grad-norm log, lr anneal, AdamW step, EMA — one fused kernel."""
         self._anneal_lr()
-        self.opt.step(ema=self.ema_params[0][0], ema_rate=self.ema_rate[0], grad_scale=getattr(self, "_grad_scale", 1.0))
+        self.opt.step(ema=self.ema_params[0][0], ema_rate=self.ema_rate[0], grad_scale=getattr(self, "_grad_scale", 1.0),
+                      guarded=guarded, grads=getattr(self, "_reduced_grads", None))
         for rate, params in zip(self.ema_rate[1:], self.ema_params[1:]):
-            ops.ema_update(params[0], self.engine.arena, rate)
+            if guarded:     # the extra rates must skip with the step: blend towards the (unchanged) arena is not a no-op
+                ok = th.isfinite(self.opt.guard[0])
+                params[0].copy_(th.where(ok, params[0] * rate + self.engine.arena * (1 - rate), params[0]))
+            else:
+                ops.ema_update(params[0], self.engine.arena, rate)
         self._log_grad_norm()
 
     def _log_grad_norm(self):
@@ -284,14 +334,31 @@ def find_resume_checkpoint():
     return None
 
 
+def _rank0_decides(fn):
+    """Evaluate a filesystem question on rank 0 and broadcast the answer: `dist_util.load_state_dict` is a collective
+    (rank 0 reads, the bytes are broadcast), so every rank must take the same branch even without a shared filesystem."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return fn()
+    box = [fn() if dist.get_rank() == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    return box[0]
+
+
 def find_ema_checkpoint(main_checkpoint, step, rate):
+    """ref train_util.py:386-394: `ema_{rate}_{step}.pt` next to the model checkpoint.  The reference scripts also write
+    a rolling `ema_checkpoint.pt` (overwritten by every rate and every save): it is only a fallback, with a warning,
+    because it may belong to another step or rate."""
     if main_checkpoint is None:
         return None
     d = os.path.dirname(main_checkpoint)
-    for name in (f"ema_{rate}_{step:06d}.pt", "ema_checkpoint.pt"):
-        path = os.path.join(d, name)
-        if os.path.exists(path):
-            return path
+    path = os.path.join(d, f"ema_{rate}_{step:06d}.pt")
+    if os.path.exists(path):
+        return path
+    path = os.path.join(d, "ema_checkpoint.pt")
+    if os.path.exists(path):
+        logger.log(f"warning: ema_{rate}_{step:06d}.pt not found; falling back to the rolling {path} "
+                   "(may belong to another step or EMA rate)")
+        return path
     return None
 
 

@@ -230,6 +230,15 @@ class UNetModel(nn.Module):
         object.__setattr__(self, "_engine", None)
         return super()._apply(fn, *a, **k)
 
+    def zero_grad(self, set_to_none=False):
+        """Gradients are views of the engine's flat gradient arena (the fused optimizer and the NCCL all-reduce read that
+        buffer): zero it in place; never drop the views (torch's default set_to_none=True would detach `.grad` from it)."""
+        if self._engine is not None:
+            self._engine.grad_arena.zero_()
+            self._engine.rebind_grads(discard=True)
+            return
+        super().zero_grad(set_to_none=set_to_none)
+
     # ------------------------------------------------------------------ forward
     def embed(self, timesteps, y=None, c=None):
         """time_embed(timestep_embedding(t)) (+ label_emb(y)) (+ c_emb(c))   (ref unet.py:545-554)"""

@@ -47,11 +47,19 @@ int cdae_mse_loss(const float* pred, const float* target, float* mse, const floa
 int cdae_ddim_step(const float* x, const float* eps_c, const float* eps_u, float w, int use_w,
                    const float* coef_table, const int32_t* t_idx, int t_idx_stride, const float* noise,
                    float* x_prev, float* pred_xstart, int64_t B, int64_t per_sample, cdae_stream s);
-/* fused AdamW + EMA + grad-norm + bf16 weight copy over the flat parameter arena
- * (train_util.py:292-303 optimize_normal, nn.py:503-513 update_ema, torch.optim.AdamW defaults)
- * hyper: device floats {lr, beta1, beta2, eps, weight_decay, bias_corr1, bias_corr2, ema_rate, grad_scale} */
-int cdae_adam_ema(float* p, const float* g, float* m, float* v, float* ema, const float* hyper,
-                  float* gsq_out, int64_t n, cdae_stream s);
+/* fused AdamW + EMA + grad-norm over the flat parameter arena, one pass
+ * (train_util.py:276-303 optimize_fp16 / optimize_normal, nn.py:503-513 update_ema, torch.optim.AdamW defaults)
+ * hyper: device floats {lr, beta1, beta2, eps, weight_decay, ema_rate, grad_scale}; step: device counter of the steps
+ * taken so far (bias corrections of step+1 are evaluated in double on the device; the counter is incremented after the
+ * update); g: the gradient arena, fp32 or (g_is_bf16) its bf16 copy as all-reduced; guard: optional device scalar - when
+ * it is not finite the launch changes nothing and the counter stays (the reference's "found NaN: skip the step",
+ * train_util.py:277-280); gsq_out += sum((g*grad_scale)^2). */
+int cdae_adam_ema(float* p, const void* g, int g_is_bf16, float* m, float* v, float* ema, const float* hyper,
+                  int64_t* step, const float* guard, float* gsq_out, int64_t n, cdae_stream s);
+/* out += sum(g^2) over a flat fp32 (or bf16) buffer (the guard above; train_util.py:277 isfinite check, :299-303 grad norm) */
+int cdae_sumsq(const void* g, int g_is_bf16, float* out, int64_t n, cdae_stream s);
+/* fp32 -> bf16 (RNE) copy of a flat buffer: the gradient arena as it crosses NVLink (train_util.py:107-126 DDP buckets) */
+int cdae_cast_bf16(const float* src, void* dst_bf16, int64_t n, cdae_stream s);
 /* extra EMA rates (train_util.py:296-297): ema = rate*ema + (1-rate)*p */
 int cdae_ema_update(float* ema, const float* p, float rate, int64_t n, cdae_stream s);
 int cdae_zero(void* p, int64_t bytes, cdae_stream s);

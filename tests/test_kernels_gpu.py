@@ -89,6 +89,8 @@ def test_ddim_step_vs_oracle(eta, w):
 
 
 def test_adam_ema_vs_torch_adamw():
+    """fused AdamW + EMA + sum(g^2) against torch.optim.AdamW (ref train_util.py:292-303): device step counter, device-side
+    bias corrections, the non-finite guard of optimize_fp16 (ref :277-280) and bf16 gradients (the all-reduced copy)"""
     from causaldiffae_b200 import ops
     from causaldiffae_b200.train_util import adam_hyper
     g = torch.Generator().manual_seed(3)
@@ -98,18 +100,41 @@ def test_adam_ema_vs_torch_adamw():
     opt = torch.optim.AdamW([pr], lr=1e-3, weight_decay=0.01)
     ema_ref = p0.clone()
     p, m, v, ema = p0.clone().to(dev()), torch.zeros(n, device=dev()), torch.zeros(n, device=dev()), p0.clone().to(dev())
-    gsq = torch.zeros(1, device=dev())
-    for step in range(1, 6):
+    gsq, guard = torch.zeros(1, device=dev()), torch.zeros(1, device=dev())
+    step = torch.zeros(1, device=dev(), dtype=torch.int64)
+    hyper = torch.tensor(adam_hyper(1e-3, weight_decay=0.01, ema_rate=0.99) + [0.0], device=dev())
+    for it in range(1, 6):
         grad = torch.randn(n, generator=g)
         pr.grad = grad.clone()
         opt.step()
         ema_ref.mul_(0.99).add_(pr.detach(), alpha=0.01)
-        hyper = torch.tensor(adam_hyper(1e-3, step, weight_decay=0.01, ema_rate=0.99), device=dev())
-        gsq.zero_()
-        ops.adam_ema(p, grad.to(dev()), m, v, ema, hyper, gsq)
+        gsq.zero_(); guard.zero_()
+        gd = grad.to(dev())
+        ops.sumsq(gd, guard)
+        ops.adam_ema(p, gd, m, v, ema, hyper, step, gsq, guard)
         np.testing.assert_allclose(float(gsq), float((grad ** 2).sum()), rtol=1e-5)
+        np.testing.assert_allclose(float(guard), float((grad ** 2).sum()), rtol=1e-5)
+        assert int(step) == it
     np.testing.assert_allclose(p.cpu().numpy(), pr.detach().numpy(), rtol=2e-5, atol=2e-7)
     np.testing.assert_allclose(ema.cpu().numpy(), ema_ref.numpy(), rtol=2e-5, atol=2e-7)
+    # a NaN / Inf gradient: the guarded launch changes nothing and the step counter stays
+    snap = [t.clone() for t in (p, m, v, ema)]
+    for bad in (float("nan"), float("inf")):
+        gd = torch.randn(n, generator=g).to(dev()); gd[n // 2] = bad
+        guard.zero_(); gsq.zero_()
+        ops.sumsq(gd, guard)
+        ops.adam_ema(p, gd, m, v, ema, hyper, step, gsq, guard)
+        assert int(step) == 5 and not bool(torch.isfinite(guard).all())
+        for a, b in zip(snap, (p, m, v, ema)):
+            assert torch.equal(a, b)
+    # bf16 gradients (as they come off the all-reduce): same step as fp32 Adam on the rounded values
+    gd = torch.randn(n, generator=g).to(dev())
+    gb = ops.cast_bf16(gd)
+    assert torch.equal(gb, gd.to(bf16))
+    p2, m2, v2, e2, s2 = p.clone(), m.clone(), v.clone(), ema.clone(), step.clone()
+    ops.adam_ema(p, gb, m, v, ema, hyper, step, None, None)
+    ops.adam_ema(p2, gb.float(), m2, v2, e2, hyper, s2, None, None)
+    assert torch.equal(p, p2) and torch.equal(m, m2) and torch.equal(v, v2) and torch.equal(ema, e2) and int(step) == 6
 
 
 # ------------------------------------------------------------------ layout kernels

@@ -112,3 +112,99 @@ def test_500_step_loss_parity_then_ddim_psnr():
         mu_o, _ = om.encoder_encode(osd2, cfg, x.to(dev), training=False)
         _, mu_m, zp_m = encode(model, x.to(dev))
     assert float((mu_m - mu_o).norm() / mu_o.norm()) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE configs[2] / [4]: CausalCircuit-shaped 3x64x64 at the FULL benchmark width (nc128 x 2, attention at 16x16 / 8x8,
+# 93.5 M parameters), classifier-free masking=True training, then guided DDIM-50 at several strengths and DDIM-100.
+CIRCUIT = [[0, 1, 1, 1], [0, 0, 0, 1], [0, 0, 0, 1], [0, 0, 0, 0]]
+FLAGS2 = dict(image_size=64, num_channels=128, num_res_blocks=2, num_heads=4, attention_resolutions="16,8",
+              class_cond=False, rep_cond=True, n_vars=4, causal_modeling=True, in_channels=3, learn_sigma=False,
+              rescale_timesteps=False, rescale_learned_sigmas=False, diffusion_steps=1000, masking=True)
+
+
+def structured_batch64(B, gen):
+    """3x64x64 images that depend on four causal labels: disc radius (c0), disc x-position (c1), disc colour (c2),
+    background shade (c3) - so that the loss actually falls and guidance has something to amplify"""
+    c = torch.rand(B, 4, generator=gen)
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, 64), torch.linspace(-1, 1, 64), indexing="ij")
+    r = (0.15 + 0.35 * c[:, 0])[:, None, None]
+    cx = (-0.5 + c[:, 1])[:, None, None]
+    disc = (((xx[None] - cx) ** 2 + yy[None] ** 2) < r ** 2).float()
+    col = torch.stack([0.3 + 0.7 * c[:, 2], 1.0 - 0.6 * c[:, 2], 0.5 + 0.0 * c[:, 2]], dim=1)[:, :, None, None]
+    bg = (0.1 + 0.3 * c[:, 3])[:, None, None, None]
+    img = disc[:, None] * col + (1 - disc[:, None]) * bg
+    return img.contiguous(), c
+
+
+def test_cfg2_masking_500_step_loss_parity_then_guided_ddim_psnr():
+    from causaldiffae_b200 import script_util as su, dist_util, logger
+    from causaldiffae_b200.train_util import TrainLoop
+    from oracle import model as om, diffusion as od, schedules
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device("cuda:0")
+    full = {**su.model_and_diffusion_defaults(), **FLAGS2}
+    torch.manual_seed(0)
+    model, diff = su.create_model_and_diffusion(**full, A=CIRCUIT)
+    sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model.to(dev)
+    dist_util.setup_dist()
+    logger.configure(dir="/tmp/cdae_parity2", format_strs=[])
+    B, STEPS, LR = 16, 500, 1e-4
+    loop = TrainLoop(model=model, diffusion=diff, data=None, batch_size=B, microbatch=-1, lr=LR, ema_rate="0.9999",
+                     log_interval=10 ** 9, save_interval=10 ** 9, resume_checkpoint="", rep_cond=True, n_vars=4,
+                     causal_modeling=True, in_channels=3, masking=True)
+    cfg = om.config_from_flags(**full, A=CIRCUIT)
+    osd = {k: v.to(dev).clone() for k, v in sd0.items()}
+    odiff = od.Diffusion(steps=1000)
+    ref = od.RefTrainer(osd, cfg, odiff, lr=LR, ema_rate=0.9999)
+    gen = torch.Generator().manual_seed(321)
+    mine, theirs = [], []
+    for step in range(STEPS):
+        x, c = structured_batch64(B, gen)
+        np.random.seed(2000 + step)
+        t, w = schedules.uniform_sample_t(1000, B)
+        t, w = torch.from_numpy(t).to(dev), torch.from_numpy(w).to(dev)
+        noise = torch.randn(x.shape, generator=gen).to(dev)
+        x, c = x.to(dev), c.to(dev)
+        torch.manual_seed(7000 + step)          # xi and the Bernoulli keep-mask come off the CPU generator on both sides
+        theirs.append(ref.run_step(x, t, noise, w, c=c)["loss"])
+        torch.manual_seed(7000 + step)
+        loop.engine.grad_arena.zero_()
+        losses = diff.training_losses(model, x, t, model_kwargs=dict(c=c), noise=noise, rep_cond=True, causal_modeling=True)
+        loss = (losses["loss"] * w).mean()
+        loss.backward()
+        loop._grad_scale = 1.0
+        loop.optimize_normal()
+        loop.step += 1
+        diff.kl_weight = loop.linear_kl_weight_scheduler(loop.step, 50000, 0.0, 1.0)
+        mine.append(float(loss))
+    mine, theirs = np.array(mine), np.array(theirs)
+    assert theirs[-50:].mean() < 0.25 * theirs[:10].mean(), "the reference run itself did not learn"
+    win = 50
+    sm_m, sm_t = mine.reshape(-1, win).mean(1), theirs.reshape(-1, win).mean(1)
+    rel = np.abs(sm_m - sm_t) / sm_t
+    print("cfg2 masking: smoothed loss (ours)", np.round(sm_m, 4))
+    print("cfg2 masking: smoothed loss (ref) ", np.round(sm_t, 4))
+    print("cfg2 masking: max rel diff", rel.max())
+    assert rel.max() < 0.02, rel
+
+    # ---- guided (w) DDIM-50 and DDIM-100 counterfactual PSNR on the trained weights
+    trained = {k: v.detach().float().clone().contiguous() for k, v in model.state_dict().items()}
+    model.eval()
+    x, c = structured_batch64(8, gen)
+    noise = torch.randn(x.shape, generator=gen)
+    xi = torch.randn(8, 512, generator=gen)
+    for spec, w_guid in (("ddim50", 0.5), ("ddim50", 1.5), ("ddim50", 3.0), ("ddim100", None), ("ddim50", 0.0)):
+        _, d_s = su.create_model_and_diffusion(**{**full, "timestep_respacing": spec}, A=CIRCUIT)
+        od_s = od.Diffusion(steps=1000, timestep_respacing=spec)
+        ref_img, z_ref, _ = od.counterfactual(od_s, trained, cfg, x.to(dev), noise.to(dev), xi.to(dev), do_var=0, do_value=0.2,
+                                              on="mu", w=w_guid)
+        t_last = torch.full((8,), d_s.num_timesteps - 1, device=dev, dtype=torch.long)
+        x_T = d_s.q_sample(x.to(dev), t_last, noise=noise.to(dev))
+        img = d_s.ddim_sample_loop(model, tuple(x.shape), noise=x_T, clip_denoised=True, model_kwargs=dict(z=z_ref), w=w_guid)
+        mse = float(((img - ref_img) ** 2).mean())
+        psnr = 10 * np.log10(1.0 / max(mse, 1e-12))
+        print(f"cfg2 masking: {spec} w={w_guid} PSNR vs oracle {psnr:.1f} dB")
+        assert psnr >= 40.0, (spec, w_guid, psnr)
