@@ -75,7 +75,7 @@ def test_full_width_eps_vs_oracle(A):
             got = model(x_t, inp["t"], z=inp["z"])[0]
             err = relerr(got, ref)
             print(f"full-width eps rel L2 vs fp32 oracle: {err:.3e} (torch bf16 autocast of the oracle: {yard:.3e})")
-            assert err < 3e-2, (rep, err)
+            assert err < 2e-2 and err < 1.5 * yard, (rep, err, yard)       # measured 9.0e-3 vs 1.37e-2 for torch autocast
 
 
 def layer_cases(model):
@@ -231,5 +231,7 @@ def test_full_width_training_losses_and_gradients(A, masking):
         print(f"rep {rep}: whole-gradient rel L2 {tot:.3e}; worst tensor {worst} {errs[worst]:.3e} "
               f"(median {np.median(list(errs.values())):.3e}); torch-autocast yardstick worst {wy} {yard[wy]:.3e} "
               f"(median {np.median(list(yard.values())):.3e})")
-        assert tot < 3e-2, (rep, tot)
-        assert errs[worst] < 8e-2, (rep, worst, errs[worst])
+        # measured on B200 (profiles/r2_tests_gpu_106pass.log): whole gradient 1.2e-4, worst tensor 1.1e-2, median 7e-3 -
+        # below what torch's own bf16 autocast of the reference reaches (worst 1.5e-1, median 1.2e-2)
+        assert tot < 1e-3, (rep, tot)
+        assert errs[worst] < 2.5e-2, (rep, worst, errs[worst])
