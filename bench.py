@@ -88,26 +88,103 @@ def synth_batch(B, seed, device=None, pinned=False):
 
 
 # ---------------------------------------------------------------------------------------------- reference arm (CPU)
+CFG1 = dict(image_size=32, num_channels=64, num_res_blocks=2, class_cond=True, rep_cond=True, n_vars=2, causal_modeling=True,
+            in_channels=1, learn_sigma=False, rescale_timesteps=False, rescale_learned_sigmas=False, diffusion_steps=1000,
+            noise_schedule="linear")
+
+
+def _dezero(model, seed=1):
+    """the reference init zeroes every out conv (eps == 0): de-zero like the CUDA arm so the math is generic"""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if float(p.abs().sum()) == 0.0 and p.dim() > 1:
+                p.copy_(torch.randn(p.shape, generator=g) * p[0].numel() ** -0.5)
+
+
+def _reference_trainloop(flags, A, B, n_vars, in_channels):
+    """the UNMODIFIED reference (oracle/refshim.py imports it from /root/reference or oracle/_ref; two stand-in modules for
+    blobfile / mpi4py and the documented patches: encoder depth, injectable DAG) behind its own TrainLoop"""
+    from oracle import refshim
+    ns = refshim.load()
+    torch.manual_seed(0)
+    model, diff = refshim.build({**ns.su.model_and_diffusion_defaults(), **flags}, rep_dim=512, A=A)
+    _dezero(model)
+    model.train()
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29577")
+    if not torch.distributed.is_initialized():
+        torch.distributed.init_process_group(backend="gloo", rank=0, world_size=1)
+    ns.logger.configure(dir=os.path.join("/tmp", f"cdae_ref_{os.getpid()}"), format_strs=[])
+    tl = ns.train.TrainLoop(model=model, diffusion=diff, data=None, batch_size=B, microbatch=-1, lr=1e-4, ema_rate="0.9999",
+                            log_interval=10 ** 9, save_interval=10 ** 9, resume_checkpoint="", rep_cond=True, n_vars=n_vars,
+                            causal_modeling=True, in_channels=in_channels)
+    return ns, model, diff, tl
+
+
+def _reference_cfg1_workload(cores):
+    """BASELINE.json configs[0] / SURVEY 8(d): MorphoMNIST-shaped 1x32x32, 2-variable graph, 64 ch x 2 res blocks, B = 16:
+    100 reference `TrainLoop.run_step` + one 10-step DDIM counterfactual through the reference's own API, on the CPU"""
+    from oracle import refshim
+    B = 16
+    ns, model, diff, tl = _reference_trainloop(CFG1, None, B, 2, 1)
+    g = torch.Generator().manual_seed(0)
+    x, c, y = torch.rand(B, 1, 32, 32, generator=g), torch.rand(B, 2, generator=g), torch.randint(0, 10, (B,), generator=g)
+    np.random.seed(0); torch.manual_seed(0)
+    tl.run_step(x, {"c": c, "y": y})
+    t0 = time.perf_counter()
+    for _ in range(100):
+        tl.run_step(x, {"c": c, "y": y})
+    dt_train = time.perf_counter() - t0
+    _, d10 = refshim.build({**ns.su.model_and_diffusion_defaults(), **CFG1, "timestep_respacing": "ddim10"}, rep_dim=512)
+    model.eval()
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        mu, var = model.rep_emb.encode(x)
+        var = torch.ones(var.shape) * 0.001
+        mu[:, :256] = 0.2
+        At = torch.tensor([[0, 1], [0, 0]], dtype=torch.float32)
+        z_post = model.causal_mask.nonlinearity_add_back_noise(mu, model.causal_mask.causal_masking(mu, At))
+        z = ns.nn.reparameterize(z_post, var)
+        x_T = d10.q_sample(x, torch.tensor([d10.num_timesteps - 1] * B), noise=torch.randn_like(x))
+        img = d10.ddim_sample_loop(model, tuple(x.shape), noise=x_T, clip_denoised=True, model_kwargs=dict(z=z, y=y))
+    dt_ddim = time.perf_counter() - t0
+    assert img.shape == x.shape
+    return {"workload": "cfg1 morphomnist32: 100 reference TrainLoop.run_step + DDIM-10 counterfactual, batch 16, fp32",
+            "train_img_per_s": B * 100 / dt_train, "train_s": dt_train, "ddim10_img_per_s": B / dt_ddim, "ddim10_s": dt_ddim,
+            "cores": cores}
+
+
 def run_reference(args):
-    """The reference algorithm (oracle/ = restatement pinned against the real reference) on the host cores, same
-    config/metric; each step is a bounded sample of the workload (small batch) so the run ends within minutes."""
+    """`--impl reference`: the reference's own CPU implementation of the path on the host cores - the unmodified reference
+    package through its own TrainLoop when it is available (oracle/_ref on the GPU box), else the oracle port.  Same config /
+    metric as the CUDA arm; each step is a bounded sample of the workload (batch --ref-batch of the per-GPU batch)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import model as om, diffusion as od, schedules
+    from oracle import refshim
     cores = os.cpu_count()
     torch.set_num_threads(cores)
     Bs = args.ref_batch
-    cfg = om.config_from_flags(**FLAGS, A=PENDULUM)
-    sd = om.seeded_state_dict(cfg, seed=0)
-    diff = od.Diffusion(steps=1000)
-    tr = od.RefTrainer(sd, cfg, diff, lr=1e-4, ema_rate=0.9999)
     x, cond = synth_batch(Bs, 0)
     np.random.seed(0); torch.manual_seed(0)
+    extra = {}
+    if refshim.available():
+        kind = "reference"
+        ns, model, diff, tl = _reference_trainloop(FLAGS, PENDULUM, Bs, 4, 3)
 
-    def step():
-        t, w = schedules.uniform_sample_t(1000, Bs)
-        tr.run_step(x, torch.from_numpy(t), torch.randn_like(x), torch.from_numpy(w), c=cond["c"])
+        def step():
+            tl.run_step(x, dict(cond))
+    else:
+        kind = "port"
+        from oracle import model as om, diffusion as od, schedules
+        cfg = om.config_from_flags(**FLAGS, A=PENDULUM)
+        sd = om.seeded_state_dict(cfg, seed=0)
+        tr = od.RefTrainer(sd, cfg, od.Diffusion(steps=1000), lr=1e-4, ema_rate=0.9999)
+
+        def step():
+            t, w = schedules.uniform_sample_t(1000, Bs)
+            tr.run_step(x, torch.from_numpy(t), torch.randn_like(x), torch.from_numpy(w), c=cond["c"])
 
     for _ in range(args.warmup):
         step()
@@ -116,41 +193,56 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     val = Bs * args.steps / dt
-    sample = f"{args.steps} optimisation steps at batch {Bs} (of the per-GPU batch {args.batch}), fp32, {cores} threads"
+    if kind == "reference" and not args.no_cfg1:
+        try:
+            extra["cfg1_workload"] = _reference_cfg1_workload(cores)
+        except Exception as ex:
+            extra["cfg1_workload"] = {"error": repr(ex)}
+    sample = (f"{args.steps} TrainLoop.run_step of the {'unmodified reference' if kind == 'reference' else 'oracle port'} at batch "
+              f"{Bs} (of the per-GPU batch {args.batch}), fp32, {cores} threads")
     print(json.dumps({
         "impl": "reference", "metric": "train_img_per_s", "value": val, "unit": "img/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD % args.batch, "sample": sample},
-        "cpu_baseline": {"value": val, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": val, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline": {"value": val, "unit": "img/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, **extra,
     }))
 
 
 def cpu_baseline_sample(batch):
-    """oracle timed on the host cores for ~10-30 s (rank 0, N=1 only)"""
-    from oracle import model as om, diffusion as od, schedules
+    """the reference (or, without it, the oracle port) timed on the host cores for ~10-30 s (rank 0, N=1 only)"""
+    from oracle import refshim
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    Bs, n = 4, 16       # ~10 s of CPU work on the GPU box's host cores
-    cfg = om.config_from_flags(**FLAGS, A=PENDULUM)
-    sd = om.seeded_state_dict(cfg, seed=0)
-    diff = od.Diffusion(steps=1000)
-    tr = od.RefTrainer(sd, cfg, diff, lr=1e-4)
+    Bs, n = 4, 16
     x, cond = synth_batch(Bs, 0)
     np.random.seed(0); torch.manual_seed(0)
+    if refshim.available():
+        kind = "reference"
+        ns, model, diff, tl = _reference_trainloop(FLAGS, PENDULUM, Bs, 4, 3)
 
-    def step():
-        t, w = schedules.uniform_sample_t(1000, Bs)
-        tr.run_step(x, torch.from_numpy(t), torch.randn_like(x), torch.from_numpy(w), c=cond["c"])
+        def step():
+            tl.run_step(x, dict(cond))
+    else:
+        kind = "port"
+        from oracle import model as om, diffusion as od, schedules
+        cfg = om.config_from_flags(**FLAGS, A=PENDULUM)
+        sd = om.seeded_state_dict(cfg, seed=0)
+        tr = od.RefTrainer(sd, cfg, od.Diffusion(steps=1000), lr=1e-4)
+
+        def step():
+            t, w = schedules.uniform_sample_t(1000, Bs)
+            tr.run_step(x, torch.from_numpy(t), torch.randn_like(x), torch.from_numpy(w), c=cond["c"])
 
     step()
     t0 = time.perf_counter()
     for _ in range(n):
         step()
     dt = time.perf_counter() - t0
-    return {"value": Bs * n / dt, "unit": "img/s", "cores": cores, "kind": "port",
-            "sample": f"{n} oracle optimisation steps at batch {Bs} (workload batch {batch}), fp32 torch CPU"}
+    return {"value": Bs * n / dt, "unit": "img/s", "cores": cores, "kind": kind,
+            "sample": f"{n} TrainLoop.run_step of the {'unmodified reference' if kind == 'reference' else 'oracle port'} at batch {Bs} "
+                      f"(workload batch {batch}), fp32 torch CPU"}
 
 
 # ---------------------------------------------------------------------------------------------- dominant-kernel roofline
@@ -283,6 +375,15 @@ def hbm_kernels(peaks):
         ops.gn_bwd(a["dy"], a["x0"], gam, bet, a["mean"], a["rstd"], x1=a["x1"], film=film, silu=True, dx0=a["dx0"],
                    dx1=a["dx1"], dgamma=dg, dbeta=db, dfilm=dfl)
     ms = timeit([lambda a=a: gbwd(a) for a in gsets])
+    out["groupnorm_bwd_resident"] = (6.0 * ng, ms)     # fallback kernel (reduces and applies in one launch)
+    # the backward the training step runs: du and {sum du, sum du*x} come out of the data-gradient conv's epilogue
+    # (cdae_igemm_desc.gnb_*), the norm's own backward is this one streaming pass: read du, x; write dx = 6 B / element
+    ws = torch.randn(Bg, Cg, 2, device=dev)
+
+    def gbwd2(a):
+        ops.gn_bwd_apply(a["dy"], a["x0"], gam, bet, a["mean"], a["rstd"], ws, x1=a["x1"], film=film, dx0=a["dx0"],
+                         dx1=a["dx1"], dgamma=dg, dbeta=db, dfilm=dfl)
+    ms = timeit([lambda a=a: gbwd2(a) for a in gsets])
     out["groupnorm_bwd"] = (6.0 * ng, ms)
     return {k: {"GB/s": round(b / ms / 1e6, 1), "frac": round(b / ms / 1e6 / peaks["hbm"], 3), "ms": round(ms, 4)}
             for k, (b, ms) in out.items()} | {"peak": peaks["hbm"], "peak_source": peaks["src"] + " hbm copy",
@@ -319,7 +420,6 @@ def run_cuda(args):
     loop = TrainLoop(model=model, diffusion=diff, data=None, batch_size=B, microbatch=-1, lr=1e-4, ema_rate="0.9999",
                      log_interval=10 ** 9, save_interval=10 ** 9, resume_checkpoint="", rep_cond=True, n_vars=4,
                      causal_modeling=True, in_channels=3)
-    loop.log_quartiles = False
     np.random.seed(1234 + rank)
     dev_batches = [synth_batch(B, 100 + rank * 10 + i, device=dev) for i in range(2)]
     host_batches = [synth_batch(B, 200 + rank * 10 + i, pinned=True) for i in range(3)]
@@ -371,8 +471,9 @@ def run_cuda(args):
             step_dev(0)
     clk = clocks.stop()
 
-    pl = model.engine.plan(B, True)
-    launches_per_step = pl.n_fwd_launch + pl.n_bwd_launch + 9     # + q_sample, mse fwd/bwd, zero, pack, adam, DAG layer fwd/bwd/finish
+    # counted, not derived: kernels issued through the C ABI while the step graph was captured (+ the optimizer's two)
+    fs = loop._fused.get(B)
+    launches_per_step = (fs.graph_kernels + 2) if fs is not None and getattr(fs, "graph_kernels", None) else None
     value = B * world / (ms_step / 1000)
     e2e = B * world / (ms_e2e / 1000)
     train_flops = 3 * FWD_GFLOP_PER_IMG * 1e9 * B
@@ -386,7 +487,8 @@ def run_cuda(args):
         "e2e": {"value": e2e, "unit": "img/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(B * (3 * 64 * 64 + 4) * 4 + B * 12), "d2h_bytes_per_step": 4,
                 "loss": last.get("loss")},
-        "gpu_launches": int(launches_per_step * args.steps),
+        "gpu_launches": int(launches_per_step * args.steps) if launches_per_step else None,
+        "gpu_launches_per_step": launches_per_step,
         "clocks": clk,
         "step_roofline": {"bound": "tensor", "achieved": train_flops / ms_step / 1e9, "peak": peaks["tf_sus"],
                           "unit": "TFLOP/s", "frac": train_flops / ms_step / 1e9 / peaks["tf_sus"],
@@ -482,6 +584,7 @@ def main():
     ap.add_argument("--ddim-batch", type=int, default=512, help="interventions per GPU (BASELINE configs[3]: 4096 over 8 GPUs)")
     ap.add_argument("--no-ddim", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cfg1", action="store_true", help="reference arm: skip the cfg1 (100 steps + DDIM-10) workload")
     args = ap.parse_args()
     if args.impl == "reference":
         # every step is a bounded sample (batch --ref-batch, ~0.5 s of CPU work): K and W are honoured as given

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcdae.so")
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["core.cu", "elementwise.cu", "layout.cu", "groupnorm.cu", "igemm.cu", "attention.cu", "small.cu", "dataset.cu"]
+SOURCES = ["core.cu", "elementwise.cu", "layout.cu", "groupnorm.cu", "igemm.cu", "attention.cu", "small.cu", "dataset.cu", "rep.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 # no --use_fast_math: the fp32 diffusion kernels are compared bit-for-bit with the oracle; kernels that want
 # approximate transcendentals call the intrinsics (__expf, ...) explicitly.

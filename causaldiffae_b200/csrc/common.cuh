@@ -45,6 +45,17 @@ __device__ __forceinline__ bf16x8 pack8(const float* f) {
 __device__ __forceinline__ bf16x8 ld8(const void* p) { return *reinterpret_cast<const bf16x8*>(p); }
 __device__ __forceinline__ void st8(void* p, const bf16x8& v) { *reinterpret_cast<bf16x8*>(p) = v; }
 
+// SiLU through one MUFU: with h = u/2, silu(u) = h + h*tanh(h) and silu'(u) = (1 + t + h*(1 - t^2)) / 2, t = tanh(h)
+__device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float2 tanh2(float2 h) { return make_float2(tanh_fast(h.x), tanh_fast(h.y)); }
+__device__ __forceinline__ float2 dsilu_half(float2 h) {
+  const float2 kM1 = make_float2(-1.f, -1.f), kHalf = make_float2(0.5f, 0.5f);
+  const float2 t = tanh2(h);
+  const float2 q = __ffma2_rn(t, t, kM1);                        // t^2 - 1
+  const float2 w = __ffma2_rn(__fmul2_rn(h, kM1), q, t);         // t + h*(1 - t^2)
+  return __ffma2_rn(w, kHalf, kHalf);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

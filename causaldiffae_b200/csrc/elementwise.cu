@@ -31,11 +31,11 @@ __global__ void __launch_bounds__(kEwThreads) q_sample_kernel(const float4* __re
 __global__ void __launch_bounds__(kEwThreads) mse_kernel(const float4* __restrict__ pred, const float4* __restrict__ tgt,
                                                          float* __restrict__ mse, const float* __restrict__ gscale,
                                                          float4* __restrict__ dpred, int64_t vec_per_sample,
-                                                         float inv_per_sample) {
+                                                         float inv_per_sample, float gmul) {
   const int64_t b = blockIdx.x;
   const float4* p = pred + b * vec_per_sample;
   const float4* q = tgt + b * vec_per_sample;
-  const float gs = (dpred && gscale) ? 2.0f * gscale[b] * inv_per_sample : 0.f;
+  const float gs = (dpred && gscale) ? 2.0f * (gscale[b] * gmul) * inv_per_sample : 0.f;
   float acc = 0.f;
   for (int64_t i = threadIdx.x; i < vec_per_sample; i += blockDim.x) {
     const float4 a = p[i], c = q[i];
@@ -157,8 +157,9 @@ __global__ void __launch_bounds__(kEwThreads) adam_ema_kernel(float4* __restrict
 }
 
 // runs after the update: the step counter moves on unless the guard vetoed the step
-__global__ void adam_tick_kernel(int64_t* step, const float* guard) {
+__global__ void adam_tick_kernel(int64_t* step, const float* guard, const float* gsq, float* lognorm) {
   if (!(guard && !isfinite(*guard))) *step += 1;
+  if (lognorm && gsq) { lognorm[0] += sqrtf(*gsq); lognorm[1] += 1.f; }     // the logger's running mean of the gradient norm
 }
 
 // sum of squares of a flat fp32 buffer accumulated into *out (the non-finite-gradient guard; also a grad-norm probe)
@@ -218,14 +219,14 @@ extern "C" int cdae_q_sample(const float* x0, const float* noise, const int64_t*
   return CDAE_OK;
 }
 
-extern "C" int cdae_mse_loss(const float* pred, const float* target, float* mse, const float* gscale, float* dpred,
-                             int64_t B, int64_t per_sample, cdae_stream s) {
+extern "C" int cdae_mse_loss(const float* pred, const float* target, float* mse, const float* gscale, float gmul,
+                             float* dpred, int64_t B, int64_t per_sample, cdae_stream s) {
   if (B == 0) return CDAE_OK;
   CDAE_CHECK_ARG(pred && target && mse, "mse_loss: null pointer");
   CDAE_CHECK_SHAPE(per_sample % 4 == 0 && aligned16(pred) && aligned16(target) && (!dpred || aligned16(dpred)),
                    "mse_loss: per_sample %% 4 and 16-byte alignment required");
   mse_kernel<<<(unsigned)B, kEwThreads, 0, (cudaStream_t)s>>>((const float4*)pred, (const float4*)target, mse, gscale,
-                                                               (float4*)dpred, per_sample / 4, 1.0f / (float)per_sample);
+                                                               (float4*)dpred, per_sample / 4, 1.0f / (float)per_sample, gmul);
   CDAE_CHECK_LAUNCH("mse_kernel");
   return CDAE_OK;
 }
@@ -246,7 +247,7 @@ extern "C" int cdae_ddim_step(const float* x, const float* eps_c, const float* e
 }
 
 extern "C" int cdae_adam_ema(float* p, const void* g, int g_is_bf16, float* m, float* v, float* ema, const float* hyper,
-                             int64_t* step, const float* guard, float* gsq_out, int64_t n, cdae_stream s) {
+                             int64_t* step, const float* guard, float* gsq_out, float* lognorm, int64_t n, cdae_stream s) {
   if (n == 0) return CDAE_OK;
   CDAE_CHECK_ARG(p && g && m && v && hyper && step, "adam_ema: null pointer");
   CDAE_CHECK_SHAPE(n % 4 == 0 && aligned16(p) && aligned16(m) && aligned16(v) && (!ema || aligned16(ema)) &&
@@ -261,7 +262,7 @@ extern "C" int cdae_adam_ema(float* p, const void* g, int g_is_bf16, float* m, f
                                                                                (float4*)v, (float4*)ema, hyper, step, guard,
                                                                                gsq_out, n / 4);
   CDAE_CHECK_LAUNCH("adam_ema_kernel");
-  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)s>>>(step, guard);
+  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)s>>>(step, guard, gsq_out, lognorm);
   CDAE_CHECK_LAUNCH("adam_tick_kernel");
   return CDAE_OK;
 }

@@ -343,8 +343,6 @@ constexpr int kPipeElems = 16384;       // 32 KB slab; two of them + statistics 
 constexpr int kResThreads = 256;
 constexpr int kResWarps = kResThreads / 32;
 
-__device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -380,8 +378,6 @@ __device__ __forceinline__ uint4 pack_u4_2(const float2* f) {
   h = __float22bfloat162_rn(f[3]); r.w = *reinterpret_cast<uint32_t*>(&h);
   return r;
 }
-__device__ __forceinline__ float2 tanh2(float2 h) { return make_float2(tanh_fast(h.x), tanh_fast(h.y)); }
-
 // eight consecutive floats (two 128-bit loads when the address allows)
 __device__ __forceinline__ void load8f(const float* q, bool v4, float* o) {
   if (v4) {
@@ -793,6 +789,8 @@ struct GnApplyParams {
   int C0, C1, C, HW;
   const float* gamma; const float* beta; const float* film; int film_ld, film_off;
   __nv_bfloat16* y; float* mean; float* rstd;
+  float* ab;                                // optional fp32 [B][C][2]: the per-(image, channel) constants {a, b} with
+                                            // u (or u/2 under SiLU) = a x + b, kept for the fused backward (igemm gnb_ab)
   int ppc;                                  // pixels per CTA
   int nvec, R;                              // 16 B vectors per pixel row; pixel rows per CTA pass (threads >= nvec*R idle)
 };
@@ -856,6 +854,8 @@ __global__ void __launch_bounds__(kApplyThreads, 3) gn_apply_fwd_kernel(const Gn
     const float m = gm[g], rs = gr[g];
     cs[c] = half * rs * gk;
     cq[c] = half * (hk - m * rs * gk);
+    if (p.ab && blockIdx.x == 0)
+      *reinterpret_cast<float2*>(p.ab + ((size_t)b * p.C + c) * 2) = make_float2(cs[c], cq[c]);
   }
   __syncthreads();
   if (!active) return;
@@ -893,150 +893,39 @@ __global__ void __launch_bounds__(kApplyThreads, 3) gn_apply_fwd_kernel(const Gn
 }
 
 // ------------------------------------------------------------------------------------------------ streaming backward
-// Two passes, both plain streaming kernels (no clusters, nothing resident on chip):
-//   gn_bwd_reduce_kernel : reads dy and x once, recomputes du = dy * silu'(u) and accumulates P_c = sum du,
-//                          Qx_c = sum du*x per (sample, channel) into the workspace ws[b][2][C] (fp32 red.add);
-//   gn_bwd_apply_kernel  : folds ws into the group constants, reads dy and x again - samples and pixel chunks are walked
-//                          in REVERSE launch order, so what the reduce pass touched last is still in the 126 MB L2 -
-//                          recomputes du and writes dx = K1*du - K2' - x*K3' (+ dadd) (+ old dx); the first pixel chunk of
-//                          every sample also emits d gamma / d beta / d FiLM.
-// DRAM traffic approaches the single-pass 6 B/element whenever dy and x of a layer fit in L2.  Same math as
-// gn_bwd_pipe_kernel (see the derivation above it).
+// The data-gradient convolution that produces the gradient w.r.t. the GroupNorm OUTPUT has already (cdae_igemm_desc.gnb_*)
+// turned it into du = dy * silu'(u) and accumulated P_c = sum du, Qx_c = sum du*x per (image, channel) in its epilogue - the
+// backward twin of the forward statistics epilogue.  What is left is a pure streaming pass with the shape of
+// gn_apply_fwd_kernel: every CTA folds the <= 1024 channel sums of its sample into three per-channel constants and streams
+// its pixel range once:   dx = K1*du - K2' - x*K3'  (+ dadd) (+ old dx)
+//   G = gamma (1 + scale), Qc = rstd (Qx_c - mean P_c), s1 = sum_group G P, s2 = sum_group G Qc, n = HW * C/32
+//   K1 = rstd G,  K3' = rstd^2 s2 / n,  K2' = rstd s1 / n - mean K3'
+// The first pixel chunk of every sample also emits d gamma / d beta / d FiLM.  2 B (du) + 2 B (x) read, 2 B written per
+// element; no clusters, no reduction, no second read.
 struct GnBwdParams {
-  const __nv_bfloat16* dy; const __nv_bfloat16* x0; const __nv_bfloat16* x1; const __nv_bfloat16* dadd;
+  const __nv_bfloat16* du; const __nv_bfloat16* x0; const __nv_bfloat16* x1; const __nv_bfloat16* dadd;
   __nv_bfloat16* dx0; __nv_bfloat16* dx1;
   int C0, C1, C, HW, B;
   const float* gamma; const float* beta; const float* film; int film_ld, film_off;
   const float* mean; const float* rstd;
-  float* ws;                                // [B][2][C]
+  const float* ws;                          // [B][C][2] = {P_c, Qx_c}
   float* dgamma; float* dbeta; float* dfilm;
   int accumulate_dx;
   int ppc, nvec, R;
 };
 constexpr int kBwdThreads = 256;
+constexpr int kBwdUnroll = 2;
 
-// silu'(u) from h = u/2: (1 + t + h*(1 - t^2)) / 2 with t = tanh(h)
-__device__ __forceinline__ float2 dsilu_half(float2 h) {
-  const float2 kM1 = make_float2(-1.f, -1.f), kHalf = make_float2(0.5f, 0.5f);
-  const float2 t = tanh2(h);
-  const float2 q = __ffma2_rn(t, t, kM1);                        // t^2 - 1
-  const float2 w = __ffma2_rn(__fmul2_rn(h, kM1), q, t);         // t + h*(1 - t^2)
-  return __ffma2_rn(w, kHalf, kHalf);
-}
-
-// per-channel forward constants of sample b into shared memory: a[c] = half*rstd*G, bb[c] = half*(H - mean*rstd*G)
-__device__ __forceinline__ void gn_bwd_fwd_consts(const GnBwdParams& p, int b, float half, float* a, float* bb, float* Gs) {
-  const int cpg = p.C / kGroups;
-  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
-    const float ga = __ldg(p.gamma + c), be = __ldg(p.beta + c);
-    float sc1 = 1.f, sh = 0.f;
-    if (p.film) {
-      const float* fr = p.film + (size_t)b * p.film_ld + p.film_off;
-      sc1 = 1.f + __ldg(fr + c); sh = __ldg(fr + p.C + c);
-    }
-    const float G = ga * sc1, Hh = be * sc1 + sh;
-    const int g = c / cpg;
-    const float m = __ldg(p.mean + b * kGroups + g), rs = __ldg(p.rstd + b * kGroups + g);
-    a[c] = half * rs * G;
-    bb[c] = half * (Hh - m * rs * G);
-    if (Gs) Gs[c] = G;
-  }
-}
-
-// smem: float a[C] | float bb[C] | float red[R][2][C]
-template <bool SILU>
-__global__ void __launch_bounds__(kBwdThreads, 3) gn_bwd_reduce_kernel(const GnBwdParams p) {
+// smem: float K1[C] | float K2n[C] | float K3n[C] | float G[C] | float P[C] | float Qc[C]
+__global__ void __launch_bounds__(kBwdThreads, 3) gn_bwd_apply_kernel(const GnBwdParams p) {
   extern __shared__ __align__(16) float sm_bwd[];
-  float* a = sm_bwd;
-  float* bb = a + p.C;
-  float* red = bb + p.C;
-  const int b = blockIdx.y;
-  const int vec = threadIdx.x % p.nvec, row = threadIdx.x / p.nvec;
-  const bool active = row < p.R;
-  const int cl = vec * 8;
-  const bool in0 = cl < p.C0;
-  const int xpitch = in0 ? p.C0 : p.C1;
-  const __nv_bfloat16* xb = in0 ? p.x0 + (size_t)b * p.HW * p.C0 + cl : p.x1 + (size_t)b * p.HW * p.C1 + (cl - p.C0);
-  const __nv_bfloat16* db = p.dy + (size_t)b * p.HW * p.C + cl;
-  const int p0 = blockIdx.x * p.ppc, p1 = min(p.HW, p0 + p.ppc);
-  int pix = p0 + row;
-  uint4 vx[2], vd[2];
-  if (active) {
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int pk = pix + k * p.R;
-      if (pk < p1) {
-        vx[k] = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)pk * xpitch));
-        vd[k] = __ldg(reinterpret_cast<const uint4*>(db + (size_t)pk * p.C));
-      }
-    }
-  }
-  if (SILU) gn_bwd_fwd_consts(p, b, 0.5f, a, bb, nullptr);
-  __syncthreads();
-  float2 P2[4], Q2[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) { P2[k] = make_float2(0.f, 0.f); Q2[k] = make_float2(0.f, 0.f); }
-  if (active) {
-    float2 aG[4], bH[4];
-    if (SILU) {
-      *reinterpret_cast<float4*>(aG) = *reinterpret_cast<const float4*>(a + cl);
-      *reinterpret_cast<float4*>(aG + 2) = *reinterpret_cast<const float4*>(a + cl + 4);
-      *reinterpret_cast<float4*>(bH) = *reinterpret_cast<const float4*>(bb + cl);
-      *reinterpret_cast<float4*>(bH + 2) = *reinterpret_cast<const float4*>(bb + cl + 4);
-    }
-    const int step = 2 * p.R;
-    for (; pix < p1; pix += step) {
-      uint4 nx[2], nd[2];
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int pk = pix + step + k * p.R;
-        if (pk < p1) {
-          nx[k] = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)pk * xpitch));
-          nd[k] = __ldg(reinterpret_cast<const uint4*>(db + (size_t)pk * p.C));
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        if (pix + k * p.R < p1) {
-          float2 f[4], d[4];
-          unpack_u4_2(vx[k], f); unpack_u4_2(vd[k], d);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (SILU) d[e] = __fmul2_rn(d[e], dsilu_half(__ffma2_rn(f[e], aG[e], bH[e])));
-            P2[e] = __fadd2_rn(P2[e], d[e]); Q2[e] = __ffma2_rn(d[e], f[e], Q2[e]);
-          }
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 2; ++k) { vx[k] = nx[k]; vd[k] = nd[k]; }
-    }
-    float* r = red + (size_t)row * 2 * p.C;
-    *reinterpret_cast<float4*>(r + cl) = make_float4(P2[0].x, P2[0].y, P2[1].x, P2[1].y);
-    *reinterpret_cast<float4*>(r + cl + 4) = make_float4(P2[2].x, P2[2].y, P2[3].x, P2[3].y);
-    *reinterpret_cast<float4*>(r + p.C + cl) = make_float4(Q2[0].x, Q2[0].y, Q2[1].x, Q2[1].y);
-    *reinterpret_cast<float4*>(r + p.C + cl + 4) = make_float4(Q2[2].x, Q2[2].y, Q2[3].x, Q2[3].y);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) {
-    float t = 0.f;
-    for (int rr = 0; rr < p.R; ++rr) t += red[(size_t)rr * 2 * p.C + i];
-    atomicAdd(p.ws + (size_t)b * 2 * p.C + i, t);
-  }
-}
-
-// smem: float a[C] | float bb[C] | float G[C] | float tot[2][C] | float K1[C] | float K2n[C] | float K3n[C]
-template <bool SILU>
-__global__ void __launch_bounds__(kBwdThreads, 2) gn_bwd_apply_kernel(const GnBwdParams p) {
-  extern __shared__ __align__(16) float sm_bwd[];
-  float* a = sm_bwd;
-  float* bb = a + p.C;
-  float* Gs = bb + p.C;
-  float* tot = Gs + p.C;
-  float* K1s = tot + 2 * p.C;
+  float* K1s = sm_bwd;
   float* K2s = K1s + p.C;
   float* K3s = K2s + p.C;
-  const int b = p.B - 1 - (int)blockIdx.y;                       // reverse order: the tail of the reduce pass is still in L2
-  const int chunk = (int)gridDim.x - 1 - (int)blockIdx.x;
+  float* Gs = K3s + p.C;
+  float* Ps = Gs + p.C;
+  float* Qs = Ps + p.C;
+  const int b = blockIdx.y, chunk = blockIdx.x;
   const int cpg = p.C / kGroups;
   const float inv_n = 1.f / ((float)cpg * (float)p.HW);
   const int vec = threadIdx.x % p.nvec, row = threadIdx.x / p.nvec;
@@ -1045,13 +934,14 @@ __global__ void __launch_bounds__(kBwdThreads, 2) gn_bwd_apply_kernel(const GnBw
   const bool in0 = cl < p.C0;
   const int xpitch = in0 ? p.C0 : p.C1;
   const __nv_bfloat16* xb = in0 ? p.x0 + (size_t)b * p.HW * p.C0 + cl : p.x1 + (size_t)b * p.HW * p.C1 + (cl - p.C0);
-  const __nv_bfloat16* db = p.dy + (size_t)b * p.HW * p.C + cl;
+  const __nv_bfloat16* db = p.du + (size_t)b * p.HW * p.C + cl;
   const int p0 = chunk * p.ppc, p1 = min(p.HW, p0 + p.ppc);
   int pix = p0 + row;
-  uint4 vx[2], vd[2];
+  // the first rows are requested before the constant prologue: their DRAM latency hides its dependent L2 round trips
+  uint4 vx[kBwdUnroll], vd[kBwdUnroll];
   if (active) {
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < kBwdUnroll; ++k) {
       const int pk = pix + k * p.R;
       if (pk < p1) {
         vx[k] = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)pk * xpitch));
@@ -1059,8 +949,14 @@ __global__ void __launch_bounds__(kBwdThreads, 2) gn_bwd_apply_kernel(const GnBw
       }
     }
   }
-  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) tot[i] = __ldcg(p.ws + (size_t)b * 2 * p.C + i);
-  gn_bwd_fwd_consts(p, b, SILU ? 0.5f : 1.f, a, bb, Gs);
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    const float2 t = __ldcg(reinterpret_cast<const float2*>(p.ws) + (size_t)b * p.C + c);
+    const int g = c / cpg;
+    const float m = __ldg(p.mean + b * kGroups + g), rs = __ldg(p.rstd + b * kGroups + g);
+    float G = __ldg(p.gamma + c);
+    if (p.film) G *= 1.f + __ldg(p.film + (size_t)b * p.film_ld + p.film_off + c);
+    Gs[c] = G; Ps[c] = t.x; Qs[c] = rs * (t.y - m * t.x);
+  }
   __syncthreads();
   for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
     const int g = c / cpg;
@@ -1068,15 +964,14 @@ __global__ void __launch_bounds__(kBwdThreads, 2) gn_bwd_apply_kernel(const GnBw
     float s1 = 0.f, s2 = 0.f;
     for (int k = 0; k < cpg; ++k) {
       const int lc = g * cpg + k;
-      const float Pc = tot[lc], Qc = rs * (tot[p.C + lc] - m * Pc);
-      s1 = fmaf(Gs[lc], Pc, s1); s2 = fmaf(Gs[lc], Qc, s2);
+      s1 = fmaf(Gs[lc], Ps[lc], s1); s2 = fmaf(Gs[lc], Qs[lc], s2);
     }
     const float K3 = rs * rs * s2 * inv_n;
     K1s[c] = rs * Gs[c];
     K2s[c] = -(rs * s1 * inv_n - m * K3);     // stored negated: dx = K1*du + (x*(-K3') + (-K2'))
     K3s[c] = -K3;
     if (chunk == 0) {                         // one CTA per sample owns the parameter gradients
-      const float Pc = tot[c], Qc = rs * (tot[p.C + c] - m * Pc);
+      const float Pc = Ps[c], Qc = Qs[c];
       const float ga = __ldg(p.gamma + c), be = __ldg(p.beta + c);
       float sc1 = 1.f;
       if (p.film) {
@@ -1093,20 +988,20 @@ __global__ void __launch_bounds__(kBwdThreads, 2) gn_bwd_apply_kernel(const GnBw
   }
   __syncthreads();
   if (!active) return;
-  float2 aG[4], bH[4], K1[4], K2[4], K3[4];
+  float2 K1[4], K2[4], K3[4];
 #define LD8(dst, src) *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>((src) + cl); \
                       *reinterpret_cast<float4*>((dst) + 2) = *reinterpret_cast<const float4*>((src) + cl + 4)
-  LD8(aG, a); LD8(bH, bb); LD8(K1, K1s); LD8(K2, K2s); LD8(K3, K3s);
+  LD8(K1, K1s); LD8(K2, K2s); LD8(K3, K3s);
 #undef LD8
   const bool acc = (p.accumulate_dx >> (in0 ? 0 : 1)) & 1;
   const bool hasadd = p.dadd != nullptr;
   __nv_bfloat16* ob = in0 ? p.dx0 + (size_t)b * p.HW * p.C0 + cl : p.dx1 + (size_t)b * p.HW * p.C1 + (cl - p.C0);
   const __nv_bfloat16* ab = hasadd ? p.dadd + (size_t)b * p.HW * p.C + cl : nullptr;
-  const int step = 2 * p.R;
+  const int step = kBwdUnroll * p.R;
   for (; pix < p1; pix += step) {
-    uint4 nx[2], nd[2], vo[2], va[2];
+    uint4 nx[kBwdUnroll], nd[kBwdUnroll], vo[kBwdUnroll], va[kBwdUnroll];
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < kBwdUnroll; ++k) {
       const int pk = pix + step + k * p.R;
       if (pk < p1) {
         nx[k] = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)pk * xpitch));
@@ -1119,16 +1014,13 @@ __global__ void __launch_bounds__(kBwdThreads, 2) gn_bwd_apply_kernel(const GnBw
       }
     }
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < kBwdUnroll; ++k) {
       const int pc = pix + k * p.R;
       if (pc < p1) {
         float2 f[4], d[4], o[4];
         unpack_u4_2(vx[k], f); unpack_u4_2(vd[k], d);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if (SILU) d[e] = __fmul2_rn(d[e], dsilu_half(__ffma2_rn(f[e], aG[e], bH[e])));
-          o[e] = __ffma2_rn(K1[e], d[e], __ffma2_rn(f[e], K3[e], K2[e]));       // K2, K3 are negated
-        }
+        for (int e = 0; e < 4; ++e) o[e] = __ffma2_rn(K1[e], d[e], __ffma2_rn(f[e], K3[e], K2[e]));       // K2, K3 are negated
         if (acc) {
           float2 t[4];
           unpack_u4_2(vo[k], t);
@@ -1145,10 +1037,9 @@ __global__ void __launch_bounds__(kBwdThreads, 2) gn_bwd_apply_kernel(const GnBw
       }
     }
 #pragma unroll
-    for (int k = 0; k < 2; ++k) { vx[k] = nx[k]; vd[k] = nd[k]; }
+    for (int k = 0; k < kBwdUnroll; ++k) { vx[k] = nx[k]; vd[k] = nd[k]; }
   }
 }
-
 
 static inline size_t gn_pipe_smem(const GnParams& p, bool bwd) {
   const size_t slabs = 2 * (size_t)p.per * p.CC * 2;
@@ -1313,15 +1204,16 @@ extern "C" int cdae_gn_fwd(const void* x0, int C0, const void* x1, int C1, int B
 
 extern "C" int cdae_gn_apply_fwd(const void* x0, int C0, const float* stats0, const void* x1, int C1, const float* stats1,
                                  int B, int HW, const float* gamma, const float* beta, const float* film, int film_ld,
-                                 int film_off, int silu, void* y, float* mean, float* rstd, cdae_stream s) {
+                                 int film_off, int silu, void* y, float* mean, float* rstd, float* ab, cdae_stream s) {
   if (B == 0 || HW == 0) return CDAE_OK;
   CDAE_CHECK_ARG(x0 && stats0 && gamma && beta && y && mean && rstd && (C1 == 0 || (x1 && stats1)), "gn_apply_fwd: null pointer");
+  CDAE_CHECK_ARG((reinterpret_cast<uintptr_t>(ab) & 7) == 0, "gn_apply_fwd: misaligned constant table");
   GnApplyParams p;
   memset(&p, 0, sizeof(p));
   p.x0 = (const __nv_bfloat16*)x0; p.x1 = (const __nv_bfloat16*)x1; p.st0 = stats0; p.st1 = stats1;
   p.C0 = C0; p.C1 = C1; p.C = C0 + C1; p.HW = HW;
   p.gamma = gamma; p.beta = beta; p.film = film; p.film_ld = film_ld; p.film_off = film_off;
-  p.y = (__nv_bfloat16*)y; p.mean = mean; p.rstd = rstd;
+  p.y = (__nv_bfloat16*)y; p.mean = mean; p.rstd = rstd; p.ab = ab;
   CDAE_CHECK_SHAPE(p.C % kGroups == 0 && C0 % 8 == 0 && C1 % 8 == 0, "gn_apply_fwd: C0=%d C1=%d (C %% 32, C0/C1 %% 8)", C0, C1);
   CDAE_CHECK_SHAPE(p.C / 8 <= kApplyThreads, "gn_apply_fwd: C=%d too large", p.C);
   CDAE_CHECK_ARG(aligned16(x0) && aligned16(y) && (!x1 || aligned16(x1)) && (reinterpret_cast<uintptr_t>(stats0) & 7) == 0 &&
@@ -1374,42 +1266,36 @@ extern "C" int cdae_gn_bwd(const void* dy, const void* x0, int C0, const void* x
   return gn_launch(gn_bwd_kernel<4, 4>, p, B, S, smem, (cudaStream_t)s, "gn_bwd_kernel");
 }
 
-extern "C" int cdae_gn_bwd_stream(const void* dy, const void* x0, int C0, const void* x1, int C1, int B, int HW,
-                                  const float* gamma, const float* beta, const float* film, int film_ld, int film_off,
-                                  int silu, const float* mean, const float* rstd, const void* dadd, void* dx0, void* dx1,
-                                  int accumulate_dx, float* dgamma, float* dbeta, float* dfilm, float* ws, cdae_stream s) {
+extern "C" int cdae_gn_bwd_apply(const void* du, const void* x0, int C0, const void* x1, int C1, int B, int HW,
+                                 const float* gamma, const float* beta, const float* film, int film_ld, int film_off,
+                                 const float* mean, const float* rstd, const float* ws, const void* dadd, void* dx0, void* dx1,
+                                 int accumulate_dx, float* dgamma, float* dbeta, float* dfilm, cdae_stream s) {
   if (B == 0 || HW == 0) return CDAE_OK;
-  CDAE_CHECK_ARG(dy && x0 && gamma && beta && mean && rstd && dx0 && ws && (C1 == 0 || (x1 && dx1)), "gn_bwd_stream: null pointer");
+  CDAE_CHECK_ARG(du && x0 && gamma && beta && mean && rstd && dx0 && ws && (C1 == 0 || (x1 && dx1)), "gn_bwd_apply: null pointer");
   GnBwdParams p;
   memset(&p, 0, sizeof(p));
-  p.dy = (const __nv_bfloat16*)dy; p.x0 = (const __nv_bfloat16*)x0; p.x1 = (const __nv_bfloat16*)x1;
+  p.du = (const __nv_bfloat16*)du; p.x0 = (const __nv_bfloat16*)x0; p.x1 = (const __nv_bfloat16*)x1;
   p.dadd = (const __nv_bfloat16*)dadd; p.dx0 = (__nv_bfloat16*)dx0; p.dx1 = (__nv_bfloat16*)dx1;
   p.C0 = C0; p.C1 = C1; p.C = C0 + C1; p.HW = HW; p.B = B;
   p.gamma = gamma; p.beta = beta; p.film = film; p.film_ld = film_ld; p.film_off = film_off;
   p.mean = mean; p.rstd = rstd; p.ws = ws; p.dgamma = dgamma; p.dbeta = dbeta; p.dfilm = dfilm;
   p.accumulate_dx = accumulate_dx;
-  CDAE_CHECK_SHAPE(p.C % kGroups == 0 && C0 % 8 == 0 && C1 % 8 == 0, "gn_bwd_stream: C0=%d C1=%d (C %% 32, C0/C1 %% 8)", C0, C1);
-  CDAE_CHECK_SHAPE(p.C / 8 <= kBwdThreads && B <= 65535, "gn_bwd_stream: C=%d or B=%d too large", p.C, B);
-  CDAE_CHECK_ARG(aligned16(dy) && aligned16(x0) && aligned16(dx0) && (!x1 || (aligned16(x1) && aligned16(dx1))) &&
-                 (!dadd || aligned16(dadd)), "gn_bwd_stream: misaligned pointer");
+  CDAE_CHECK_SHAPE(p.C % kGroups == 0 && C0 % 8 == 0 && C1 % 8 == 0, "gn_bwd_apply: C0=%d C1=%d (C %% 32, C0/C1 %% 8)", C0, C1);
+  CDAE_CHECK_SHAPE(p.C / 8 <= kBwdThreads && B <= 65535, "gn_bwd_apply: C=%d or B=%d too large", p.C, B);
+  CDAE_CHECK_ARG(aligned16(du) && aligned16(x0) && aligned16(dx0) && (!x1 || (aligned16(x1) && aligned16(dx1))) &&
+                 (!dadd || aligned16(dadd)) && (reinterpret_cast<uintptr_t>(ws) & 7) == 0, "gn_bwd_apply: misaligned pointer");
   p.nvec = p.C / 8;
   p.R = kBwdThreads / p.nvec;
-  const int quantum = 2 * p.R;
-  int ppc = (32 * 1024) / (p.C * 2);               // ~32 KB of dy (and as much of x) per CTA
+  const int quantum = kBwdUnroll * p.R;
+  int ppc = (32 * 1024) / (p.C * 2);               // ~32 KB of du (and as much of x) per CTA
   ppc = ppc / quantum * quantum;
   if (ppc < quantum) ppc = quantum;
   while (ppc > quantum && (int64_t)B * ((HW + ppc - 1) / ppc) < 2 * 3 * kNumSMs) ppc -= quantum;
   if (ppc > HW) ppc = HW;
   p.ppc = ppc;
   dim3 grid((unsigned)((HW + ppc - 1) / ppc), (unsigned)B);
-  const size_t smem_r = sizeof(float) * (2 * (size_t)p.C + (size_t)p.R * 2 * p.C);
-  const size_t smem_a = sizeof(float) * (8 * (size_t)p.C);
-  cudaStream_t st = (cudaStream_t)s;
-  if (silu) gn_bwd_reduce_kernel<true><<<grid, kBwdThreads, smem_r, st>>>(p);
-  else gn_bwd_reduce_kernel<false><<<grid, kBwdThreads, smem_r, st>>>(p);
-  CDAE_CHECK_LAUNCH("gn_bwd_reduce_kernel");
-  if (silu) gn_bwd_apply_kernel<true><<<grid, kBwdThreads, smem_a, st>>>(p);
-  else gn_bwd_apply_kernel<false><<<grid, kBwdThreads, smem_a, st>>>(p);
+  const size_t smem = sizeof(float) * (6 * (size_t)p.C);
+  gn_bwd_apply_kernel<<<grid, kBwdThreads, smem, (cudaStream_t)s>>>(p);
   CDAE_CHECK_LAUNCH("gn_bwd_apply_kernel");
   return CDAE_OK;
 }

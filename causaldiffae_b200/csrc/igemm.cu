@@ -76,6 +76,15 @@ struct alignas(64) IgemmKParams {
   const float* bias;
   const float* bias2;
   float* stats;      // optional fp32 [Nimg][cout][2]: per-(image, channel) sum / sum of squares of the stored bf16 output
+  // GroupNorm-backward fusion of a data-gradient launch (cdae_igemm_desc.gnb_*): the output dy is the gradient w.r.t. the
+  // OUTPUT of a GroupNorm(+FiLM)(+SiLU) whose input x = concat(gnb_x0, gnb_x1) has the same pixel grid.  The epilogue
+  // fetches the matching x slab over the residual TMA path, turns dy into du = dy * silu'(u) (u/2 = a x + b from the forward
+  // pass's per-(image, channel) constant table), stores du, and accumulates sum du / sum du*x per (image, channel).
+  CUtensorMap tmR2;  // x slab of the second source
+  float* gnb_ws;     // fp32 [Nimg][cout][2] += {sum du, sum du*x}
+  const float* gnb_ab;
+  const __nv_bfloat16* gnb_x0; const __nv_bfloat16* gnb_x1;
+  int gnb_c0, gnb_ld0, gnb_ld1, gnb_silu, lgBW, lgBH;
   int nboxes, ntn;   // number of 128-pixel boxes and of N tiles
   // halo kernel (3x3 stride 1): K is walked source-chunk-major; each 64-channel chunk brings ONE halo tile per box
   struct { int src, c0, nchunk, ntap, wk0; } hs[8];
@@ -89,7 +98,18 @@ struct EpiCtx {
   uint32_t tmem_base, stg_base;
   uint32_t tfull0, tempty0, sready0, sfree0;   // shared addresses of the first barrier of each kind (8 B apart)
   int total_tiles, boxes_per_img;
+  uint32_t abs_base;                           // [NS][ABI] x 512 B: {a, b} of the 64 slab channels per image of the box
+  int abi;
 };
+
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128f(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 // warps 2..5: tcgen05.ld -> +bias (+bias2) (+residual) -> bf16 -> 128B-swizzled smem slab -> TMA store.  Nothing here
 // waits on global memory: stores are asynchronous bulk copies, the residual slab is prefetched by the staging warp
@@ -130,7 +150,8 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmKParams& p, const EpiC
         // are real output pixels, and the image they belong to (BW*BH >= 32, checked on the host)
         uint32_t vmask = 0;
         int nimg = 0;
-        if (SLABW == 64 && p.stats != nullptr) {
+        const bool gnb = SLABW == 64 && p.gnb_ws != nullptr;
+        if (SLABW == 64 && (p.stats != nullptr || gnb)) {
           const int pb = p.BW * p.BH;
           const bool row_ok = (nn0 + r / pb < p.Nimg) && (h0 + (r / p.BW) % p.BH < p.OHt) && (w0 + r % p.BW < p.OWt);
           vmask = __ballot_sync(0xffffffffu, row_ok);
@@ -154,6 +175,8 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmKParams& p, const EpiC
           tmem_ld_wait();
           mbar_wait(sready_bar(buf), sph);           // staging buffer drained (and residual slab landed)
           const uint32_t row = stg_base + buf * kSlabStride + r * (SLABW * 2);
+          // GroupNorm-backward fusion: forward constants of this warp's image, staged by the manager warp
+          const uint32_t abrow = cx.abs_base + (uint32_t)(buf * cx.abi + (q * 32) / (p.BW * p.BH)) * 512u;
 #pragma unroll
           for (int j = 0; j < SLABW / 8; ++j) {
             float v[8];
@@ -174,7 +197,19 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmKParams& p, const EpiC
             // 16 B chunk j of row r sits at chunk (j ^ (r & 7)) under the 128B swizzle (SLABW == 64); narrower slabs
             // are stored unswizzled (their tensor maps use SWIZZLE_NONE)
             const uint32_t a = SLABW == 64 ? row + (uint32_t)((j ^ (r & 7)) << 4) : row + (uint32_t)(j << 4);
-            if (p.has_resid) {
+            if (gnb) {
+              if (p.gnb_silu) {                          // du = dy * silu'(u), u/2 = a x + b
+                float rv[8];
+                unpack8(lds8(a), rv);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float4 c4 = lds128f(abrow + (uint32_t)(j * 8 + 2 * e) * 8u);      // {a0, b0, a1, b1}
+                  const float2 h = make_float2(fmaf(rv[2 * e], c4.x, c4.y), fmaf(rv[2 * e + 1], c4.z, c4.w));
+                  const float2 d = dsilu_half(h);
+                  v[2 * e] *= d.x; v[2 * e + 1] *= d.y;
+                }
+              }
+            } else if (p.has_resid) {
               float rv[8];
               unpack8(lds8(a), rv);
 #pragma unroll
@@ -197,15 +232,40 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmKParams& p, const EpiC
             const uint32_t sb = stg_base + buf * kSlabStride + (uint32_t)(q * 32) * 128u + (uint32_t)((lane & 3) << 2);
             const uint32_t cj = (uint32_t)(lane >> 2);
             float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+            if (!gnb) {
 #pragma unroll 8
-            for (int i = 0; i < 32; ++i) {
-              uint32_t u = lds32(sb + (uint32_t)i * 128u + ((cj ^ (uint32_t)(i & 7)) << 4));
-              if (!((vmask >> i) & 1u)) u = 0u;
-              const float2 f = make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
-              s2 = __fadd2_rn(s2, f);
-              q2 = __ffma2_rn(f, f, q2);
+              for (int i = 0; i < 32; ++i) {
+                uint32_t u = lds32(sb + (uint32_t)i * 128u + ((cj ^ (uint32_t)(i & 7)) << 4));
+                if (!((vmask >> i) & 1u)) u = 0u;
+                const float2 f = make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+                s2 = __fadd2_rn(s2, f);
+                q2 = __ffma2_rn(f, f, q2);
+              }
+            } else {
+              // {sum du, sum du*x}: du as stored from the slab, the x pair of the same pixel from global memory (the slab
+              // the TMA just fetched: an L2 hit; its shared-memory copy was overwritten by du)
+              const bool in1 = co0 >= p.gnb_c0;
+              const int ldx = in1 ? p.gnb_ld1 : p.gnb_ld0;
+              const __nv_bfloat16* xg = (in1 ? p.gnb_x1 + (co0 - p.gnb_c0) : p.gnb_x0 + co0) + 2 * lane;
+#pragma unroll 8
+              for (int i = 0; i < 32; ++i) {
+                uint32_t u = lds32(sb + (uint32_t)i * 128u + ((cj ^ (uint32_t)(i & 7)) << 4));
+                uint32_t xu = 0u;
+                if ((vmask >> i) & 1u) {
+                  const int rr = q * 32 + i;
+                  const int bw = rr & (p.BW - 1), t = rr >> p.lgBW, bh = t & (p.BH - 1), bn = t >> p.lgBH;
+                  const size_t pix = ((size_t)(nn0 + bn) * p.OH + (h0 + bh)) * p.OW + (w0 + bw);
+                  xu = __ldg(reinterpret_cast<const uint32_t*>(xg + pix * ldx));
+                } else {
+                  u = 0u;
+                }
+                const float2 f = make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+                const float2 xf = make_float2(__uint_as_float(xu << 16), __uint_as_float(xu & 0xffff0000u));
+                s2 = __fadd2_rn(s2, f);
+                q2 = __ffma2_rn(f, xf, q2);
+              }
             }
-            float* dst = p.stats + ((size_t)nimg * p.cout + co0 + 2 * lane) * 2;
+            float* dst = (gnb ? p.gnb_ws : p.stats) + ((size_t)nimg * p.cout + co0 + 2 * lane) * 2;
             atomicAdd(reinterpret_cast<float4*>(dst), make_float4(s2.x, q2.x, s2.y, q2.y));
           }
           ++sidx;
@@ -259,29 +319,48 @@ __device__ __forceinline__ void igemm_stage_manager(const IgemmKParams& p, const
   const int total_tiles = cx.total_tiles, boxes_per_img = cx.boxes_per_img;
   auto sready_bar = [&](int b) { return cx.sready0 + 8u * b; };
   auto sfree_bar = [&](int b) { return cx.sfree0 + 8u * b; };
-  if (lane == 0 && p.out_mode == 0) {
-    int sidx = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int tm = tile / p.ntn, n0 = (tile % p.ntn) * BN;
-      for (int m = 0; m < MT; ++m) {
-        const int box = tm * MT + m;
-        if (box >= p.nboxes) break;
-        const int w0 = (box % p.tilesW) * p.BW, h0 = ((box / p.tilesW) % p.tilesH) * p.BH;
-        const int nn0 = (box / boxes_per_img) * p.BNI;
-        for (int c = 0; c < BN; c += SLABW) {
-          const int co0 = n0 + c;
-          if (co0 >= p.cout) break;
-          const int buf = sidx % NS;
-          const uint32_t sph = (sidx / NS) & 1;
-          mbar_wait(sfree_bar(buf), sph ^ 1);
-          if (p.has_resid) {
-            mbar_expect_tx(sready_bar(buf), kSlabBytes);
-            tma_load_4d(stg_base + buf * kSlabStride, &p.tmR, sready_bar(buf), co0, w0, h0, nn0);
-          } else {
-            mbar_arrive(sready_bar(buf));
+  if (p.out_mode != 0) return;
+  const bool gnb = SLABW == 64 && p.gnb_ws != nullptr;
+  if (!gnb && lane != 0) return;           // only the GroupNorm-backward fusion has work for the other 31 lanes
+  int sidx = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int tm = tile / p.ntn, n0 = (tile % p.ntn) * BN;
+    for (int m = 0; m < MT; ++m) {
+      const int box = tm * MT + m;
+      if (box >= p.nboxes) break;
+      const int w0 = (box % p.tilesW) * p.BW, h0 = ((box / p.tilesW) % p.tilesH) * p.BH;
+      const int nn0 = (box / boxes_per_img) * p.BNI;
+      for (int c = 0; c < BN; c += SLABW) {
+        const int co0 = n0 + c;
+        if (co0 >= p.cout) break;
+        const int buf = sidx % NS;
+        const uint32_t sph = (sidx / NS) & 1;
+        mbar_wait(sfree_bar(buf), sph ^ 1);
+        if (gnb) {
+          // forward constants {a, b} of the slab's 64 channels, for every image of the box: 512 B per image, one 128-bit
+          // load per lane; visible to the epilogue through the release of lane 0's arrive below
+          if (p.gnb_silu) {
+            for (int bi = 0; bi < p.BNI && bi < cx.abi; ++bi) {
+              if (nn0 + bi < p.Nimg) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(p.gnb_ab + ((size_t)(nn0 + bi) * p.cout + co0) * 2) + lane);
+                sts128f(cx.abs_base + (uint32_t)(buf * cx.abi + bi) * 512u + (uint32_t)lane * 16u, v);
+              }
+            }
           }
-          ++sidx;
+          __syncwarp();
+          if (lane == 0) {
+            const bool in1 = co0 >= p.gnb_c0;
+            mbar_expect_tx(sready_bar(buf), kSlabBytes);
+            tma_load_4d(stg_base + buf * kSlabStride, in1 ? &p.tmR2 : &p.tmR, sready_bar(buf), in1 ? co0 - p.gnb_c0 : co0, w0, h0,
+                        nn0);
+          }
+        } else if (p.has_resid) {
+          mbar_expect_tx(sready_bar(buf), kSlabBytes);
+          tma_load_4d(stg_base + buf * kSlabStride, &p.tmR, sready_bar(buf), co0, w0, h0, nn0);
+        } else {
+          mbar_arrive(sready_bar(buf));
         }
+        ++sidx;
       }
     }
   }
@@ -316,6 +395,8 @@ __global__ void __launch_bounds__(224, 1) igemm2_kernel(const __grid_constant__ 
   uint64_t* bars = reinterpret_cast<uint64_t*>(stg + NS * kSlabStride);
   // bars: [0,S) full | [S,2S) empty | [2S,2S+2) tmem_full | [2S+2,2S+4) tmem_empty | NS sready | NS sfree
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + 2 * NS);
+  constexpr int kABI = 4;                                     // images per 128-pixel box (>= 32 pixels each)
+  const uint32_t abs_base = (smem_u32(tmem_slot) + 16 + 15) & ~15u;      // [NS][kABI] x 512 B, GroupNorm-backward fusion
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t stg_base = smem_u32(stg);
@@ -342,7 +423,8 @@ __global__ void __launch_bounds__(224, 1) igemm2_kernel(const __grid_constant__ 
   const int tiles_m = (p.nboxes + MT - 1) / MT;
   const int total_tiles = tiles_m * p.ntn;
   const int boxes_per_img = p.tilesW * p.tilesH;
-  const EpiCtx cx{tmem_base, stg_base, tfull_bar(0), tempty_bar(0), sready_bar(0), sfree_bar(0), total_tiles, boxes_per_img};
+  const EpiCtx cx{tmem_base, stg_base, tfull_bar(0), tempty_bar(0), sready_bar(0), sfree_bar(0), total_tiles, boxes_per_img,
+                  abs_base, kABI};
 
   if (warp == 0) {
     if (lane == 0) {
@@ -414,7 +496,7 @@ __global__ void __launch_bounds__(224, 1) igemm2_kernel(const __grid_constant__ 
 
 template <int BN, int MT, int STAGES, int NS>
 static int launch_igemm2(const IgemmKParams& kp, cudaStream_t st) {
-  constexpr int smem = STAGES * (MT * kATileBytes + BN * 128) + NS * 128 * 128 + 1024 + 256;
+  constexpr int smem = STAGES * (MT * kATileBytes + BN * 128) + NS * 128 * 128 + 1024 + 256 + NS * 4 * 512 + 32;
   static_assert(smem <= 227 * 1024, "igemm2: shared memory budget");
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -465,6 +547,8 @@ __global__ void __launch_bounds__(256, 1) igemm3_kernel(const __grid_constant__ 
   uint64_t* bars = reinterpret_cast<uint64_t*>(stg + NS * kSlabStride);
   // bars: afull[AST] aempty[AST] bfull[BST] bempty[BST] tfull[2] tempty[2] sready[NS] sfree[NS]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * AST + 2 * BST + 4 + 2 * NS);
+  constexpr int kABI = 1;                                     // the halo box is 8 x 16 pixels of ONE image
+  const uint32_t abs_base = (smem_u32(tmem_slot) + 16 + 15) & ~15u;      // [NS][1] x 512 B, GroupNorm-backward fusion
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t a_base = smem_u32(smem), b_base = smem_u32(bsm), stg_base = smem_u32(stg);
   const uint32_t bar_base = smem_u32(bars);
@@ -493,7 +577,8 @@ __global__ void __launch_bounds__(256, 1) igemm3_kernel(const __grid_constant__ 
   const int tiles_m = (p.nboxes + MT - 1) / MT;
   const int total_tiles = tiles_m * p.ntn;
   const int boxes_per_img = p.tilesW * p.tilesH;
-  const EpiCtx cx{tmem_base, stg_base, tfull_bar(0), tempty_bar(0), sready_bar(0), sfree_bar(0), total_tiles, boxes_per_img};
+  const EpiCtx cx{tmem_base, stg_base, tfull_bar(0), tempty_bar(0), sready_bar(0), sfree_bar(0), total_tiles, boxes_per_img,
+                  abs_base, kABI};
 
   if (warp == 0) {
     if (lane == 0) {
@@ -596,7 +681,7 @@ __global__ void __launch_bounds__(256, 1) igemm3_kernel(const __grid_constant__ 
 
 template <int BN, int MT, int AST, int BST, int NS>
 static int launch_igemm3(const IgemmKParams& kp, cudaStream_t st) {
-  constexpr int smem = AST * MT * kHaloStride + BST * BN * 128 + NS * 128 * 128 + 1024 + 512;
+  constexpr int smem = AST * MT * kHaloStride + BST * BN * 128 + NS * 128 * 128 + 1024 + 512 + NS * 512 + 32;
   static_assert(smem <= 227 * 1024, "igemm3: shared memory budget");
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -688,6 +773,20 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
   kp.OH = d->OH; kp.OW = d->OW; kp.cout = d->cout; kp.out_mode = d->out_mode;
   kp.out = d->out; kp.bias = d->bias; kp.bias2 = d->bias2; kp.has_resid = d->resid != nullptr;
   kp.stats = d->stats;
+  if (d->gnb_ws) {
+    CDAE_CHECK_ARG(d->gnb_x0 && (!d->gnb_silu || d->gnb_ab), "igemm: GroupNorm-backward fusion needs x0 (and the constant table with SiLU)");
+    CDAE_CHECK_SHAPE(kp.out_mode == 0 && !d->resid && !d->stats && !d->bias && d->cout % 64 == 0 && kp.BW * kp.BH >= 32 &&
+                         d->gnb_c0 % 64 == 0 && d->gnb_c0 > 0 && d->gnb_c0 <= d->cout && (d->gnb_c0 == d->cout || d->gnb_x1) &&
+                         d->gnb_ld0 % 8 == 0 && (!d->gnb_x1 || d->gnb_ld1 % 8 == 0) &&
+                         (reinterpret_cast<uintptr_t>(d->gnb_ws) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->gnb_ab) & 15) == 0,
+                     "igemm: GroupNorm-backward fusion needs a plain NHWC data-gradient launch (no bias / residual / statistics), "
+                     "cout %% 64 == 0, 64-channel aligned sources and >= 32 output pixels per image");
+    kp.gnb_ws = d->gnb_ws; kp.gnb_ab = d->gnb_ab; kp.gnb_silu = d->gnb_silu;
+    kp.gnb_x0 = reinterpret_cast<const __nv_bfloat16*>(d->gnb_x0); kp.gnb_x1 = reinterpret_cast<const __nv_bfloat16*>(d->gnb_x1);
+    kp.gnb_c0 = d->gnb_c0; kp.gnb_ld0 = d->gnb_ld0; kp.gnb_ld1 = d->gnb_ld1;
+    for (kp.lgBW = 0; (1 << kp.lgBW) < kp.BW; ++kp.lgBW) {}
+    for (kp.lgBH = 0; (1 << kp.lgBH) < kp.BH; ++kp.lgBH) {}
+  }
   CDAE_CHECK_SHAPE(!d->stats || (kp.out_mode == 0 && d->cout % 64 == 0 && kp.BW * kp.BH >= 32 &&
                                  (reinterpret_cast<uintptr_t>(d->stats) & 15) == 0),
                    "igemm: channel statistics need NHWC output, cout %% 64 == 0 and >= 32 output pixels per image");
@@ -715,7 +814,7 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
     else if (c >= 192 && c % 192 == 0 && (int64_t)nboxes * (c / 192) >= kNumSMs) bn = 192;
     else bn = c >= 128 ? 128 : c >= 64 ? 64 : c > 16 ? 32 : 16;
   }
-  CDAE_CHECK_SHAPE(!d->stats || bn >= 64, "igemm: channel statistics need an N tile of at least 64 (bn %d)", bn);
+  CDAE_CHECK_SHAPE(!(d->stats || d->gnb_ws) || bn >= 64, "igemm: channel statistics need an N tile of at least 64 (bn %d)", bn);
   const int ntn = (d->cout + bn - 1) / bn;
   if (bn <= 128 && (int64_t)((nboxes + 1) / 2) * ntn >= kNumSMs) mt = 2;
   {
@@ -741,6 +840,16 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
       uint64_t str[3] = {L * 2, L * 2 * d->OW, L * 2 * (uint64_t)d->OW * d->OH};
       int rc = make_tmap_bf16(&kp.tmR, d->resid, 4, dims, str, box, nullptr, slabw == 64);
       if (rc) return rc;
+    }
+    if (d->gnb_ws) {      // x slabs of the GroupNorm input arrive over the residual path: one map per concatenated source
+      for (int si = 0; si < (d->gnb_x1 ? 2 : 1); ++si) {
+        const uint64_t L = si ? d->gnb_ld1 : d->gnb_ld0;
+        const uint64_t Cs = si ? (uint64_t)(d->cout - d->gnb_c0) : (uint64_t)d->gnb_c0;
+        uint64_t dims[4] = {Cs, (uint64_t)d->OW, (uint64_t)d->OH, (uint64_t)d->N};
+        uint64_t str[3] = {L * 2, L * 2 * d->OW, L * 2 * (uint64_t)d->OW * d->OH};
+        int rc = make_tmap_bf16(si ? &kp.tmR2 : &kp.tmR, si ? d->gnb_x1 : d->gnb_x0, 4, dims, str, box, nullptr, slabw == 64);
+        if (rc) return rc;
+      }
     }
   }
   int nkb = 0;

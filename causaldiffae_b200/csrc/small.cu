@@ -253,8 +253,8 @@ __global__ void __launch_bounds__(kDagThreads) dag_bwd_kernel(const float* __res
 
 // du[b,j,:] = dzpost[b,j,:] + sum_i A[j,i] dzp[b,i,:] ; dzp is cleared for the next call
 __global__ void __launch_bounds__(kDagThreads) dag_bwd_finish_kernel(const float* __restrict__ A, const float* __restrict__ dzpost,
-                                                                     float* __restrict__ dzp, float* __restrict__ du, int B,
-                                                                     int n, int d) {
+                                                                     float* __restrict__ dzp, float* __restrict__ du,
+                                                                     const float* __restrict__ du_add, int B, int n, int d) {
   const int64_t total = (int64_t)B * d;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = idx / d;
@@ -264,6 +264,7 @@ __global__ void __launch_bounds__(kDagThreads) dag_bwd_finish_kernel(const float
     for (int j = 0; j < n; ++j) {
       const size_t o = ((size_t)b * n + j) * d + k;
       float v = du ? dzpost[o] : 0.f;
+      if (du_add) v += du_add[o];
       for (int i = 0; i < n; ++i) v = fmaf(__ldg(A + j * n + i), z[i], v);
       if (du) du[o] = v;
     }
@@ -298,7 +299,8 @@ extern "C" int cdae_dag_fwd(const float* u, const float* A, const void* const* p
 }
 
 extern "C" int cdae_dag_bwd(const float* u, const float* A, const void* const* params, const float* dzpost,
-                            void* const* grads, float* dzp_ws, float* du, int B, int n, int d, int D, cdae_stream s) {
+                            void* const* grads, float* dzp_ws, float* du, const float* du_add, int B, int n, int d, int D,
+                            cdae_stream s) {
   if (B == 0) return CDAE_OK;
   CDAE_CHECK_ARG(u && A && params && dzpost && grads && dzp_ws, "dag_bwd: null pointer");
   CDAE_CHECK_SHAPE(n >= 1 && n <= 8 && D % kDagHT == 0, "dag_bwd: n=%d D=%d unsupported", n, D);
@@ -316,7 +318,7 @@ extern "C" int cdae_dag_bwd(const float* u, const float* A, const void* const* p
   const int64_t total = (int64_t)B * d;
   int blocks = (int)((total + kDagThreads - 1) / kDagThreads);
   if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
-  dag_bwd_finish_kernel<<<blocks, kDagThreads, 0, st>>>(A, dzpost, dzp_ws, du, B, n, d);
+  dag_bwd_finish_kernel<<<blocks, kDagThreads, 0, st>>>(A, dzpost, dzp_ws, du, du_add, B, n, d);
   CDAE_CHECK_LAUNCH("dag_bwd_finish_kernel");
   return CDAE_OK;
 }

@@ -27,11 +27,11 @@ bf16 = th.bfloat16
 USE_GRAPHS = os.environ.get("CDAE_GRAPHS", "1") != "0"
 # GroupNorm statistics from the producing conv's epilogue + one streaming normalise pass (0: reduce inside the GN kernel)
 FUSED_GN_STATS = os.environ.get("CDAE_FUSED_GN_STATS", "1") != "0"
-# GroupNorm backward as two streaming passes (reduce, then apply in reverse order) instead of the resident cluster kernel.
-# Measured on B200 (profiles/r1_gn_bench_bwd_stream.log): SLOWER - 96 vs 80 us on the 128-channel 64x64 layer, 3123 vs
-# 3229 img/s for the whole step - the second read of dy / x does not hit L2 for the big layers and the two launches cost
-# more than the cluster barriers they avoid.  Kept as an opt-in (tests cover both), off by default.
-GN_BWD_STREAM = os.environ.get("CDAE_GN_BWD_STREAM", "0") != "0"
+# GroupNorm backward statistics from the epilogue of the data-gradient conv that produces the norm's output gradient + one
+# streaming apply pass (0: the resident cluster kernel reduces and applies in one launch).  Round 1 measured a two-pass
+# streaming backward that re-read dy and x (profiles/r1_gn_bench_bwd_stream.log): slower than the resident kernel; this is
+# the version without the second read.
+FUSED_GN_BWD = os.environ.get("CDAE_FUSED_GN_BWD", "1") != "0"
 
 
 def _round_up(v, m):
@@ -60,6 +60,7 @@ class T:
         self.g = None
         self.g_written = False
         self.stats = None       # fp32 [B, C, 2] channel sums written by the producing conv's epilogue (GroupNorm input)
+        self.gnb = None         # set on a GroupNorm OUTPUT: dict(x0, x1, ab, ws, silu) for the fused backward statistics
 
     def grad(self):
         if self.g is None:
@@ -109,15 +110,12 @@ class Plan:
             ops.zero_(c)
 
     def alloc_bwd_ws(self, B, C):
-        """zeroed-at-backward-start fp32 [B, 2, C] workspace of one streaming GroupNorm backward (None: resident kernel)"""
-        if not GN_BWD_STREAM:
-            return None
+        """zeroed-at-backward-start fp32 [B, C, 2] {sum du, sum du*x} accumulator of one fused GroupNorm backward"""
         n = B * C * 2
         if not self.bws_chunks or self._bws_used + n > self.bws_chunks[-1].numel():
             self.bws_chunks.append(th.zeros(max(n, 1 << 21), device=self.dev, dtype=th.float32))
             self._bws_used = 0
-        self.n_bwd_launch += 1                   # the streaming backward is two kernels
-        v = self.bws_chunks[-1][self._bws_used:self._bws_used + n].view(B, 2, C)
+        v = self.bws_chunks[-1][self._bws_used:self._bws_used + n].view(B, C, 2)
         self._bws_used += (n + 3) // 4 * 4
         return v
 
@@ -421,7 +419,9 @@ class Engine:
         return chans
 
     def plan_conv_bwd(self, pl, cw, srcs, dy, ksize, stride=1, need_dgrad=True):
-        """gradients of out = conv(concat(srcs)): bias, weight, and data (into srcs[i].grad()). dy: bf16 NHWC tensor."""
+        """gradients of out = conv(concat(srcs)): bias, weight, and data (into srcs[i].grad()). dy: bf16 NHWC tensor.
+        A single source that is the output of a streaming GroupNorm (srcs[0].gnb) gets du = dy_src * silu'(u) instead of
+        its plain gradient, plus the backward statistics of that norm, from the data-gradient epilogue."""
         fns = []
         gb, gw = self._gparam(cw.bias), self._gparam(cw.param)
         # the bias gradient (column sums of dy) rides along in the weight-gradient kernel of the first source
@@ -456,7 +456,10 @@ class Engine:
             for s in srcs:
                 c = s.shape[3]
                 acc, g = s.grad_acc(), s.grad()
-                d = ops.make_igemm_desc([dyz], segs, cw.tr[off:off + c], g, c, resid=g if acc else None)
+                gnb = s.gnb if (len(srcs) == 1 and not acc and stride == 1) else None
+                if s.gnb is not None and gnb is None:
+                    s.gnb = None                     # this gradient is a plain dy: the norm's backward must reduce itself
+                d = ops.make_igemm_desc([dyz], segs, cw.tr[off:off + c], g, c, resid=g if acc else None, gnb=gnb)
                 fns.append(lambda d=d: ops.igemm(d))
                 off += c
         return fns
@@ -467,11 +470,30 @@ class Engine:
         x1t = x1.t if x1 is not None else None
         if x0.stats is not None and (x1 is None or x1.stats is not None):
             s1 = x1.stats if x1 is not None else None
+            ab = None
+            Ct = out.shape[3]
+            if pl.train and FUSED_GN_BWD and Ct % 64 == 0 and x0.shape[3] % 64 == 0 and out.shape[1] * out.shape[2] >= 32:
+                # the data-gradient conv that will produce d(out) also produces this norm's backward statistics
+                ab = pl.alloc((out.shape[0], Ct, 2), th.float32) if silu else None
+                out.gnb = dict(x0=x0.t, x1=x1t, ab=ab, ws=pl.alloc_bwd_ws(out.shape[0], Ct), silu=silu)
             pl.add_fwd(lambda: ops.gn_apply_fwd(x0.t, x0.stats, gn.weight, gn.bias, x1=x1t, stats1=s1, film=film,
-                                                film_off=film_off, silu=silu, out=out.t, mean=st[0], rstd=st[1]))
+                                                film_off=film_off, silu=silu, out=out.t, mean=st[0], rstd=st[1], ab=ab))
         else:
             pl.add_fwd(lambda: ops.gn_fwd(x0.t, gn.weight, gn.bias, x1=x1t, film=film, film_off=film_off, silu=silu,
                                           out=out.t, mean=st[0], rstd=st[1]))
+
+    def plan_gn_bwd(self, a, x0, x1, gn, st, dx0, dx1=None, accmask=0, film=None, film_off=0, silu=True, dfilm=None, dadd=None):
+        """backward of a = [SiLU](FiLM(GroupNorm32(concat(x0, x1)))): one streaming pass when the conv that produced d(a) left
+        du and the statistics behind (a.gnb, see plan_conv_bwd), else the resident reduce-and-apply kernel."""
+        da = a.grad()
+        gw, gb = self._gparam(gn.weight), self._gparam(gn.bias)
+        x1t = x1.t if x1 is not None else None
+        if a.gnb is not None:
+            ws = a.gnb["ws"]
+            return lambda: ops.gn_bwd_apply(da, x0.t, gn.weight, gn.bias, st[0], st[1], ws, x1=x1t, film=film, film_off=film_off,
+                                            dx0=dx0, dx1=dx1, accumulate_dx=accmask, dgamma=gw, dbeta=gb, dfilm=dfilm, dadd=dadd)
+        return lambda: ops.gn_bwd(da, x0.t, gn.weight, gn.bias, st[0], st[1], x1=x1t, film=film, film_off=film_off, silu=silu,
+                                  dx0=dx0, dx1=dx1, accumulate_dx=accmask, dgamma=gw, dbeta=gb, dfilm=dfilm, dadd=dadd)
 
     # ------------------------------------------------------------------ layer planners
     def plan_resblock(self, pl, rb, x0, x1, film, dfilm):
@@ -515,27 +537,19 @@ class Engine:
                         fns.append(lambda d=d: ops.igemm(d))
                         off += c
                 # GN2 (+FiLM) backward -> dh1
-                ggn2w, ggn2b = self._gparam(gn2.weight), self._gparam(gn2.bias)
-                da2, dh1 = a2.grad(), h1.grad()
-                ws2 = pl.alloc_bwd_ws(B, cout)
-                fns.append(lambda: ops.gn_bwd(da2, h1.t, gn2.weight, gn2.bias, st2[0], st2[1], film=film, film_off=foff,
-                                              silu=True, dx0=dh1, dgamma=ggn2w, dbeta=ggn2b, dfilm=dfilm, ws=ws2))
+                dh1 = h1.grad()
+                fns.append(self.plan_gn_bwd(a2, h1, None, gn2, st2, dh1, film=film, film_off=foff, dfilm=dfilm))
                 h1.g_written = True
                 # conv1
                 fns += self.plan_conv_bwd(pl, cw1, [a1], dh1, 3)
                 # GN1 backward -> dx (+ identity-skip gradient)
-                ggn1w, ggn1b = self._gparam(gn1.weight), self._gparam(gn1.bias)
-                da1 = a1.grad()
                 acc0 = x0.grad_acc()
                 acc1 = x1.grad_acc() if x1 is not None else False
                 dx0 = x0.grad()
                 dx1 = x1.grad() if x1 is not None else None
                 accmask = (1 if acc0 else 0) | (2 if acc1 else 0)
                 dadd = None if has_skip else dout
-                ws1 = pl.alloc_bwd_ws(B, cin)
-                fns.append(lambda: ops.gn_bwd(da1, x0.t, gn1.weight, gn1.bias, st1[0], st1[1], x1=x1t, silu=True,
-                                              dx0=dx0, dx1=dx1, accumulate_dx=accmask, dgamma=ggn1w, dbeta=ggn1b,
-                                              dadd=dadd, ws=ws1))
+                fns.append(self.plan_gn_bwd(a1, x0, x1, gn1, st1, dx0, dx1, accmask, dadd=dadd))
                 return fns
             pl.bwd_builders.append(build_bwd)
         return out
@@ -565,13 +579,9 @@ class Engine:
                                                 dsum=dsum))
                 qkv.g_written = True
                 fns += self.plan_conv_bwd(pl, cwq, [n], dqkv, 1)
-                gw, gb = self._gparam(ab.norm.weight), self._gparam(ab.norm.bias)
-                dn = n.grad()
                 acc = x.grad_acc()
                 dx = x.grad()
-                wsn = pl.alloc_bwd_ws(B, Cc)
-                fns.append(lambda: ops.gn_bwd(dn, x.t, ab.norm.weight, ab.norm.bias, st[0], st[1], silu=False, dx0=dx,
-                                              accumulate_dx=1 if acc else 0, dgamma=gw, dbeta=gb, dadd=dout, ws=wsn))
+                fns.append(self.plan_gn_bwd(n, x, None, ab.norm, st, dx, accmask=1 if acc else 0, silu=False, dadd=dout))
                 return fns
             pl.bwd_builders.append(build_bwd)
         return out
@@ -659,12 +669,8 @@ class Engine:
             def build_out_bwd():
                 fns = [lambda: ops.nchw_to_nhwc_pad(pl.deps_in, 64, out=dyo)]
                 fns += self.plan_conv_bwd(pl, cwo, [a], dyo, 3)
-                gw, gb = self._gparam(gno.weight), self._gparam(gno.bias)
-                da = a.grad()
                 acc, dx = hfin.grad_acc(), hfin.grad()
-                wso = pl.alloc_bwd_ws(B, hfin.shape[3])
-                fns.append(lambda: ops.gn_bwd(da, hfin.t, gno.weight, gno.bias, sto[0], sto[1], silu=True, dx0=dx,
-                                              accumulate_dx=1 if acc else 0, dgamma=gw, dbeta=gb, ws=wso))
+                fns.append(self.plan_gn_bwd(a, hfin, None, gno, sto, dx, accmask=1 if acc else 0))
                 return fns
             pl.bwd_builders.append(build_out_bwd)
             # backward ops are built in REVERSE layer order so that "first producer writes, later ones accumulate"
@@ -699,13 +705,23 @@ class Engine:
 
     # ------------------------------------------------------------------ public entry: the torso as one autograd node
     def film(self, emb):
-        """all 22 emb_layers(SiLU(emb)) as one GEMM (ref unet.py:148-154,186) -> [B, sum 2*Cout] fp32"""
-        return F.linear(F.silu(emb.float()), self.film_w, self.film_b)
+        """all 22 emb_layers(SiLU(emb)) as one GEMM (ref unet.py:148-154,186) -> [B, sum 2*Cout] fp32 (no gradient:
+        standalone layer calls; the model path goes through rep.TrunkRunner)"""
+        e = emb.detach().float().contiguous()
+        out = th.empty(e.shape[0], self.film_width, device=e.device, dtype=th.float32)
+        return ops.linear_fwd(e, self.film_w, self.film_b, out, silu_in=True)
 
-    def torso(self, x, emb):
+    @property
+    def trunk(self):
+        from .rep import TrunkRunner
+        if getattr(self, "_trunk", None) is None:
+            self._trunk = TrunkRunner(self.model)
+        return self._trunk
+
+    def torso_film(self, x, film):
+        """eps = torso(x | FiLM vectors of all ResBlocks): ONE autograd node, forward / backward = CUDA-graph replays"""
         if not self.owns(next(self.model.parameters())):
             raise _lib.CdaeError("model parameters were re-homed after the engine was built; access model.engine again")
-        film = self.film(emb)
         train = th.is_grad_enabled() and film.requires_grad
         return _Torso.apply(self, x, film, train)
 

@@ -8,7 +8,7 @@ import time
 from collections import defaultdict
 
 _STATE = {"dir": None, "kv": {}, "mean": defaultdict(lambda: [0.0, 0]), "vec": defaultdict(lambda: [0.0, 0.0]),
-          "formats": ["stdout", "log", "csv"], "csv_keys": None}
+          "formats": ["stdout", "log", "csv"], "csv_keys": None, "hooks": {}}
 
 
 def configure(dir=None, format_strs=None, comm=None, log_suffix=""):
@@ -58,6 +58,11 @@ def logkv_mean_n(prefix, sums, counts):
     acc[1] = acc[1] + counts
 
 
+def set_dump_hook(name, fn):
+    """fn() -> {key: float}: values a producer accumulates on the device and only reads when the log is dumped"""
+    _STATE["hooks"][name] = fn
+
+
 def _to_float(v):
     return float(v.item()) if hasattr(v, "item") else float(v)
 
@@ -71,6 +76,8 @@ def getkvs():
         for i, (si, ci) in enumerate(zip(sl, cl)):
             if ci > 0:
                 out[f"{prefix}{i}"] = si / ci
+    for fn in list(_STATE["hooks"].values()):
+        out.update(fn())
     return out
 
 

@@ -164,7 +164,9 @@ def encoder_hidden_dims(image_size, n_vars):
 
 class GaussianConvEncoder(nn.Module):
     """ref nn.py:15-110: [Conv3x3 s2 -> BatchNorm2d -> LeakyReLU] x L -> fc_mu / softplus(fc_var)+1e-8.
-    0.02 % of the model FLOPs; runs on library kernels for now (out of the tensor-core hot path)."""
+    The modules are parameter containers (reference state_dict keys incl. the BatchNorm buffers); `encode` runs the
+    hand-written fp32 kernels of csrc/rep.cu through rep.EncoderRunner (implicit-im2col SGEMM with the previous layer's
+    BatchNorm + LeakyReLU applied on load, batch statistics from the conv epilogue), forward and backward."""
 
     def __init__(self, in_channels, latent_dim, hidden_dims=None, num_vars=4, **kwargs):
         super().__init__()
@@ -180,10 +182,20 @@ class GaussianConvEncoder(nn.Module):
         self.fc_mu = nn.Linear(hidden_dims[-1] * 4, latent_dim)
         self.fc_var = nn.Linear(hidden_dims[-1] * 4, latent_dim)
 
+    @property
+    def runner(self):
+        from .rep import EncoderRunner
+        r = self.__dict__.get("_runner")
+        if r is None:
+            r = self.__dict__["_runner"] = EncoderRunner(self)
+        return r
+
     def encode(self, input):
-        h = th.flatten(self.encoder(input), start_dim=1)
-        mu = self.fc_mu(h)
-        var = F.softplus(self.fc_var(h)) + 1e-8
+        from . import _lib
+        from .rep import _EncodeFn, anchor
+        if not input.is_cuda:
+            raise _lib.CdaeError("GaussianConvEncoder.encode needs CUDA (sm_100a) tensors; there is no CPU path")
+        mu, var = _EncodeFn.apply(self, anchor(input.device), input, th.is_grad_enabled())
         return [mu, var]
 
 

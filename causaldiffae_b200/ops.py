@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import IgemmDesc, WgradDesc, Seg, ptr, stream, check
+from ._lib import IgemmDesc, WgradDesc, SgemmDesc, Seg, ptr, stream, check
 
 bf16 = torch.bfloat16
 
@@ -38,15 +38,15 @@ def q_sample(x0, noise, t, sqrt_ac, sqrt_1mac, out=None):
     return out
 
 
-def mse_loss(pred, target, gscale=None, want_grad=False):
-    """per-sample mean((target-pred)^2) and, optionally, d(sum_b gscale[b]*mse[b])/dpred (ref gaussian_diffusion.py:847)."""
+def mse_loss(pred, target, gscale=None, want_grad=False, gmul=1.0, mse=None, dpred=None):
+    """per-sample mean((target-pred)^2) and, optionally, d(sum_b gmul*gscale[b]*mse[b])/dpred (ref gaussian_diffusion.py:847)."""
     _f32c(pred); _f32c(target)
     B = pred.shape[0]
-    mse = torch.empty(B, device=pred.device, dtype=torch.float32)
-    dpred = torch.empty_like(pred) if want_grad else None
+    mse = torch.empty(B, device=pred.device, dtype=torch.float32) if mse is None else mse
     if want_grad:
+        dpred = torch.empty_like(pred) if dpred is None else dpred
         _f32c(gscale)
-    check(_lib.lib().cdae_mse_loss(ptr(pred), ptr(target), ptr(mse), ptr(gscale), ptr(dpred), B,
+    check(_lib.lib().cdae_mse_loss(ptr(pred), ptr(target), ptr(mse), ptr(gscale), float(gmul), ptr(dpred), B,
                                    pred.numel() // max(B, 1), stream()))
     return mse, dpred
 
@@ -66,13 +66,13 @@ def ddim_step(x, eps_c, coef_table, t_idx, eps_u=None, w=None, noise=None, want_
     return out, x0
 
 
-def adam_ema(p, g, m, v, ema, hyper, step, gsq_out=None, guard=None):
+def adam_ema(p, g, m, v, ema, hyper, step, gsq_out=None, guard=None, lognorm=None):
     """ref train_util.py:276-303 + nn.py:503-513; flat fp32 arenas, hyper = device fp32[7] {lr, b1, b2, eps, wd, ema_rate,
     grad_scale}, step = device int64[1] (incremented by the launch), g fp32 or bf16, guard = device fp32[1] or None."""
     n = p.numel()
     assert step.dtype == torch.int64 and g.numel() == n
     check(_lib.lib().cdae_adam_ema(ptr(p), ptr(g), int(g.dtype == bf16), ptr(m), ptr(v), ptr(ema), ptr(hyper), ptr(step),
-                                   ptr(guard), ptr(gsq_out), n, stream()))
+                                   ptr(guard), ptr(gsq_out), ptr(lognorm), n, stream()))
 
 
 def sumsq(g, out):
@@ -184,7 +184,7 @@ def gn_fwd(x0, gamma, beta, x1=None, film=None, film_off=0, silu=True, out=None,
 
 
 def gn_apply_fwd(x0, stats0, gamma, beta, x1=None, stats1=None, film=None, film_off=0, silu=True, out=None, mean=None,
-                 rstd=None):
+                 rstd=None, ab=None):
     """gn_fwd as ONE streaming pass: the per-(image, channel) sums stats0 [B,C0,2] (stats1 [B,C1,2]) were accumulated by
     the convolutions that produced x0 (x1) (make_igemm_desc(stats=...))."""
     _bf16c(x0); _f32c(stats0)
@@ -202,14 +202,15 @@ def gn_apply_fwd(x0, stats0, gamma, beta, x1=None, stats1=None, film=None, film_
     rstd = torch.empty(B, 32, device=x0.device, dtype=torch.float32) if rstd is None else rstd
     check(_lib.lib().cdae_gn_apply_fwd(ptr(x0), C0, ptr(stats0), ptr(x1), C1, ptr(stats1), B, HW, ptr(gamma), ptr(beta),
                                        ptr(film), film.shape[1] if film is not None else 0, film_off, int(silu), ptr(out),
-                                       ptr(mean), ptr(rstd), stream()))
+                                       ptr(mean), ptr(rstd), ptr(ab), stream()))
     return out, mean, rstd
 
 
 def gn_bwd(dy, x0, gamma, beta, mean, rstd, x1=None, film=None, film_off=0, silu=True, dx0=None, dx1=None,
-           accumulate_dx=0, dgamma=None, dbeta=None, dfilm=None, dadd=None, ws=None):
+           accumulate_dx=0, dgamma=None, dbeta=None, dfilm=None, dadd=None):
     """accumulate_dx: bit0 -> add into dx0, bit1 -> add into dx1 (True == both); dadd: extra bf16 [B,HW,C] gradient.
-    ws: zeroed fp32 [B, 2, C] workspace -> the two-pass streaming kernels (cdae_gn_bwd_stream) instead of the resident one."""
+    The resident cluster kernel: reduces and applies in one launch (layers whose output gradient does not come from a
+    statistics-producing data-gradient convolution; otherwise see gn_bwd_apply)."""
     if accumulate_dx is True:
         accumulate_dx = 3
     _bf16c(dy); _bf16c(x0)
@@ -221,17 +222,32 @@ def gn_bwd(dy, x0, gamma, beta, mean, rstd, x1=None, film=None, film_off=0, silu
         _bf16c(x1); C1 = x1.shape[-1]
         dx1 = torch.empty_like(x1) if dx1 is None else dx1
     dx0 = torch.empty_like(x0) if dx0 is None else dx0
-    if ws is not None:
-        _f32c(ws)
-        assert ws.numel() == B * 2 * (C0 + C1)
-        check(_lib.lib().cdae_gn_bwd_stream(ptr(dy), ptr(x0), C0, ptr(x1), C1, B, HW, ptr(gamma), ptr(beta), ptr(film),
-                                            film.shape[1] if film is not None else 0, film_off, int(silu), ptr(mean),
-                                            ptr(rstd), ptr(dadd), ptr(dx0), ptr(dx1), int(accumulate_dx), ptr(dgamma),
-                                            ptr(dbeta), ptr(dfilm), ptr(ws), stream()))
-        return dx0, dx1
     check(_lib.lib().cdae_gn_bwd(ptr(dy), ptr(x0), C0, ptr(x1), C1, B, HW, ptr(gamma), ptr(beta), ptr(film),
                                  film.shape[1] if film is not None else 0, film_off, int(silu), ptr(mean), ptr(rstd),
                                  ptr(dadd), ptr(dx0), ptr(dx1), int(accumulate_dx), ptr(dgamma), ptr(dbeta), ptr(dfilm), stream()))
+    return dx0, dx1
+
+
+def gn_bwd_apply(du, x0, gamma, beta, mean, rstd, ws, x1=None, film=None, film_off=0, dx0=None, dx1=None, accumulate_dx=0,
+                 dgamma=None, dbeta=None, dfilm=None, dadd=None):
+    """GroupNorm backward as ONE streaming pass: du = dy * silu'(u) and ws [B, C, 2] = {sum du, sum du*x} per (sample, channel)
+    were produced by the epilogue of the data-gradient conv (make_igemm_desc(gnb=...))."""
+    if accumulate_dx is True:
+        accumulate_dx = 3
+    _bf16c(du); _bf16c(x0); _f32c(ws)
+    B = x0.shape[0]
+    C0 = x0.shape[-1]
+    HW = x0[0].numel() // C0 if B else 0
+    C1 = 0
+    if x1 is not None:
+        _bf16c(x1); C1 = x1.shape[-1]
+        dx1 = torch.empty_like(x1) if dx1 is None else dx1
+    dx0 = torch.empty_like(x0) if dx0 is None else dx0
+    assert ws.numel() == B * 2 * (C0 + C1)
+    check(_lib.lib().cdae_gn_bwd_apply(ptr(du), ptr(x0), C0, ptr(x1), C1, B, HW, ptr(gamma), ptr(beta), ptr(film),
+                                       film.shape[1] if film is not None else 0, film_off, ptr(mean), ptr(rstd), ptr(ws),
+                                       ptr(dadd), ptr(dx0), ptr(dx1), int(accumulate_dx), ptr(dgamma), ptr(dbeta), ptr(dfilm),
+                                       stream()))
     return dx0, dx1
 
 
@@ -255,7 +271,7 @@ def conv_segments(chans, ksize=3, transposed=False, wk0=0, src0=0):
 
 
 def make_igemm_desc(srcs, segs, wgt, out, cout, in_stride=1, bias=None, resid=None, out_mode=0, sps=1, ooh=0, oow=0,
-                    bn=0, out_hw=None, bias2=None, stats=None):
+                    bn=0, out_hw=None, bias2=None, stats=None, gnb=None):
     """Fill a cdae_igemm_desc.  srcs: bf16 [N,H,W,C]; wgt: bf16 [rows, K]; out: bf16 NHWC or fp32 NCHW (out_mode 1).
     stats: optional fp32 [N, cout, 2] that the epilogue ACCUMULATES per-(image, channel) sum / sum of squares of the
     stored output into (zero it first) - the GroupNorm statistics of the consumer, see gn_apply_fwd."""
@@ -291,7 +307,16 @@ def make_igemm_desc(srcs, segs, wgt, out, cout, in_stride=1, bias=None, resid=No
         _f32c(stats)
         assert out_mode == 0 and tuple(stats.shape) == (N, cout, 2)
     d.stats = ptr(stats)
-    d._keep = (srcs, wgt, out, bias, bias2, resid, stats)   # keep tensors alive as long as the descriptor
+    if gnb is not None:
+        # GroupNorm-backward fusion of a data-gradient launch: gnb = dict(x0=, x1=None, ab=None, ws=, silu=) - the epilogue
+        # stores du = dy * silu'(u) and accumulates ws [N, cout, 2] += {sum du, sum du*x} (see include/cdae.h)
+        x0, x1, ws, ab = gnb["x0"], gnb.get("x1"), gnb["ws"], gnb.get("ab")
+        _bf16c(x0); _f32c(ws)
+        assert out_mode == 0 and tuple(ws.shape) == (N, cout, 2) and x0.shape[3] + (x1.shape[3] if x1 is not None else 0) == cout
+        d.gnb_ws, d.gnb_ab, d.gnb_x0, d.gnb_x1 = ptr(ws), ptr(ab), ptr(x0), ptr(x1)
+        d.gnb_c0, d.gnb_ld0, d.gnb_ld1 = x0.shape[3], x0.shape[3], (x1.shape[3] if x1 is not None else 0)
+        d.gnb_silu = int(bool(gnb.get("silu", True)))
+    d._keep = (srcs, wgt, out, bias, bias2, resid, stats, gnb)   # keep tensors alive as long as the descriptor
     return d
 
 
@@ -371,20 +396,137 @@ def attn_bwd(qkv, out, dout, lse, heads, dqkv=None, dsum=None):
 
 
 # ------------------------------------------------------------------ causal DAG mask layer
-def dag_fwd(u, A, param_ptrs, n, d, D):
+def dag_fwd(u, A, param_ptrs, n, d, D, out=None):
     """ref nn.py:290-312 in one launch. u fp32 [B, n*d]; A fp32 [n, n]; param_ptrs: device int64 [4n] -> z_post [B, n*d]"""
     _f32c(u); _f32c(A)
     B = u.shape[0]
-    z = torch.empty_like(u)
+    z = torch.empty_like(u) if out is None else out
     check(_lib.lib().cdae_dag_fwd(ptr(u), ptr(A), ptr(param_ptrs), ptr(z), B, n, d, D, stream()))
     return z
 
 
-def dag_bwd(u, A, param_ptrs, dz, grad_ptrs, ws, n, d, D):
-    """-> du; parameter gradients are accumulated through grad_ptrs (device int64 [4n]); ws: zeroed fp32 [B, n*d] scratch"""
+def dag_bwd(u, A, param_ptrs, dz, grad_ptrs, ws, n, d, D, du=None, du_add=None):
+    """-> du (+ du_add); parameter gradients are accumulated through grad_ptrs (device int64 [4n]); ws: zeroed fp32 [B, n*d]"""
     _f32c(u); _f32c(A); _f32c(dz); _f32c(ws)
     B = u.shape[0]
-    du = torch.empty_like(u)
-    check(_lib.lib().cdae_dag_bwd(ptr(u), ptr(A), ptr(param_ptrs), ptr(dz), ptr(grad_ptrs), ptr(ws), ptr(du), B, n, d, D,
-                                  stream()))
+    du = torch.empty_like(u) if du is None else du
+    check(_lib.lib().cdae_dag_bwd(ptr(u), ptr(A), ptr(param_ptrs), ptr(dz), ptr(grad_ptrs), ptr(ws), ptr(du), ptr(du_add), B,
+                                  n, d, D, stream()))
     return du
+
+
+# ------------------------------------------------------------------ fp32 representation path (csrc/rep.cu)
+def sgemm(C_, A, B_, M, N, K, a_st, b_st, c_st, a_mode=0, b_mode=0, c_mode=0, bias=None, act_out=0, colstats=None, splits=0,
+          geo=None):
+    """C[M,N] (=, +=, scatter+=) A[M,K] B[K,N]; *_st = element strides (row, col) of each operand view; geo = (sb, sc, sh, sw,
+    Cin, H, W, OH, OW, ab) for the im2col modes (see include/cdae.h)."""
+    d = SgemmDesc()
+    d.A, d.a_sm, d.a_sk, d.a_mode = A.data_ptr(), a_st[0], a_st[1], a_mode
+    d.B, d.b_sk, d.b_sn, d.b_mode = B_.data_ptr(), b_st[0], b_st[1], b_mode
+    d.C, d.c_sm, d.c_sn, d.c_mode = C_.data_ptr(), c_st[0], c_st[1], c_mode
+    d.bias, d.act_out, d.colstats = ptr(bias), act_out, ptr(colstats)
+    d.M, d.N, d.K, d.splits = M, N, K, splits
+    if geo is not None:
+        d.g_sb, d.g_sc, d.g_sh, d.g_sw, d.g_cin, d.g_h, d.g_w, d.g_oh, d.g_ow = geo[:9]
+        d.g_ab = ptr(geo[9])
+    check(_lib.lib().cdae_sgemm(C.byref(d), stream()))
+
+
+_ONE = {}
+
+
+def _one(device):
+    t = _ONE.get(str(device))
+    if t is None:
+        t = _ONE[str(device)] = torch.ones(4, device=device)
+    return t
+
+
+def linear_fwd(x, W, b, out, silu_in=False, accumulate=False, act_out=0):
+    """out (=|+=) f(x) W^T + b  (nn.Linear; f = SiLU when silu_in).  x [B,K], W [N,K], out [B,N] contiguous fp32."""
+    Bn, K = x.shape
+    N = W.shape[0]
+    sgemm(out, x, W, Bn, N, K, (K, 1), (1, K), (N, 1), a_mode=1 if silu_in else 0, c_mode=1 if accumulate else 0, bias=b,
+          act_out=act_out, splits=1)
+    return out
+
+
+def linear_bwd(x, W, dy, dW, db, dx=None, silu_in=False, dx_accumulate=False):
+    """gradients of y = f(x) W^T + b: dW += dy^T f(x), db += colsum(dy) (straight into the flat gradient arena views),
+    dx (=|+=) dy W - the caller applies f' (silu_bwd) when silu_in."""
+    Bn, K = x.shape
+    N = W.shape[0]
+    if dW is not None:
+        sgemm(dW, dy, x, N, K, Bn, (1, N), (K, 1), (K, 1), b_mode=1 if silu_in else 0, c_mode=1)
+    if db is not None:
+        sgemm(db, _one(x.device), dy, 1, N, Bn, (0, 0), (N, 1), (N, 1), c_mode=1)
+    if dx is not None:
+        if not dx_accumulate:
+            zero_(dx)
+        sgemm(dx, dy, W, Bn, K, N, (N, 1), (K, 1), (K, 1), c_mode=1)
+    return dx
+
+
+def timestep_embedding(t, freqs, out, tmap=None, scale=0.0):
+    dim = out.shape[1]
+    assert t.is_cuda and t.dtype in (torch.int64, torch.float32) and t.is_contiguous()
+    check(_lib.lib().cdae_timestep_embedding(ptr(t), int(t.dtype == torch.float32), ptr(tmap), float(scale), ptr(freqs),
+                                             ptr(out), t.shape[0], dim, stream()))
+    return out
+
+
+def randn_(out, state, bernoulli=False, keep_prob=0.5):
+    """fill `out` (fp32) with N(0,1) draws, or Bernoulli(keep_prob) 0/1; state: device int64[2] {seed, offset}"""
+    check(_lib.lib().cdae_randn(ptr(_f32c(out)), out.numel(), ptr(state), int(bernoulli), float(keep_prob), stream()))
+    return out
+
+
+def silu_bwd_(g, x):
+    check(_lib.lib().cdae_silu_bwd(ptr(_f32c(g)), ptr(_f32c(x)), g.numel(), stream()))
+    return g
+
+
+def softplus_bwd_(g, var):
+    check(_lib.lib().cdae_softplus_bwd(ptr(_f32c(g)), ptr(_f32c(var)), g.numel(), stream()))
+    return g
+
+
+def embed_rows_(x, table, idx, backward=False, dtable=None):
+    check(_lib.lib().cdae_embed_rows(ptr(_f32c(x)), ptr(table), ptr(idx), x.shape[0], x.shape[1], int(backward), ptr(dtable),
+                                     stream()))
+    return x
+
+
+def bn_finalize(stats, count, bn, train, ab, ms):
+    check(_lib.lib().cdae_bn_finalize(ptr(stats), float(count), ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean),
+                                      ptr(bn.running_var), ptr(bn.num_batches_tracked), int(train), ptr(ab), ptr(ms),
+                                      bn.weight.shape[0], stream()))
+
+
+def enc_head(src, ab, out, B, P, Cc, backward=False):
+    check(_lib.lib().cdae_enc_head(ptr(src), ptr(ab), ptr(out), B, P, Cc, int(backward), stream()))
+    return out
+
+
+def bn_lrelu_bwd_(dact, raw, ab, ms, gamma, sums, dgamma, dbeta, M, Cc):
+    check(_lib.lib().cdae_bn_lrelu_bwd(ptr(dact), ptr(raw), ptr(ab), ptr(ms), ptr(gamma), ptr(sums), ptr(dgamma), ptr(dbeta),
+                                       M, Cc, stream()))
+    return dact
+
+
+def latent_fwd(mu, var, zp, xi, keep, c, z, zp_out, kld, n, causal, var_scale):
+    B, D = mu.shape
+    check(_lib.lib().cdae_latent_fwd(ptr(mu), ptr(var), ptr(zp), ptr(xi), ptr(keep), ptr(c), ptr(z), ptr(zp_out), ptr(kld),
+                                     B, D, n, int(causal), float(var_scale), stream()))
+
+
+def latent_bwd(mu, var, zp, xi, keep, c, dz, dkld, dzp_ext, dmu_ext, dvar_ext, dzp, dmu, dvar, n, causal, var_scale):
+    B, D = mu.shape
+    check(_lib.lib().cdae_latent_bwd(ptr(mu), ptr(var), ptr(zp), ptr(xi), ptr(keep), ptr(c), ptr(dz), ptr(dkld), ptr(dzp_ext),
+                                     ptr(dmu_ext), ptr(dvar_ext), ptr(dzp), ptr(dmu), ptr(dvar), B, D, n, int(causal),
+                                     float(var_scale), stream()))
+
+
+def step_loss(mse, kld, keep, w, kl_weight, t, num_timesteps, loss, gscale, dkld, total, logsums):
+    check(_lib.lib().cdae_step_loss(ptr(mse), ptr(kld), ptr(keep), ptr(w), ptr(kl_weight), ptr(t), num_timesteps,
+                                    mse.shape[0], ptr(loss), ptr(gscale), ptr(dkld), ptr(total), ptr(logsums), stream()))

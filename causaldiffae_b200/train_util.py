@@ -59,13 +59,14 @@ class _FlatAdamW:
             self.hyper.copy_(th.tensor(vals).pin_memory(), non_blocking=True)
             self._hyper_host = vals
 
-    def step(self, ema=None, ema_rate=0.0, grad_scale=1.0, guarded=False, grads=None):
+    def step(self, ema=None, ema_rate=0.0, grad_scale=1.0, guarded=False, grads=None, lognorm=None):
         """grads: the (all-reduced) gradient buffer, fp32 or bf16 (default: the engine's fp32 gradient arena); guarded:
-        skip the whole step on the device when sum(g^2) is not finite (ref train_util.py:277-280)."""
+        skip the whole step on the device when sum(g^2) is not finite (ref train_util.py:277-280); lognorm: device fp32[2]
+        += {grad norm, 1} for the logger."""
         self.set_hyper(ema_rate, grad_scale)
-        self.launch(ema, guarded, grads)
+        self.launch(ema, guarded, grads, lognorm)
 
-    def launch(self, ema=None, guarded=False, grads=None):
+    def launch(self, ema=None, guarded=False, grads=None, lognorm=None):
         e = self.engine
         ops.zero_(self.gsq)
         guard = None
@@ -74,7 +75,7 @@ class _FlatAdamW:
             ops.zero_(self.guard)
             ops.sumsq(g, self.guard)
             guard = self.guard
-        ops.adam_ema(e.arena, g, self.exp_avg, self.exp_avg_sq, ema, self.hyper, self.step_dev, self.gsq, guard)
+        ops.adam_ema(e.arena, g, self.exp_avg, self.exp_avg_sq, ema, self.hyper, self.step_dev, self.gsq, guard, lognorm)
         e.dirty = True
 
     def state_dict(self):
@@ -86,6 +87,138 @@ class _FlatAdamW:
         self.exp_avg.copy_(sd["exp_avg"]); self.exp_avg_sq.copy_(sd["exp_avg_sq"])
         self.param_groups = sd["param_groups"]
         self._hyper_host = None
+
+
+class FusedStep:
+    """One training micro-step - q_sample -> conv encoder -> DAG layer -> reparameterisation / keep mask / KL -> embedding
+    trunk + FiLM -> UNet torso -> eps-MSE + loss assembly -> the backward of all of it - as explicit launch sequences of
+    hand-written kernels over preallocated buffers, replayed as ONE CUDA graph per batch size (ref train_util.py:231-274
+    forward_backward + gaussian_diffusion.py:768-859 training_losses + unet.py:525-632 forward + autograd).  No ATen compute
+    kernel and no host synchronisation on the path; inputs arrive by plain copies into the static buffers."""
+
+    N_LOG = 24      # [0..19] cdae_step_loss sums, [20..21] gradient-norm sum / count (cdae_adam_ema), rest spare
+
+    @staticmethod
+    def supported(loop):
+        from .unet import UNetModel
+        from . import gaussian_diffusion as gd
+        m, d = loop.model, loop.diffusion
+        if not isinstance(m, UNetModel) or os.environ.get("CDAE_FUSED_STEP", "1") == "0":
+            return False
+        if d.model_mean_type not in (gd.ModelMeanType.EPSILON, gd.ModelMeanType.START_X):
+            return False
+        if d.loss_type not in (gd.LossType.MSE, gd.LossType.RESCALED_MSE):
+            return False
+        if d.model_var_type in (gd.ModelVarType.LEARNED, gd.ModelVarType.LEARNED_RANGE):
+            return False
+        return (m.rep_dim is not None) == bool(loop.rep_cond)
+
+    def __init__(self, loop, B):
+        from . import gaussian_diffusion as gd
+        from .rep import freqs_for
+        self.loop, self.B = loop, B
+        m, d, eng = loop.model, loop.diffusion, loop.engine
+        self.m, self.d, self.eng = m, d, eng
+        dev = eng.device
+        S, C = m.image_size, m.in_channels
+        f = lambda *s: th.zeros(*s, device=dev, dtype=th.float32)   # noqa: E731
+        self.x, self.noise = f(B, C, S, S), f(B, C, S, S)
+        self.t = th.zeros(B, device=dev, dtype=th.int64)
+        self.w = f(B)
+        self.y = th.zeros(B, device=dev, dtype=th.int64) if m.num_classes is not None else None
+        self.c = None                                              # allocated on first use (label width comes with the data)
+        self.klw = f(1)
+        self.rng = th.tensor([int(th.initial_seed()) & 0x7fffffffffffffff, 0], device=dev, dtype=th.int64)
+        self.rep = m.rep_dim is not None
+        self.target_is_noise = d.model_mean_type == gd.ModelMeanType.EPSILON
+        self.pl = eng.plan(B, True)
+        self.trunk_st = eng.trunk.alloc(B, dev, True)
+        if self.rep:
+            D = m.rep_dim
+            self.enc_st = m.rep_emb.runner.alloc(B, C, S, S, dev, True)
+            self.xi, self.keep = f(B, D), (f(B) if m.masking else None)
+            self.zp, self.z, self.zpm, self.kld = f(B, D), f(B, D), f(B, D), f(B)
+            self.dz, self.dzp, self.dmu, self.dvar, self.du = f(B, D), f(B, D), f(B, D), f(B, D), f(B, D)
+            self.dag_ws = f(B, D)
+            self.A = m._adjacency(None, dev)
+        self.mse, self.loss, self.gscale, self.dkld, self.total = f(B), f(B), f(B), f(B), f(1)
+        self.tmap = d._dev_table("timestep_map", dev, lambda: np.asarray(d.timestep_map, dtype=np.int64)) \
+            if hasattr(d, "timestep_map") else None
+        self.tscale = 1000.0 / d.original_num_steps if getattr(d, "rescale_timesteps", False) and hasattr(d, "timestep_map") else 0.0
+        if not hasattr(d, "timestep_map") and d.rescale_timesteps:
+            self.tscale = 1000.0 / d.num_timesteps
+        self.sqrt_ac = d._f32_table("sqrt_alphas_cumprod", dev)
+        self.sqrt_1mac = d._f32_table("sqrt_one_minus_alphas_cumprod", dev)
+        freqs_for(m.model_channels, dev)
+        self.graph, self.runs = None, 0
+        self.device_rng = False
+
+    # ------------------------------------------------------------------ the launch sequence (eager or under capture)
+    def _launch(self):
+        from . import nn as cnn
+        m, eng, pl, B = self.m, self.eng, self.pl, self.B
+        if self.device_rng:
+            ops.randn_(self.noise, self.rng)
+            if self.rep:
+                ops.randn_(self.xi, self.rng)
+                if self.keep is not None:
+                    ops.randn_(self.keep, self.rng, bernoulli=True, keep_prob=1 - m.drop_prob)
+        eng.pack(force=True)
+        ops.q_sample(self.x, self.noise, self.t, self.sqrt_ac, self.sqrt_1mac, out=pl.x_in)
+        z = None
+        if self.rep:
+            enc = m.rep_emb.runner
+            mu, var = enc.forward(self.enc_st, self.x, True)
+            if m.causal_modeling:
+                pp, _ = m.causal_mask._ptr_tables(want_grads=True)
+                ops.dag_fwd(mu, self.A, pp, m.n_vars, m.rep_dim // m.n_vars, m.rep_dim, out=self.zp)
+                zp = self.zp
+            else:
+                zp = mu
+            ops.latent_fwd(mu, var, zp, self.xi, self.keep, self.c, self.z, self.zpm, self.kld, m.n_vars,
+                           m.causal_modeling, 0.001)
+            z = self.z
+        eng.trunk.forward(self.trunk_st, self.t, self.y, self.c if m.c_dim is not None else None, z, pl.film_in,
+                          self.tmap, self.tscale)
+        pl._run_fwd_eager()
+        target = self.noise if self.target_is_noise else self.x
+        ops.mse_loss(pl.eps, target, self.w, want_grad=True, gmul=1.0 / B, mse=self.mse, dpred=pl.deps_in)
+        ops.step_loss(self.mse, self.kld if self.rep else None, self.keep if self.rep else None, self.w, self.klw, self.t,
+                      self.d.num_timesteps, self.loss, self.gscale, self.dkld, self.total, self.loop.logsums)
+        # ---- backward
+        ops.zero_(pl.dfilm)
+        pl._run_bwd_eager()
+        eng.trunk.backward(self.trunk_st, self.y, self.c if m.c_dim is not None else None, z, pl.dfilm,
+                           self.dz if self.rep else None)
+        if self.rep:
+            ops.latent_bwd(mu, var, zp, self.xi, self.keep, self.c, self.dz, self.dkld, None, None, None, self.dzp, self.dmu,
+                           self.dvar, m.n_vars, m.causal_modeling, 0.001)
+            if m.causal_modeling:
+                pp, gp = m.causal_mask._ptr_tables(want_grads=True)
+                ops.dag_bwd(mu, self.A, pp, self.dzp, gp, self.dag_ws, m.n_vars, m.rep_dim // m.n_vars, m.rep_dim,
+                            du=self.du, du_add=self.dmu)
+                dmu = self.du
+            else:
+                dmu = self.dmu      # dzp IS the gradient w.r.t. mu here: fold it in
+                ops.sgemm(dmu, ops._one(dmu.device), self.dzp, 1, dmu.numel(), 1, (0, 0), (dmu.numel(), 1), (dmu.numel(), 1),
+                          c_mode=1, splits=1)
+            enc.backward(self.enc_st, self.x, dmu, self.dvar)
+
+    def run(self):
+        from .engine import USE_GRAPHS, _capture
+        self.pl.generation += 1            # a pending autograd backward on this plan must fail loudly, not read these buffers
+        self.pl.pending = False
+        if USE_GRAPHS and self.runs >= 2:
+            if self.graph is None:
+                from . import _lib
+                k0 = _lib.kernel_count()
+                self.graph = _capture(self._launch)
+                self.graph_kernels = _lib.kernel_count() - k0      # kernels one replay of this graph launches (counted)
+            self.graph.replay()
+        else:
+            self._launch()
+        self.runs += 1
+        self.eng.dirty = False             # the graph packed the current weights; the optimizer marks them dirty again
 
 
 class TrainLoop:
@@ -132,6 +265,11 @@ class TrainLoop:
             self.ema_params = [[self.engine.arena.clone()] for _ in self.ema_rate]
         self.use_ddp = self.world_size > 1
         self.ddp_model = self.model       # data parallelism = flat gradient all-reduce in forward_backward
+        self.noise_override = None
+        self.logsums = th.zeros(FusedStep.N_LOG, device=self.engine.device)
+        self._fused = {}
+        self.use_fused = FusedStep.supported(self)
+        logger.set_dump_hook("train_step", self._dump_device_sums)
         dist_util.sync_params([self.engine.arena] + [b for b in model.buffers()])
 
     # ------------------------------------------------------------------ checkpoints
@@ -205,6 +343,8 @@ class TrainLoop:
         """ref train_util.py:231-274"""
         dev = self.engine.device
         ops.zero_(self.engine.grad_arena)
+        if self.use_fused and self._fused_ok(batch, cond):
+            return self._forward_backward_fused(batch, cond)
         for i in range(0, batch.shape[0], self.microbatch):
             micro = batch[i:i + self.microbatch].to(dev, non_blocking=True)
             micro_cond = {k: v[i:i + self.microbatch].to(dev, non_blocking=True) for k, v in cond.items()}
@@ -220,6 +360,85 @@ class TrainLoop:
         self._grad_scale, self._reduced_grads = 1.0, None
         if self.use_ddp:
             self._grad_scale, self._reduced_grads = self._exchange_gradients()
+
+    def _fused_ok(self, batch, cond):
+        extra = set(cond) - {"c", "y"}
+        if extra or batch.dim() != 4 or (self.rep_cond and "c" not in cond):
+            return False
+        m = self.model
+        return (("y" in cond) == (m.num_classes is not None)) and (m.c_dim is None or "c" in cond)
+
+    def _forward_backward_fused(self, batch, cond):
+        """forward_backward through FusedStep (one CUDA-graph replay per microbatch): the same mathematics as the generic
+        path below, without autograd and without a single ATen compute kernel"""
+        from . import nn as cnn
+        dev = self.engine.device
+        if not self.model.training:
+            self.model.train()
+        for i in range(0, batch.shape[0], self.microbatch):
+            micro = batch[i:i + self.microbatch]
+            B = micro.shape[0]
+            fs = self._fused.get(B)
+            if fs is None:
+                fs = self._fused[B] = FusedStep(self, B)
+            fs.x.copy_(micro, non_blocking=True)
+            if "c" in cond:
+                cc = cond["c"][i:i + self.microbatch]
+                if fs.c is None:
+                    fs.c = th.zeros(B, cc.shape[1], device=dev)
+                    fs.graph = None
+                fs.c.copy_(cc, non_blocking=True)
+            if fs.y is not None:
+                fs.y.copy_(cond["y"][i:i + self.microbatch], non_blocking=True)
+            if hasattr(self.schedule_sampler, "sample_host"):      # pinned staging -> the static buffers, no kernel
+                ti, tw = self.schedule_sampler.sample_host(B)
+                fs.t.copy_(th.from_numpy(ti).pin_memory(), non_blocking=True)
+                fs.w.copy_(th.from_numpy(tw).pin_memory(), non_blocking=True)
+            else:
+                t, weights = self.schedule_sampler.sample(B, dev)
+                fs.t.copy_(t); fs.w.copy_(weights)
+            klw = float(self.diffusion.kl_weight)
+            if klw != getattr(fs, "_klw_host", None):
+                fs.klw.copy_(th.tensor([klw], dtype=th.float32).pin_memory(), non_blocking=True)
+                fs._klw_host = klw
+            device_rng = cnn.RNG_MODE == "device"
+            if device_rng != fs.device_rng:
+                fs.device_rng, fs.graph = device_rng, None
+            if not device_rng:      # the reference's draws, in its order: noise (device generator), xi then mask (CPU generator)
+                if self.noise_override is not None:            # parity runs feed the oracle's noise (training_losses(noise=...))
+                    fs.noise.copy_(self.noise_override[i:i + self.microbatch], non_blocking=True)
+                else:
+                    fs.noise.normal_()
+                if fs.rep:
+                    fs.xi.copy_(th.randn(fs.xi.shape))
+                    if fs.keep is not None:
+                        fs.keep.copy_(th.bernoulli(th.zeros(B) + (1 - self.model.drop_prob)))
+            fs.run()
+            if isinstance(self.schedule_sampler, LossAwareSampler):
+                self.schedule_sampler.update_with_local_losses(fs.t, fs.loss.detach().clone())
+            self.last_loss = fs.total[0]
+        self._grad_scale, self._reduced_grads = 1.0, None
+        if self.use_ddp:
+            self._grad_scale, self._reduced_grads = self._exchange_gradients()
+
+    def _dump_device_sums(self):
+        """logger hook: the per-step sums the fused kernels kept on the device -> the reference's log keys (one host read
+        per dump instead of ~900 `.item()` syncs per step)"""
+        v = self.logsums.tolist()
+        self.logsums.zero_()
+        out = {}
+        if v[3] > 0:
+            for j, key in enumerate(("loss", "mse", "kld_rep")):
+                if key == "kld_rep" and not self.rep_cond:
+                    continue
+                out[key] = v[j] / v[3]
+                if self.log_quartiles:
+                    for q in range(4):
+                        if v[16 + q] > 0:
+                            out[f"{key}_q{q}"] = v[4 + 4 * j + q] / v[16 + q]
+        if v[21] > 0:
+            out["grad_norm"] = v[20] / v[21]
+        return out
 
     def _exchange_gradients(self):
         """ref train_util.py:107-126 (DDP mean).  bf16 on the wire (default): one cast pass over the arena, ONE NCCL sum
@@ -247,7 +466,7 @@ class TrainLoop:
         """ref train_util.py:292-297: grad-norm log, lr anneal, AdamW step, EMA — one fused kernel."""
         self._anneal_lr()
         self.opt.step(ema=self.ema_params[0][0], ema_rate=self.ema_rate[0], grad_scale=getattr(self, "_grad_scale", 1.0),
-                      guarded=guarded, grads=getattr(self, "_reduced_grads", None))
+                      guarded=guarded, grads=getattr(self, "_reduced_grads", None), lognorm=self.logsums[20:22])
         for rate, params in zip(self.ema_rate[1:], self.ema_params[1:]):
             if guarded:     # the extra rates must skip with the step: blend towards the (unchanged) arena is not a no-op
                 ok = th.isfinite(self.opt.guard[0])
@@ -257,7 +476,8 @@ class TrainLoop:
         self._log_grad_norm()
 
     def _log_grad_norm(self):
-        logger.logkv_mean("grad_norm", th.sqrt(self.opt.gsq[0]))
+        """ref train_util.py:299-303: the fused optimizer kernel keeps the running sum of gradient norms on the device
+        (logsums[20:22]); it reaches the logger through the dump hook"""
 
     def _anneal_lr(self):
         if not self.lr_anneal_steps:

@@ -260,28 +260,28 @@ class UNetModel(nn.Module):
             t = cache[str(device)] = th.tensor(self.A, dtype=th.float32, device=device)
         return t
 
-    def forward(self, x, timesteps, y=None, c=None, x_start=None, z=None, A=None, mask=None):
-        """ref unet.py:525-632 -> (eps, mu, var, z_post, mask)"""
+    def forward(self, x, timesteps, y=None, c=None, x_start=None, z=None, A=None, mask=None, _tmap=None, _tscale=0.0):
+        """ref unet.py:525-632 -> (eps, mu, var, z_post, mask).  Every stage is a launch sequence of hand-written kernels:
+        conv encoder (rep.EncoderRunner), DAG layer (csrc/small.cu), reparameterisation + keep mask (latent kernels),
+        embedding trunk + all FiLM projections (rep.TrunkRunner), torso (engine.Plan)."""
+        from .rep import _FilmFn, _LatentFn, anchor
+        from .nn import _randn_like_ref
         assert (y is not None) == (self.num_classes is not None), \
             "must specify y if and only if the model is class-conditional"
-        emb = self.embed(timesteps, y, c)
         mu = var = z_post = None
         mask = None
         if self.rep_dim is not None:
             if z is None:
                 mu, var = self.rep_emb.encode(x_start)
-                if self.causal_modeling:
-                    At = self._adjacency(A, mu.device)
-                    z_post = self.causal_mask(mu, At)      # causal_masking + nonlinearity_add_back_noise, fused
-                    z = reparameterize(z_post, var * 0.001)
-                else:
-                    z = reparameterize(mu, var * 0.001)
+                zp = self.causal_mask(mu, self._adjacency(A, mu.device)) if self.causal_modeling else mu
+                xi = _randn_like_ref(mu)                       # reference order of CPU-generator draws: xi, then the mask
+                keep = None
                 if self.masking:
-                    keep = th.bernoulli(th.zeros(z.shape[0]) + (1 - self.drop_prob)).to(z.device)
-                    z = (z * keep[:, None]).float()
-                    if z_post is not None:
-                        z_post = (z_post * keep[:, None]).float()
-                    mask = keep
-            emb = emb + self.up_emb(z)
-        eps = self.engine.torso(x, emb)
+                    keep = th.bernoulli(th.zeros(mu.shape[0]) + (1 - self.drop_prob)).to(mu.device)
+                z, zp_m = _LatentFn.apply(var, zp, xi, keep, 0.001, self.n_vars)
+                if self.causal_modeling:
+                    z_post = zp_m
+                mask = keep
+        film = _FilmFn.apply(self, anchor(x.device), timesteps, y, c, z, _tmap, _tscale, th.is_grad_enabled())
+        eps = self.engine.torso_film(x, film)
         return eps, mu, var, z_post, mask

@@ -37,8 +37,9 @@ int cdae_init(void);
 int cdae_q_sample(const float* x0, const float* noise, const int64_t* t, const float* sqrt_ac,
                   const float* sqrt_1mac, float* x_t, int64_t B, int64_t per_sample, cdae_stream s);
 /* per-sample MSE of (target - pred) and its gradient scale            (gaussian_diffusion.py:847, train_util.py:266)
- * mse[b] = mean_chw (target-pred)^2 ; if dpred != NULL: dpred = 2*(pred-target)*gscale[b]/per_sample */
-int cdae_mse_loss(const float* pred, const float* target, float* mse, const float* gscale, float* dpred,
+ * mse[b] = mean_chw (target-pred)^2 ; if dpred != NULL: dpred = 2*(pred-target)*gscale[b]*gmul/per_sample
+ * (gscale = the schedule sampler's weights, gmul = 1/B: the gradient of mean_b(mse[b] w[b])) */
+int cdae_mse_loss(const float* pred, const float* target, float* mse, const float* gscale, float gmul, float* dpred,
                   int64_t B, int64_t per_sample, cdae_stream s);
 /* DDIM x_{t-1} update with optional classifier-free guidance combine   (gaussian_diffusion.py:277-285,320-341,506-558)
  * coef_table: device fp32 [T'][8] rows {sqrt_recip_ac, sqrt_recipm1_ac, sqrt(ac_prev), sqrt(1-ac_prev-sigma^2),
@@ -53,9 +54,10 @@ int cdae_ddim_step(const float* x, const float* eps_c, const float* eps_u, float
  * taken so far (bias corrections of step+1 are evaluated in double on the device; the counter is incremented after the
  * update); g: the gradient arena, fp32 or (g_is_bf16) its bf16 copy as all-reduced; guard: optional device scalar - when
  * it is not finite the launch changes nothing and the counter stays (the reference's "found NaN: skip the step",
- * train_util.py:277-280); gsq_out += sum((g*grad_scale)^2). */
+ * train_util.py:277-280); gsq_out += sum((g*grad_scale)^2); lognorm (optional, 2 floats) += {sqrt(gsq_out), 1}: the running
+ * mean of the gradient norm the logger reports (train_util.py:299-303) without a host read per step. */
 int cdae_adam_ema(float* p, const void* g, int g_is_bf16, float* m, float* v, float* ema, const float* hyper,
-                  int64_t* step, const float* guard, float* gsq_out, int64_t n, cdae_stream s);
+                  int64_t* step, const float* guard, float* gsq_out, float* lognorm, int64_t n, cdae_stream s);
 /* out += sum(g^2) over a flat fp32 (or bf16) buffer (the guard above; train_util.py:277 isfinite check, :299-303 grad norm) */
 int cdae_sumsq(const void* g, int g_is_bf16, float* out, int64_t n, cdae_stream s);
 /* fp32 -> bf16 (RNE) copy of a flat buffer: the gradient arena as it crosses NVLink (train_util.py:107-126 DDP buckets) */
@@ -98,10 +100,12 @@ int cdae_gn_fwd(const void* x0, int C0, const void* x1, int C1, int B, int HW,
                 int silu, void* y, float* mean, float* rstd, cdae_stream s);
 /* same forward when the producing convolutions already accumulated the per-(image, channel) sums (cdae_igemm_desc.stats):
  * stats0 fp32 [B][C0][2], stats1 fp32 [B][C1][2] = {sum, sum of squares} over the HW pixels.  One streaming pass
- * (2 B read + 2 B written per element), no reduction; mean/rstd [B,32] are still written for the backward. */
+ * (2 B read + 2 B written per element), no reduction; mean/rstd [B,32] are still written for the backward.  ab (optional):
+ * fp32 [B][C][2] receives the per-(image, channel) constants {a, b} with u (u/2 under SiLU) = a x + b, which the fused
+ * backward statistics of the data-gradient convolution read (cdae_igemm_desc.gnb_ab). */
 int cdae_gn_apply_fwd(const void* x0, int C0, const float* stats0, const void* x1, int C1, const float* stats1,
                       int B, int HW, const float* gamma, const float* beta, const float* film, int film_ld, int film_off,
-                      int silu, void* y, float* mean, float* rstd, cdae_stream s);
+                      int silu, void* y, float* mean, float* rstd, float* ab, cdae_stream s);
 /* backward: dx split into dx0/dx1; accumulate_dx bit0/bit1: add to the existing contents of dx0/dx1;
  * dadd: optional bf16 [B,HW,C] tensor added to dx (identity-skip gradient of a ResBlock, unet.py:198);
  * dgamma/dbeta (+=, fp32), dfilm (+= into [B, film_ld] at the same columns) */
@@ -110,13 +114,14 @@ int cdae_gn_bwd(const void* dy, const void* x0, int C0, const void* x1, int C1, 
                 const float* mean, const float* rstd, const void* dadd, void* dx0, void* dx1, int accumulate_dx,
                 float* dgamma, float* dbeta, float* dfilm, cdae_stream s);
 
-/* the same backward as two streaming passes (reduce: P_c = sum du, Qx_c = sum du*x per (sample, channel) into ws; apply:
- * dx, walking the tensor in reverse so that the second read of dy / x hits the L2).  ws: caller-owned fp32 [B][2][C],
- * ZERO on entry (it is accumulated into with red.add and left holding the sums). */
-int cdae_gn_bwd_stream(const void* dy, const void* x0, int C0, const void* x1, int C1, int B, int HW,
-                       const float* gamma, const float* beta, const float* film, int film_ld, int film_off, int silu,
-                       const float* mean, const float* rstd, const void* dadd, void* dx0, void* dx1, int accumulate_dx,
-                       float* dgamma, float* dbeta, float* dfilm, float* ws, cdae_stream s);
+/* the backward as ONE streaming pass, for a GroupNorm whose output gradient was produced by a data-gradient convolution with
+ * cdae_igemm_desc.gnb_* set: du = dy * silu'(u) (bf16, same layout as dy) and ws fp32 [B][C][2] = {sum du, sum du*x} per
+ * (sample, channel) come from that launch's epilogue; this pass reads du and x once and writes dx = K1 du - K2' - x K3'
+ * (+ dadd) (+ old dx) plus dgamma / dbeta / dfilm.  6 B per element, no reduction, no clusters. */
+int cdae_gn_bwd_apply(const void* du, const void* x0, int C0, const void* x1, int C1, int B, int HW,
+                      const float* gamma, const float* beta, const float* film, int film_ld, int film_off,
+                      const float* mean, const float* rstd, const float* ws, const void* dadd, void* dx0, void* dx1,
+                      int accumulate_dx, float* dgamma, float* dbeta, float* dfilm, cdae_stream s);
 
 /* ------------------------------------------------------------------ implicit-GEMM convolution on tcgen05/TMEM/TMA
  * Replaces aten::convolution (cuDNN) at unet.py:143-171 (ResBlock convs + 1x1 skip), :69-79, :97-105 (up/down),
@@ -143,6 +148,14 @@ typedef struct {
                                               sum and sum of squares of the bf16 output as stored - the GroupNorm statistics of
                                               the consumer (cdae_gn_apply_fwd), produced by the conv epilogue so that the norm
                                               becomes one streaming pass.  Needs out_mode 0, cout % 64 == 0, OH*OW >= 32. */
+  /* GroupNorm-backward fusion of a DATA-GRADIENT launch (backward twin of `stats`; nn.py:435-437 + unet.py:185-198 backward):
+   * the output is the gradient w.r.t. the OUTPUT of y = [SiLU](FiLM(GroupNorm32(x))), x = concat(gnb_x0 [gnb_c0 channels, pitch
+   * gnb_ld0], gnb_x1 [cout - gnb_c0, pitch gnb_ld1]) on the same pixel grid.  The epilogue fetches the x slab (residual TMA
+   * path), stores du = dy * silu'(u) instead of dy (u/2 = a x + b, {a, b} = gnb_ab[image][channel][2] written by
+   * cdae_gn_apply_fwd) and ACCUMULATES gnb_ws[image][channel][2] += {sum du, sum du*x}: cdae_gn_bwd_apply then is one
+   * streaming pass.  Needs out_mode 0, no bias / residual / stats, cout and gnb_c0 % 64 == 0, OH*OW >= 32. */
+  float* gnb_ws; const float* gnb_ab; const void* gnb_x0; const void* gnb_x1;
+  int32_t gnb_c0, gnb_ld0, gnb_ld1, gnb_silu;
 } cdae_igemm_desc;
 int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s);
 
@@ -175,11 +188,81 @@ int cdae_attn_bwd(const void* qkv, const void* out, const void* dout, const floa
  * u, z_post, dzpost, du: fp32 [B, n, d]; A: fp32 [n, n] row-major; params / grads: DEVICE arrays of 4n pointers
  * {W1_i [D,d], b1_i [D], W2_i [d,D], b2_i [d]} (the reference keeps one MLP per causal variable).  n <= 8.
  * backward: recomputes the hidden layer; parameter gradients are ACCUMULATED (+=) into grads; dzp_ws is a caller-owned
- * fp32 [B, n, d] workspace that must be zero on entry and is left zero on exit; d in {64, 128, 256}, D % 32 == 0. */
+ * fp32 [B, n, d] workspace that must be zero on entry and is left zero on exit; du_add: optional fp32 [B, n, d] added to du
+ * (the direct KL gradient w.r.t. mu); d in {64, 128, 256}, D % 32 == 0. */
 int cdae_dag_fwd(const float* u, const float* A, const void* const* params, float* zpost, int B, int n, int d, int D,
                  cdae_stream s);
 int cdae_dag_bwd(const float* u, const float* A, const void* const* params, const float* dzpost, void* const* grads,
-                 float* dzp_ws, float* du, int B, int n, int d, int D, cdae_stream s);
+                 float* dzp_ws, float* du, const float* du_add, int B, int n, int d, int D, cdae_stream s);
+
+/* ------------------------------------------------------------------ the [B, 512]-sized representation path in fp32
+ * (timestep embedding trunk, FiLM projections, GaussianConvEncoder, reparameterisation / mask / KL).  Replaces, per
+ * training step, ~250 ATen / cuBLAS-SIMT / cuDNN launches of nn.py:15-110,440-467,551-569, unet.py:545-616,
+ * gaussian_diffusion.py:718-766 and their autograd.  fp32 CUDA-core math (<= 1e-4 vs the oracle): the path is 0.03 % of the
+ * step's FLOPs, what it costs is launches.
+ *
+ * cdae_sgemm: C[M,N] (=, +=, scatter+=) A[M,K] * B[K,N] with pluggable operand views:
+ *   a_mode 0 dense A[m*a_sm + k*a_sk] | 1 dense with SiLU applied on load | 2 im2col view of a 3x3 stride-2 pad-1 conv
+ *   (m = (b, oh, ow), k = (ci, kh, kw) - the OIHW weight order), source strides g_s*, optional per-input-channel {a, b} table:
+ *   the producer's BatchNorm + LeakyReLU(0.01) applied on load (zero padding AFTER the activation, like the reference) |
+ *   3 the same view transposed (m = conv k, k = conv pixel: weight gradients);
+ *   b_mode 0 dense B[k*b_sk + n*b_sn] | 1 with SiLU on load;
+ *   c_mode 0 store C[m*c_sm + n*c_sn] | 1 atomic += | 2 col2im scatter += into the g_s* tensor (data gradient; zero it first);
+ *   bias[n] added once; act_out 1 = softplus(v) + 1e-8 (nn.py:108); colstats[n][2] (double) += column sum / sum of squares
+ *   of C as stored (the BatchNorm batch statistics of the conv output).  splits: K split factor over grid.z (0 = auto; > 1
+ *   needs c_mode 1 or 2). */
+typedef struct {
+  const float* A; int64_t a_sm, a_sk; int32_t a_mode;
+  const float* B; int64_t b_sk, b_sn; int32_t b_mode;
+  float* C; int64_t c_sm, c_sn; int32_t c_mode;
+  const float* bias; int32_t act_out;
+  double* colstats;
+  int32_t M, N, K, splits;
+  int64_t g_sb, g_sc, g_sh, g_sw; int32_t g_cin, g_h, g_w, g_oh, g_ow; const float* g_ab;
+} cdae_sgemm_desc;
+int cdae_sgemm(const cdae_sgemm_desc* d, cdae_stream s);
+/* timestep_embedding (nn.py:551-569): out[b] = [cos(t_b f) | sin(t_b f)] (+ a zero column when dim is odd); freqs: device
+ * fp32 [dim/2] computed on the host exactly like the reference; t int64 or (t_is_float) fp32; map (optional): respaced ->
+ * original step table applied first, scale (0 = off): rescale_timesteps factor 1000/T (respace.py:119-124) */
+int cdae_timestep_embedding(const void* t, int t_is_float, const int64_t* map, float scale, const float* freqs, float* out,
+                            int B, int dim, cdae_stream s);
+/* counter-based normal / Bernoulli draws (Philox4x32-10 + Box-Muller), replayable inside a CUDA graph: state = device
+ * uint64 {seed, offset}; the launch advances the offset.  Replaces th.randn_like / th.bernoulli at gaussian_diffusion.py:790,
+ * nn.py:464, unet.py:601 in throughput runs (parity runs inject the reference's CPU-generator draws instead). */
+int cdae_randn(float* out, int64_t n, void* state, int bernoulli, float keep_prob, cdae_stream s);
+/* g *= silu'(x)  (backward of the SiLU-on-load operand views) ; g *= softplus'(pre) given var = softplus(pre) + 1e-8 */
+int cdae_silu_bwd(float* g, const float* x, int64_t n, cdae_stream s);
+int cdae_softplus_bwd(float* g, const float* var, int64_t n, cdae_stream s);
+/* x[b,:] += table[idx[b],:] (label_emb, unet.py:549-551); backward: dtable[idx[b],:] += x[b,:] */
+int cdae_embed_rows(float* x, const float* table, const int64_t* idx, int B, int D, int backward, float* dtable, cdae_stream s);
+/* nn.BatchNorm2d bookkeeping of one encoder layer (nn.py:52-61; eps 1e-5, momentum 0.1): train = batch statistics from the
+ * double column sums (count = B*OH*OW) and running-buffer update, else running statistics -> ab[c] = {a, b} with
+ * bn(x) = a x + b, mean_rstd[c] = {mean, rstd} */
+int cdae_bn_finalize(const double* stats, double count, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, int64_t* num_batches_tracked, int train, float* ab, float* mean_rstd, int C,
+                     cdae_stream s);
+/* last encoder layer: BatchNorm + LeakyReLU + th.flatten (nn.py:104): NHWC raw [B,P,C] -> [B, C*P]; backward = the permutation */
+int cdae_enc_head(const float* in, const float* ab, float* out, int B, int P, int C, int backward, cdae_stream s);
+/* BatchNorm(batch stats) + LeakyReLU backward over NHWC [M, C]: dact (gradient w.r.t. the activation) is overwritten by the
+ * gradient w.r.t. the raw conv output; dgamma / dbeta += ; sums: double [C][2] scratch */
+int cdae_bn_lrelu_bwd(float* dact, const float* raw, const float* ab, const float* mean_rstd, const float* gamma,
+                      double* sums, float* dgamma, float* dbeta, int64_t M, int C, cdae_stream s);
+/* reparameterize + classifier-free keep mask + closed-form KL of representation_loss (nn.py:440-467, unet.py:590-613,
+ * gaussian_diffusion.py:718-766), one launch:  z = (zp + sqrt(var_scale*var) xi) keep, zp_out = zp keep,
+ * kld[b] = KL(N(mu,var) || N(0,1)) + [causal] 0.5 sum_i |zp_out_i - c_i|^2.  keep / c / zp_out / kld may be NULL. */
+int cdae_latent_fwd(const float* mu, const float* var, const float* zp, const float* xi, const float* keep, const float* c,
+                    float* z, float* zp_out, float* kld, int B, int D, int n, int causal, float var_scale, cdae_stream s);
+/* its backward: dz [B,D] and dkld [B] (either may be NULL) plus optional external gradients -> dzp, dmu (direct part), dvar */
+int cdae_latent_bwd(const float* mu, const float* var, const float* zp, const float* xi, const float* keep, const float* c,
+                    const float* dz, const float* dkld, const float* dzp_ext, const float* dmu_ext, const float* dvar_ext,
+                    float* dzp, float* dmu, float* dvar, int B, int D, int n, int causal, float var_scale, cdae_stream s);
+/* loss assembly of a training step (gaussian_diffusion.py:849-855, train_util.py:262-266): loss[b] = mse[b] + kl_weight *
+ * kld_rep (kld_rep = kld[b], or sum(kld keep)/sum(keep) when keep != NULL), total = mean(loss w); emits the gradient scales
+ * gscale[b] = w[b]/B (for cdae_mse_loss) and dkld[b] (for cdae_latent_bwd), and (optional) the logger's running sums
+ * logsums[20] += {loss w, mse w, kld w, count, 3x4 per-timestep-quartile sums, 4 quartile counts} (train_util.py:401-407) */
+int cdae_step_loss(const float* mse, const float* kld, const float* keep, const float* w, const float* kl_weight,
+                   const int64_t* t, int num_timesteps, int B, float* loss, float* gscale, float* dkld, float* total,
+                   float* logsums, cdae_stream s);
 
 /* ------------------------------------------------------------------ HBM-resident dataset batch assembly
  * (the step before the hot path: image_datasets.py:141-183,241-296,344-392,411-483 = PIL decode + ToTensor + DataLoader

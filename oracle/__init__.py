@@ -15,7 +15,9 @@ the reference Python executed by this container's torch in fp32.
 
 Pinning: the reference ships no tests or golden vectors, so the
 oracle is pinned against outputs of the *reference itself* imported in the build
-container (``tests/golden/make_golden.py`` -> ``tests/golden/*.npz``) and, when
-``/root/reference`` is present, live against it (``tests/test_oracle_vs_reference.py``).
+container (``tests/golden/make_golden.py`` -> ``tests/golden/*.npz``, checked by
+``tests/test_oracle_golden.py``).  ``oracle/refshim.py`` imports the unmodified reference
+(in place, or from the copy ``oracle/build_ref.py`` puts under the git-ignored ``oracle/_ref``)
+for fixture generation and for ``bench.py --impl reference``.
 """
 from . import schedules, model, diffusion  # noqa: F401

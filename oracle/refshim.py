@@ -1,7 +1,7 @@
 """Import the *real* reference (read-only tree) in the build container to pin the oracle.
 
 Test infrastructure only.  Used by tests/golden/make_golden.py (fixture generation) and by
-tests/test_oracle_vs_reference.py (live check, skipped where the tree is absent, e.g. the GPU box).
+`bench.py --impl reference` (the reference arm: the unmodified reference timed on the host cores).
 Nothing here is copied from the reference: it is imported in place with
   * two stand-in modules for imports the container lacks (blobfile, mpi4py)  [SURVEY.md App. B]
   * the four documented oracle patches of SURVEY.md 8c:
@@ -14,7 +14,17 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("CDAE_REFERENCE_ROOT", "/root/reference")
+def _find_root():
+    """the reference tree in the build container, else the unmodified copy oracle/build_ref.py placed under oracle/_ref
+    (git-ignored; it travels to the GPU box, where /root/reference does not exist)"""
+    cands = [os.environ.get("CDAE_REFERENCE_ROOT"), "/root/reference", os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "improved_diffusion")):
+            return c
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 
 def available():

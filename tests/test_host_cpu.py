@@ -173,9 +173,9 @@ def test_c_abi_error_convention_without_a_gpu():
     assert lib.cdae_gather_images(p, None, p, p, None, 2, 8, 8, 5, 0, 0, None) == ERR_SHAPE   # 5 channels
     assert b"channels" in lib.cdae_last_error()
     assert lib.cdae_gather_images(p, None, p, p, None, 2, 3, 3, 1, 0, 0, None) == ERR_SHAPE   # H*W % 4
-    assert lib.cdae_gn_apply_fwd(p, 40, p, None, 0, None, 2, 16, p, p, None, 0, 0, 1, p, p, p, None) == ERR_SHAPE   # C % 32
-    assert lib.cdae_gn_bwd_stream(p, p, 64, None, 0, 2, 16, p, p, None, 0, 0, 1, p, p, None, p, None, 0, None, None, None,
-                                  None, None) == ERR_ARG                                   # workspace missing
+    assert lib.cdae_gn_apply_fwd(p, 40, p, None, 0, None, 2, 16, p, p, None, 0, 0, 1, p, p, p, None, None) == ERR_SHAPE   # C % 32
+    assert lib.cdae_gn_bwd_apply(p, p, 64, None, 0, 2, 16, p, p, None, 0, 0, p, p, None, None, p, None, 0, None, None, None,
+                                 None) == ERR_ARG                                          # statistics workspace missing
     d = _lib.IgemmDesc()
     d.out, d.wgt, d.nsrc, d.nseg, d.N, d.H, d.W = p, p, 1, 0, 1, 8, 8
     assert lib.cdae_igemm(ctypes.byref(d), None) == ERR_ARG                                   # no K segments

@@ -162,8 +162,7 @@ def test_layout_kernels():
 @pytest.mark.parametrize("C0,C1,HW,film,silu", [(128, 0, 64 * 64, True, True), (64, 0, 16 * 16, False, True),
                                                 (512, 384, 8 * 8, False, True), (256, 128, 32 * 32, True, True),
                                                 (384, 0, 16 * 16, False, False), (64, 64, 4 * 4, True, True)])
-@pytest.mark.parametrize("stream", [False, True])
-def test_groupnorm_fwd_bwd(C0, C1, HW, film, silu, stream):
+def test_groupnorm_fwd_bwd(C0, C1, HW, film, silu):
     from causaldiffae_b200 import ops
     g = torch.Generator().manual_seed(C0 + C1 + HW)
     B, Ct = 3, C0 + C1
@@ -188,10 +187,8 @@ def test_groupnorm_fwd_bwd(C0, C1, HW, film, silu, stream):
     assert relerr(nchw(y), yref) < 6e-3
     dgamma, dbeta = torch.zeros(Ct, device=dev()), torch.zeros(Ct, device=dev())
     dfilm = torch.zeros_like(film_t) if film else None
-    # stream: the two-pass streaming kernels (cdae_gn_bwd_stream, zeroed workspace); else the resident cluster kernel
-    mkws = lambda: torch.zeros(B, 2, Ct, device=dev()) if stream else None
     dx0, dx1 = ops.gn_bwd(nhwc(dy), x0, gamma, beta, mean, rstd, x1=x1, film=film_t, film_off=foff, silu=silu,
-                          dgamma=dgamma, dbeta=dbeta, dfilm=dfilm, ws=mkws())
+                          dgamma=dgamma, dbeta=dbeta, dfilm=dfilm)
     dx = torch.cat([dx0, dx1], dim=-1) if C1 else dx0
     assert relerr(nchw(dx), xr.grad) < 8e-3
     assert relerr(dgamma, gr.grad) < 3e-3 and relerr(dbeta, br.grad) < 3e-3
@@ -203,7 +200,7 @@ def test_groupnorm_fwd_bwd(C0, C1, HW, film, silu, stream):
     acc1 = torch.zeros_like(dx1) if C1 else None
     dadd = torch.randn(B, S, S, Ct, generator=g).to(dev()).to(bf16)
     ops.gn_bwd(nhwc(dy), x0, gamma, beta, mean, rstd, x1=x1, film=film_t, film_off=foff, silu=silu, dx0=acc0, dx1=acc1,
-               accumulate_dx=True, dadd=dadd, ws=mkws())
+               accumulate_dx=True, dadd=dadd)
     assert relerr(acc0.float(), base.float() + dx0.float() + dadd[..., :C0].float()) < 1e-2
     if C1:
         assert relerr(acc1.float(), dx1.float() + dadd[..., C0:].float()) < 1e-2
@@ -372,6 +369,75 @@ def test_igemm_channel_stats_rejects_unsupported():
                             stats=torch.zeros(2, 64, 2, device=dev()))
     with pytest.raises(CdaeError):
         ops.igemm(d)
+
+
+@pytest.mark.parametrize("N,H,C0,C1,cin,ksize,film,silu", [
+    (2, 64, 128, 0, 128, 3, True, True),        # halo kernel, one image per box, FiLM (ResBlock out_layers norm)
+    (3, 32, 256, 128, 256, 3, False, True),     # concat input of the norm: x slab comes from two tensors
+    (5, 8, 512, 512, 512, 3, False, True),      # two images per 128-pixel box (tap-streaming kernel), ragged batch
+    (2, 16, 384, 0, 1152, 1, False, False),     # attention norm: 1x1 qkv data gradient, no SiLU
+    (2, 48, 64, 64, 64, 3, True, True),         # non-power-of-two image: partial boxes masked out of the sums
+    (67, 16, 128, 0, 128, 3, True, True),       # many boxes (MT = 2 tail)
+])
+def test_groupnorm_backward_from_dgrad_epilogue(N, H, C0, C1, cin, ksize, film, silu):
+    """The fused GroupNorm backward: y = act(FiLM(GN(x))) feeds a conv; that conv's DATA-GRADIENT launch (gnb_*) stores
+    du = dy * silu'(u) and accumulates {sum du, sum du*x} per (image, channel); cdae_gn_bwd_apply is then one streaming
+    pass.  Checked against fp32 torch autograd of the same composition (GroupNorm -> FiLM -> SiLU -> conv)."""
+    from causaldiffae_b200 import ops
+    g = torch.Generator().manual_seed(N * 131 + H + C0)
+    Ct = C0 + C1
+    cout_conv = cin                                   # the consumer conv: Ct -> cout_conv channels
+    x = (torch.randn(N, Ct, H, H, generator=g) * 1.5 + 0.3).to(dev()).to(bf16).float()
+    gamma = (1 + 0.2 * torch.randn(Ct, generator=g)).to(dev())
+    beta = (0.2 * torch.randn(Ct, generator=g)).to(dev())
+    film_t = (0.3 * torch.randn(N, 2 * Ct + 32, generator=g)).to(dev()) if film else None
+    foff = 16
+    w = (torch.randn(cout_conv, Ct, ksize, ksize, generator=g) * (Ct * ksize * ksize) ** -0.5).to(dev()).to(bf16).float()
+    dz = torch.randn(N, cout_conv, H, H, generator=g).to(dev()).to(bf16).float()      # gradient w.r.t. the conv output
+    xr, gr, br = x.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    fr = film_t.clone().requires_grad_(True) if film else None
+    u = F.group_norm(xr, 32, gr, br, eps=1e-5)
+    if film:
+        u = u * (1 + fr[:, foff:foff + Ct, None, None]) + fr[:, foff + Ct:foff + 2 * Ct, None, None]
+    a = u * torch.sigmoid(u) if silu else u
+    F.conv2d(a, w, padding=ksize // 2).backward(dz)
+    # CUDA path: streaming forward (leaves the {a, b} table), data-gradient conv with the fused statistics, streaming apply
+    x_nhwc = nhwc(x)
+    x0 = x_nhwc[..., :C0].contiguous()
+    x1 = x_nhwc[..., C0:].contiguous() if C1 else None
+    st = torch.stack([x.sum(dim=(2, 3)), (x * x).sum(dim=(2, 3))], dim=-1)
+    ab = torch.full((N, Ct, 2), float("nan"), device=dev())
+    y, mean, rstd = ops.gn_apply_fwd(x0, st[:, :C0].contiguous(), gamma, beta, x1=x1, stats1=st[:, C0:].contiguous() if C1 else None,
+                                     film=film_t, film_off=foff, silu=silu, ab=ab)
+    assert relerr(nchw(y), a) < 6e-3
+    wt = w.permute(1, 2, 3, 0).reshape(Ct, -1).contiguous().to(bf16)       # [Ct, taps*cout]: transposed packing of the engine
+    segs, _ = ops.conv_segments([cout_conv], ksize, transposed=True)
+    du = torch.full((N, H, H, Ct), float("nan"), device=dev(), dtype=bf16)
+    ws = torch.zeros(N, Ct, 2, device=dev())
+    d = ops.make_igemm_desc([nhwc(dz)], segs, wt, du, Ct, gnb=dict(x0=x0, x1=x1, ab=ab if silu else None, ws=ws, silu=silu))
+    ops.igemm(d)
+    dgamma, dbeta = torch.zeros(Ct, device=dev()), torch.zeros(Ct, device=dev())
+    dfilm = torch.zeros_like(film_t) if film else None
+    dx0, dx1 = ops.gn_bwd_apply(du, x0, gamma, beta, mean, rstd, ws, x1=x1, film=film_t, film_off=foff, dgamma=dgamma,
+                                dbeta=dbeta, dfilm=dfilm)
+    dx = torch.cat([dx0, dx1], dim=-1) if C1 else dx0
+    # the statistics are those of du as stored
+    duf, xf = du.double(), x_nhwc.double()
+    ref_ws = torch.stack([duf.sum(dim=(1, 2)), (duf * xf).sum(dim=(1, 2))], dim=-1)
+    np.testing.assert_allclose(ws.double().cpu().numpy(), ref_ws.cpu().numpy(), rtol=3e-4, atol=3e-3 * H)
+    assert relerr(nchw(dx), xr.grad) < 1e-2, relerr(nchw(dx), xr.grad)
+    assert relerr(dgamma, gr.grad) < 5e-3 and relerr(dbeta, br.grad) < 5e-3
+    if film:
+        assert relerr(dfilm, fr.grad) < 5e-3
+    # accumulate / dadd modes of the apply pass
+    base = torch.randn_like(dx0.float()).to(bf16)
+    acc0, acc1 = base.clone(), (torch.zeros_like(dx1) if C1 else None)
+    dadd = torch.randn(N, H, H, Ct, generator=g).to(dev()).to(bf16)
+    ops.gn_bwd_apply(du, x0, gamma, beta, mean, rstd, ws, x1=x1, film=film_t, film_off=foff, dx0=acc0, dx1=acc1,
+                     accumulate_dx=True, dadd=dadd)
+    assert relerr(acc0.float(), base.float() + dx0.float() + dadd[..., :C0].float()) < 1e-2
+    if C1:
+        assert relerr(acc1.float(), dx1.float() + dadd[..., C0:].float()) < 1e-2
 
 
 @pytest.mark.parametrize("C0,C1,HW,film,silu,B", [(128, 0, 64 * 64, True, True, 3), (64, 0, 16 * 16, False, True, 2),

@@ -123,6 +123,16 @@ FLAGS2 = dict(image_size=64, num_channels=128, num_res_blocks=2, num_heads=4, at
               rescale_timesteps=False, rescale_learned_sigmas=False, diffusion_steps=1000, masking=True)
 
 
+class _Fixed:
+    """schedule sampler that hands out the timesteps / weights the oracle step uses"""
+
+    def __init__(self, t, w):
+        self.t, self.w = t.astype(np.int64), w.astype(np.float32)
+
+    def sample_host(self, batch_size):
+        return self.t, self.w
+
+
 def structured_batch64(B, gen):
     """3x64x64 images that depend on four causal labels: disc radius (c0), disc x-position (c1), disc colour (c2),
     background shade (c3) - so that the loss actually falls and guidance has something to amplify"""
@@ -170,16 +180,16 @@ def test_cfg2_masking_500_step_loss_parity_then_guided_ddim_psnr():
         x, c = x.to(dev), c.to(dev)
         torch.manual_seed(7000 + step)          # xi and the Bernoulli keep-mask come off the CPU generator on both sides
         theirs.append(ref.run_step(x, t, noise, w, c=c)["loss"])
+        # this repo: TrainLoop.run_step itself = the fused CUDA-graph step the benchmark times (same t / w through the
+        # schedule sampler, same noise, xi and keep mask off the CPU generator)
         torch.manual_seed(7000 + step)
-        loop.engine.grad_arena.zero_()
-        losses = diff.training_losses(model, x, t, model_kwargs=dict(c=c), noise=noise, rep_cond=True, causal_modeling=True)
-        loss = (losses["loss"] * w).mean()
-        loss.backward()
-        loop._grad_scale = 1.0
-        loop.optimize_normal()
+        loop.schedule_sampler = _Fixed(t.cpu().numpy(), w.cpu().numpy())
+        loop.noise_override = noise
+        loop.run_step(x, {"c": c})
+        assert loop.use_fused and loop._fused[B].runs == step + 1
         loop.step += 1
         diff.kl_weight = loop.linear_kl_weight_scheduler(loop.step, 50000, 0.0, 1.0)
-        mine.append(float(loss))
+        mine.append(float(loop.last_loss))
     mine, theirs = np.array(mine), np.array(theirs)
     assert theirs[-50:].mean() < 0.25 * theirs[:10].mean(), "the reference run itself did not learn"
     win = 50
