@@ -97,7 +97,8 @@ _SIGS = {
     "cdae_gather_images": ([P, P, P, P, P, I32, I32, I32, I32, I32, I32, P], C.c_int),
     "cdae_dag_bwd": ([P, P, P, P, P, P, P, P, I32, I32, I32, I32, P], C.c_int),
     "cdae_sgemm": ([C.POINTER(SgemmDesc), P], C.c_int),
-    "cdae_timestep_embedding": ([P, I32, P, F32, P, P, I32, I32, P], C.c_int),
+    "cdae_timestep_embedding": ([P, I32, I32, P, F32, P, P, I32, I32, P], C.c_int),
+    "cdae_step_tick": ([P, P, I32, P], C.c_int),
     "cdae_randn": ([P, I64, P, I32, F32, P], C.c_int),
     "cdae_silu_bwd": ([P, P, I64, P], C.c_int),
     "cdae_softplus_bwd": ([P, P, I64, P], C.c_int),

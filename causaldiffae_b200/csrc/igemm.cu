@@ -177,6 +177,8 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmKParams& p, const EpiC
           const uint32_t row = stg_base + buf * kSlabStride + r * (SLABW * 2);
           // GroupNorm-backward fusion: forward constants of this warp's image, staged by the manager warp
           const uint32_t abrow = cx.abs_base + (uint32_t)(buf * cx.abi + (q * 32) / (p.BW * p.BH)) * 512u;
+          const bool row_valid = (vmask >> lane) & 1u;
+          float gsum[SLABW / 8 > 0 ? SLABW / 8 : 1];
 #pragma unroll
           for (int j = 0; j < SLABW / 8; ++j) {
             float v[8];
@@ -198,9 +200,9 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmKParams& p, const EpiC
             // are stored unswizzled (their tensor maps use SWIZZLE_NONE)
             const uint32_t a = SLABW == 64 ? row + (uint32_t)((j ^ (r & 7)) << 4) : row + (uint32_t)(j << 4);
             if (gnb) {
+              float rv[8];
+              unpack8(lds8(a), rv);                      // x of this pixel row (the slab the manager warp fetched)
               if (p.gnb_silu) {                          // du = dy * silu'(u), u/2 = a x + b
-                float rv[8];
-                unpack8(lds8(a), rv);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const float4 c4 = lds128f(abrow + (uint32_t)(j * 8 + 2 * e) * 8u);      // {a0, b0, a1, b1}
@@ -209,6 +211,33 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmKParams& p, const EpiC
                   v[2 * e] *= d.x; v[2 * e + 1] *= d.y;
                 }
               }
+              // column sums over this warp's 32 pixel rows of {du, du*x} (du as stored: rounded to bf16), entirely in
+              // registers: a halving butterfly - every xor step trades half of the values for the partner's other half -
+              // leaves lane l with ONE fully reduced value: P (bit 4 clear) or Q (bit 4 set) of channel j*8 + ((l >> 1) & 7)
+              float val[16];
+              {
+                const bf16x8 pk = pack8(v);
+                unpack8(pk, val);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  if (!row_valid) val[e] = 0.f;
+                  val[8 + e] = val[e] * rv[e];
+                }
+              }
+              const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
+              float k8[8], k4[4], k2[2];
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                k8[i] = (h4 ? val[i + 8] : val[i]) + __shfl_xor_sync(0xffffffffu, h4 ? val[i] : val[i + 8], 16);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                k4[i] = (h3 ? k8[i + 4] : k8[i]) + __shfl_xor_sync(0xffffffffu, h3 ? k8[i] : k8[i + 4], 8);
+#pragma unroll
+              for (int i = 0; i < 2; ++i)
+                k2[i] = (h2 ? k4[i + 2] : k4[i]) + __shfl_xor_sync(0xffffffffu, h2 ? k4[i] : k4[i + 2], 4);
+              float k1 = (h1 ? k2[1] : k2[0]) + __shfl_xor_sync(0xffffffffu, h1 ? k2[0] : k2[1], 2);
+              k1 += __shfl_xor_sync(0xffffffffu, k1, 1);
+              gsum[j] = k1;
             } else if (p.has_resid) {
               float rv[8];
               unpack8(lds8(a), rv);
@@ -225,47 +254,29 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmKParams& p, const EpiC
             bulk_wait_read<NS - 2>();                 // every store but the newest NS-2 has finished reading smem
             if (sidx >= NS - 2) mbar_arrive(sfree_bar((sidx - (NS - 2)) % NS));
           }
-          if (SLABW == 64 && vmask != 0) {
+          if (gnb) {
+            // lanes with bit 0 clear own the pair's result: 8 channels (one per 8-channel chunk) of P or Q
+            if (vmask != 0 && !(lane & 1)) {
+              float* dst = p.gnb_ws + ((size_t)nimg * p.cout + co0 + ((lane >> 1) & 7)) * 2 + (lane >> 4);
+#pragma unroll
+              for (int j = 0; j < SLABW / 8; ++j) atomicAdd(dst + j * 16, gsum[j]);
+            }
+          } else if (SLABW == 64 && vmask != 0) {
             // column sums of the slab as stored (bf16): lane = channel pair, this warp's 32 rows; one 128-bit red
             // per lane into stats[nimg][co0 + 2*lane .. +1][sum, sumsq].  The buffer is recycled no earlier than the
             // named barrier of a later slab, i.e. after every thread has left this loop.
             const uint32_t sb = stg_base + buf * kSlabStride + (uint32_t)(q * 32) * 128u + (uint32_t)((lane & 3) << 2);
             const uint32_t cj = (uint32_t)(lane >> 2);
             float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
-            if (!gnb) {
 #pragma unroll 8
-              for (int i = 0; i < 32; ++i) {
-                uint32_t u = lds32(sb + (uint32_t)i * 128u + ((cj ^ (uint32_t)(i & 7)) << 4));
-                if (!((vmask >> i) & 1u)) u = 0u;
-                const float2 f = make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
-                s2 = __fadd2_rn(s2, f);
-                q2 = __ffma2_rn(f, f, q2);
-              }
-            } else {
-              // {sum du, sum du*x}: du as stored from the slab, the x pair of the same pixel from global memory (the slab
-              // the TMA just fetched: an L2 hit; its shared-memory copy was overwritten by du)
-              const bool in1 = co0 >= p.gnb_c0;
-              const int ldx = in1 ? p.gnb_ld1 : p.gnb_ld0;
-              const __nv_bfloat16* xg = (in1 ? p.gnb_x1 + (co0 - p.gnb_c0) : p.gnb_x0 + co0) + 2 * lane;
-#pragma unroll 8
-              for (int i = 0; i < 32; ++i) {
-                uint32_t u = lds32(sb + (uint32_t)i * 128u + ((cj ^ (uint32_t)(i & 7)) << 4));
-                uint32_t xu = 0u;
-                if ((vmask >> i) & 1u) {
-                  const int rr = q * 32 + i;
-                  const int bw = rr & (p.BW - 1), t = rr >> p.lgBW, bh = t & (p.BH - 1), bn = t >> p.lgBH;
-                  const size_t pix = ((size_t)(nn0 + bn) * p.OH + (h0 + bh)) * p.OW + (w0 + bw);
-                  xu = __ldg(reinterpret_cast<const uint32_t*>(xg + pix * ldx));
-                } else {
-                  u = 0u;
-                }
-                const float2 f = make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
-                const float2 xf = make_float2(__uint_as_float(xu << 16), __uint_as_float(xu & 0xffff0000u));
-                s2 = __fadd2_rn(s2, f);
-                q2 = __ffma2_rn(f, xf, q2);
-              }
+            for (int i = 0; i < 32; ++i) {
+              uint32_t u = lds32(sb + (uint32_t)i * 128u + ((cj ^ (uint32_t)(i & 7)) << 4));
+              if (!((vmask >> i) & 1u)) u = 0u;
+              const float2 f = make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+              s2 = __fadd2_rn(s2, f);
+              q2 = __ffma2_rn(f, f, q2);
             }
-            float* dst = (gnb ? p.gnb_ws : p.stats) + ((size_t)nimg * p.cout + co0 + 2 * lane) * 2;
+            float* dst = p.stats + ((size_t)nimg * p.cout + co0 + 2 * lane) * 2;
             atomicAdd(reinterpret_cast<float4*>(dst), make_float4(s2.x, q2.x, s2.y, q2.y));
           }
           ++sidx;

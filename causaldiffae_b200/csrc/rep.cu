@@ -208,16 +208,16 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmP p) {
 // ---------------------------------------------------------------- small elementwise pieces
 // timestep_embedding (ref nn.py:551-569): out[b, j] = cos(t_b f_j), out[b, half + j] = sin(t_b f_j); freqs come from the
 // host (computed exactly like the reference and uploaded once), t is int64 or fp32 (rescale_timesteps)
-__global__ void temb_kernel(const void* t, int t_is_float, const int64_t* __restrict__ map, float scale,
+__global__ void temb_kernel(const void* t, int t_is_float, int t_stride, const int64_t* __restrict__ map, float scale,
                             const float* __restrict__ freqs, float* __restrict__ out, int B, int half, int dim) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * dim) return;
   const int b = idx / dim, j = idx - b * dim;
   float tv;
   if (t_is_float) {
-    tv = reinterpret_cast<const float*>(t)[b];
+    tv = reinterpret_cast<const float*>(t)[b * t_stride];
   } else {
-    int64_t ti = reinterpret_cast<const int64_t*>(t)[b];
+    int64_t ti = reinterpret_cast<const int64_t*>(t)[b * t_stride];
     if (map) ti = map[ti];                       // _WrappedModel: respaced step -> original step (ref respace.py:119-124)
     tv = (float)ti;
     if (scale != 0.f) tv *= scale;               // rescale_timesteps: * 1000 / T in fp32
@@ -502,6 +502,11 @@ __global__ void __launch_bounds__(256) randn_kernel(float* __restrict__ out, int
   }
 }
 __global__ void randn_tick_kernel(uint64_t* state, uint64_t groups) { state[1] += groups; }
+// the sampler's step counters (int64 for the embedding kernel, int32 for cdae_ddim_step) move together on the device
+__global__ void step_tick_kernel(int64_t* a, int32_t* b, int delta) {
+  if (a) *a += delta;
+  if (b) *b += delta;
+}
 
 }  // namespace cdae
 using namespace cdae;
@@ -516,6 +521,12 @@ extern "C" int cdae_randn(float* out, int64_t n, void* state, int bernoulli, flo
   CDAE_CHECK_LAUNCH("randn_kernel");
   randn_tick_kernel<<<1, 1, 0, (cudaStream_t)s>>>(reinterpret_cast<uint64_t*>(state), (uint64_t)groups);
   CDAE_CHECK_LAUNCH("randn_tick_kernel");
+  return CDAE_OK;
+}
+
+extern "C" int cdae_step_tick(int64_t* step64, int32_t* step32, int delta, cdae_stream s) {
+  step_tick_kernel<<<1, 1, 0, (cudaStream_t)s>>>(step64, step32, delta);
+  CDAE_CHECK_LAUNCH("step_tick_kernel");
   return CDAE_OK;
 }
 
@@ -559,12 +570,12 @@ extern "C" int cdae_sgemm(const cdae_sgemm_desc* d, cdae_stream s) {
   return CDAE_OK;
 }
 
-extern "C" int cdae_timestep_embedding(const void* t, int t_is_float, const int64_t* map, float scale, const float* freqs,
-                                       float* out, int B, int dim, cdae_stream s) {
+extern "C" int cdae_timestep_embedding(const void* t, int t_is_float, int t_stride, const int64_t* map, float scale,
+                                       const float* freqs, float* out, int B, int dim, cdae_stream s) {
   if (B == 0) return CDAE_OK;
-  CDAE_CHECK_ARG(t && freqs && out && dim >= 2, "timestep_embedding: bad arguments");
+  CDAE_CHECK_ARG(t && freqs && out && dim >= 2 && (t_stride == 0 || t_stride == 1), "timestep_embedding: bad arguments");
   const int n = B * dim;
-  temb_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)s>>>(t, t_is_float, map, scale, freqs, out, B, dim / 2, dim);
+  temb_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)s>>>(t, t_is_float, t_stride, map, scale, freqs, out, B, dim / 2, dim);
   CDAE_CHECK_LAUNCH("temb_kernel");
   return CDAE_OK;
 }

@@ -28,10 +28,14 @@ USE_GRAPHS = os.environ.get("CDAE_GRAPHS", "1") != "0"
 # GroupNorm statistics from the producing conv's epilogue + one streaming normalise pass (0: reduce inside the GN kernel)
 FUSED_GN_STATS = os.environ.get("CDAE_FUSED_GN_STATS", "1") != "0"
 # GroupNorm backward statistics from the epilogue of the data-gradient conv that produces the norm's output gradient + one
-# streaming apply pass (0: the resident cluster kernel reduces and applies in one launch).  Round 1 measured a two-pass
-# streaming backward that re-read dy and x (profiles/r1_gn_bench_bwd_stream.log): slower than the resident kernel; this is
-# the version without the second read.
-FUSED_GN_BWD = os.environ.get("CDAE_FUSED_GN_BWD", "1") != "0"
+# streaming apply pass (cdae_igemm_desc.gnb_*, cdae_gn_bwd_apply) instead of the resident cluster kernel that reduces and
+# applies in one launch.  Built, parity-tested (tests/test_kernels_gpu.py::test_groupnorm_backward_from_dgrad_epilogue, the
+# per-layer and model-level tests pass with it on) and MEASURED on B200 (profiles/r2_gnb_bench.log, r2_ncu_igemm3_gnb_*):
+# the norm's own backward gets faster (128 ch @ 64x64: 76 -> 57 us, 0.40 -> 0.54 of the HBM peak) but the conv pays more than
+# that in its epilogue (67 -> 124 us): silu' + the register butterfly add ~1400 instructions per thread and slab to the ONE
+# epilogue warp per scheduler, which cannot hide its own latencies (tensor pipe 53 % -> 28 %).  Whole step 19.25 -> 20.3 ms.
+# Off by default until the epilogue runs two warps per scheduler.
+FUSED_GN_BWD = os.environ.get("CDAE_FUSED_GN_BWD", "0") != "0"
 
 
 def _round_up(v, m):

@@ -317,7 +317,27 @@ class GaussianDiffusion:
 
     def ddim_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, model_kwargs=None,
                          device=None, progress=False, eta=0.0, w=None):
-        """ref :598-630"""
+        """ref :598-630.  With this package's UNet the loop is sampling.DdimRunner (one CUDA graph per step, device-side step
+        counter, guidance as one 2B batch); anything else takes the step-by-step path below."""
+        from .sampling import DdimRunner
+        inner = getattr(model, "model", model) if type(model).__name__ == "_WrappedModel" else model
+        if DdimRunner.supported(self, inner, denoised_fn, model_kwargs):
+            if device is None:
+                device = next(inner.parameters()).device
+            x_T = noise if noise is not None else th.randn(*shape, device=device)
+            kw = model_kwargs or {}
+            rows = DdimRunner.MAX_ROWS // (2 if w is not None else 1)      # torso rows per replay (guidance doubles them)
+            outs = []
+            with th.no_grad():
+                for i in range(0, int(shape[0]), rows):
+                    n = min(rows, int(shape[0]) - i)
+                    key = (id(inner), n, w is not None, bool(clip_denoised), float(eta))
+                    runners = self.__dict__.setdefault("_ddim_runners", {})
+                    r = runners.get(key)
+                    if r is None or r.eng is not inner.engine:
+                        r = runners[key] = DdimRunner(self, inner, n, w is not None, clip_denoised, eta)
+                    outs.append(r(x_T[i:i + n], {k: v[i:i + n] for k, v in kw.items()}, w))
+            return outs[0] if len(outs) == 1 else th.cat(outs, dim=0)
         final = None
         for sample in self.ddim_sample_loop_progressive(model, shape, noise=noise, clip_denoised=clip_denoised,
                                                         denoised_fn=denoised_fn, model_kwargs=model_kwargs,

@@ -468,11 +468,16 @@ def linear_bwd(x, W, dy, dW, db, dx=None, silu_in=False, dx_accumulate=False):
 
 
 def timestep_embedding(t, freqs, out, tmap=None, scale=0.0):
-    dim = out.shape[1]
-    assert t.is_cuda and t.dtype in (torch.int64, torch.float32) and t.is_contiguous()
-    check(_lib.lib().cdae_timestep_embedding(ptr(t), int(t.dtype == torch.float32), ptr(tmap), float(scale), ptr(freqs),
-                                             ptr(out), t.shape[0], dim, stream()))
+    """t: [B] int64 / fp32, or ONE element (a device-side loop counter) broadcast over the B rows of `out`"""
+    B, dim = out.shape
+    assert t.is_cuda and t.dtype in (torch.int64, torch.float32) and t.is_contiguous() and t.numel() in (1, B)
+    check(_lib.lib().cdae_timestep_embedding(ptr(t), int(t.dtype == torch.float32), 1 if t.numel() == B else 0,
+                                             ptr(tmap), float(scale), ptr(freqs), ptr(out), B, dim, stream()))
     return out
+
+
+def step_tick(step64, step32, delta):
+    check(_lib.lib().cdae_step_tick(ptr(step64), ptr(step32), int(delta), stream()))
 
 
 def randn_(out, state, bernoulli=False, keep_prob=0.5):

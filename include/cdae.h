@@ -223,9 +223,13 @@ typedef struct {
 int cdae_sgemm(const cdae_sgemm_desc* d, cdae_stream s);
 /* timestep_embedding (nn.py:551-569): out[b] = [cos(t_b f) | sin(t_b f)] (+ a zero column when dim is odd); freqs: device
  * fp32 [dim/2] computed on the host exactly like the reference; t int64 or (t_is_float) fp32; map (optional): respaced ->
- * original step table applied first, scale (0 = off): rescale_timesteps factor 1000/T (respace.py:119-124) */
-int cdae_timestep_embedding(const void* t, int t_is_float, const int64_t* map, float scale, const float* freqs, float* out,
-                            int B, int dim, cdae_stream s);
+ * original step table applied first, scale (0 = off): rescale_timesteps factor 1000/T (respace.py:119-124); t_stride 0 = one
+ * timestep for the whole batch (a device scalar: the sampling loop's counter) */
+int cdae_timestep_embedding(const void* t, int t_is_float, int t_stride, const int64_t* map, float scale, const float* freqs,
+                            float* out, int B, int dim, cdae_stream s);
+/* device-side step counters of a graph-replayed sampling loop (gaussian_diffusion.py:632-680 `for i in indices`): both
+ * (either may be NULL) += delta */
+int cdae_step_tick(int64_t* step64, int32_t* step32, int delta, cdae_stream s);
 /* counter-based normal / Bernoulli draws (Philox4x32-10 + Box-Muller), replayable inside a CUDA graph: state = device
  * uint64 {seed, offset}; the launch advances the offset.  Replaces th.randn_like / th.bernoulli at gaussian_diffusion.py:790,
  * nn.py:464, unet.py:601 in throughput runs (parity runs inject the reference's CPU-generator draws instead). */

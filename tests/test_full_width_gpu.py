@@ -119,11 +119,15 @@ def layer_cases(model):
     return cases
 
 
-def test_full_width_per_layer_forward_and_backward():
+@pytest.mark.parametrize("fused_gn_bwd", [False, True], ids=["gn-bwd-resident", "gn-bwd-from-dgrad-epilogue"])
+def test_full_width_per_layer_forward_and_backward(fused_gn_bwd, monkeypatch):
     """north_star: per-layer relative L2 <= 1e-2 in bf16 - forward output, input gradient(s), FiLM gradient and every
-    parameter gradient of the layer, teacher-forced (both sides get the same fp32 input / output gradient)"""
+    parameter gradient of the layer, teacher-forced (both sides get the same fp32 input / output gradient).  Both GroupNorm
+    backward variants: the resident reduce-and-apply kernel (default) and the statistics from the data-gradient epilogue."""
+    from causaldiffae_b200 import engine as eng_mod
     from causaldiffae_b200.engine import run_layer_train
     from oracle import model as om
+    monkeypatch.setattr(eng_mod, "FUSED_GN_BWD", fused_gn_bwd)
     model, diff, cfg, sd, odiff = build(CFG2_FULL, PENDULUM)
     model.train()
     eng = model.engine
