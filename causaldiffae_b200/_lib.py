@@ -34,7 +34,8 @@ class IgemmDesc(C.Structure):
                 ("bn", C.c_int32),
                 ("stats", C.c_void_p),
                 ("gnb_ws", C.c_void_p), ("gnb_ab", C.c_void_p), ("gnb_x0", C.c_void_p), ("gnb_x1", C.c_void_p),
-                ("gnb_c0", C.c_int32), ("gnb_ld0", C.c_int32), ("gnb_ld1", C.c_int32), ("gnb_silu", C.c_int32)]
+                ("gnb_c0", C.c_int32), ("gnb_ld0", C.c_int32), ("gnb_ld1", C.c_int32), ("gnb_silu", C.c_int32),
+                ("bias_img", C.c_void_p), ("bias_img_ld", C.c_int32)]
 
 
 class WgradDesc(C.Structure):
@@ -84,7 +85,8 @@ _SIGS = {
     "cdae_upsample2x": ([P, P, I32, I32, I32, I32, P], C.c_int),
     "cdae_sumpool2x": ([P, P, I32, I32, I32, I32, I32, P], C.c_int),
     "cdae_zero_insert2x": ([P, P, I32, I32, I32, I32, P], C.c_int),
-    "cdae_colsum": ([P, P, I64, I32, I32, P], C.c_int),
+    "cdae_colsum": ([P, P, I64, I32, I32, I32, I32, P], C.c_int),
+    "cdae_dropout": ([P, I64, P, I64, P, P], C.c_int),
     "cdae_gn_fwd": ([P, I32, P, I32, I32, I32, P, P, P, I32, I32, I32, P, P, P, P], C.c_int),
     "cdae_gn_apply_fwd": ([P, I32, P, P, I32, P, I32, I32, P, P, P, I32, I32, I32, P, P, P, P, P], C.c_int),
     "cdae_gn_bwd": ([P, P, I32, P, I32, I32, I32, P, P, P, I32, I32, I32, P, P, P, P, P, I32, P, P, P, P], C.c_int),

@@ -75,6 +75,7 @@ struct alignas(64) IgemmKParams {
   void* out;
   const float* bias;
   const float* bias2;
+  const float* bias_img; int bias_img_ld;   // optional per-(image, channel) additive term: + bias_img[n * ld + co]
   float* stats;      // optional fp32 [Nimg][cout][2]: per-(image, channel) sum / sum of squares of the stored bf16 output
   // GroupNorm-backward fusion of a data-gradient launch (cdae_igemm_desc.gnb_*): the output dy is the gradient w.r.t. the
   // OUTPUT of a GroupNorm(+FiLM)(+SiLU) whose input x = concat(gnb_x0, gnb_x1) has the same pixel grid.  The epilogue
@@ -193,6 +194,13 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmKParams& p, const EpiC
               if (bias2) {
                 const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias2 + co0 + j * 8));
                 const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias2 + co0 + j * 8 + 4));
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              }
+              if (p.bias_img) {        // additive timestep conditioning (use_scale_shift_norm=False): + emb_out[image, channel]
+                const int nrow = min(nn0 + r / (p.BW * p.BH), p.Nimg - 1);
+                const float* bi = p.bias_img + (size_t)nrow * p.bias_img_ld + co0 + j * 8;
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bi));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bi + 4));
                 v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
               }
             }
@@ -783,6 +791,9 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
   kp.in_stride = es; kp.Nimg = d->N; kp.OHt = OHt; kp.OWt = OWt;
   kp.OH = d->OH; kp.OW = d->OW; kp.cout = d->cout; kp.out_mode = d->out_mode;
   kp.out = d->out; kp.bias = d->bias; kp.bias2 = d->bias2; kp.has_resid = d->resid != nullptr;
+  kp.bias_img = d->bias_img; kp.bias_img_ld = d->bias_img_ld;
+  CDAE_CHECK_SHAPE(!d->bias_img || (d->out_mode == 0 && d->bias_img_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(d->bias_img) & 15) == 0),
+                   "igemm: the per-image bias needs NHWC output, a pitch %% 4 == 0 and a 16-byte aligned pointer");
   kp.stats = d->stats;
   if (d->gnb_ws) {
     CDAE_CHECK_ARG(d->gnb_x0 && (!d->gnb_silu || d->gnb_ab), "igemm: GroupNorm-backward fusion needs x0 (and the constant table with SiLU)");

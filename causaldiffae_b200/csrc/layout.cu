@@ -115,9 +115,11 @@ __global__ void zero_insert2x_kernel(const bf16x8* __restrict__ x, bf16x8* __res
 
 // column sums: block = 8 vector lanes (64 channels) x 32 rows
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out,
-                                                     int64_t rows, int C, int ld) {
+                                                     int64_t rows, int C, int ld, int out_ld) {
   const int vl = threadIdx.x & 7, rl = threadIdx.x >> 3;
   const int c = blockIdx.x * 64 + vl * 8;
+  x += (size_t)blockIdx.z * rows * ld;          // group g: its own [rows, C] matrix and its own output row
+  out += (size_t)blockIdx.z * out_ld;
   float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (c < C) {
     for (int64_t r = blockIdx.y * 32 + rl; r < rows; r += (int64_t)gridDim.y * 32) {
@@ -200,16 +202,17 @@ extern "C" int cdae_zero_insert2x(const void* x, void* out, int N, int H, int W,
   return CDAE_OK;
 }
 
-extern "C" int cdae_colsum(const void* x, float* out, int64_t rows, int C, int ld, cdae_stream s) {
+extern "C" int cdae_colsum(const void* x, float* out, int64_t rows, int C, int ld, int groups, int out_ld, cdae_stream s) {
   CDAE_CHECK_ARG(x && out, "colsum: null pointer");
-  CDAE_CHECK_SHAPE(C % 8 == 0 && ld % 8 == 0, "colsum: C, ld %% 8");
+  CDAE_CHECK_SHAPE(C % 8 == 0 && ld % 8 == 0 && groups >= 1 && groups <= 65535, "colsum: C, ld %% 8; 1 <= groups <= 65535");
   if (rows == 0) return CDAE_OK;
   int gx = (C + 63) / 64;
   int64_t gy = ceil_div(rows, 32 * 16);
-  int64_t cap = (int64_t)kNumSMs * 4 / gx; if (cap < 1) cap = 1;
+  int64_t cap = (int64_t)kNumSMs * 4 / ((int64_t)gx * groups); if (cap < 1) cap = 1;
   if (gy > cap) gy = cap;
   if (gy < 1) gy = 1;
-  colsum_kernel<<<dim3(gx, (unsigned)gy), 256, 0, (cudaStream_t)s>>>((const __nv_bfloat16*)x, out, rows, C, ld);
+  colsum_kernel<<<dim3(gx, (unsigned)gy, (unsigned)groups), 256, 0, (cudaStream_t)s>>>((const __nv_bfloat16*)x, out, rows, C, ld,
+                                                                                        out_ld);
   CDAE_CHECK_LAUNCH("colsum_kernel");
   return CDAE_OK;
 }

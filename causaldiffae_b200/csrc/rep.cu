@@ -502,6 +502,32 @@ __global__ void __launch_bounds__(256) randn_kernel(float* __restrict__ out, int
   }
 }
 __global__ void randn_tick_kernel(uint64_t* state, uint64_t groups) { state[1] += groups; }
+
+// inverted dropout in place, 8 bf16 per thread: one Philox call = eight 16-bit uniforms
+__global__ void __launch_bounds__(256) dropout_kernel(uint4* __restrict__ x, int64_t ngroups, const uint64_t* __restrict__ state,
+                                                      uint64_t layer_off, const float* __restrict__ pp) {
+  const float p = *pp;
+  if (p <= 0.f) return;                                        // eval mode: identity
+  const uint64_t seed = state[0], base = state[1] + layer_off;
+  const uint32_t thr = (uint32_t)(p * 65536.0f);
+  const float scale = 1.0f / (1.0f - p);
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < ngroups; g += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t ctr = base + (uint64_t)g;
+    uint32_t r[4];
+    philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), 0x5eedu, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    uint4 v = x[g];
+    uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const bool k0 = (r[i] & 0xffffu) >= thr, k1 = (r[i] >> 16) >= thr;
+      const float lo = k0 ? __uint_as_float(w[i] << 16) * scale : 0.f;
+      const float hi = k1 ? __uint_as_float(w[i] & 0xffff0000u) * scale : 0.f;
+      const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    x[g] = v;
+  }
+}
 // the sampler's step counters (int64 for the embedding kernel, int32 for cdae_ddim_step) move together on the device
 __global__ void step_tick_kernel(int64_t* a, int32_t* b, int delta) {
   if (a) *a += delta;
@@ -521,6 +547,18 @@ extern "C" int cdae_randn(float* out, int64_t n, void* state, int bernoulli, flo
   CDAE_CHECK_LAUNCH("randn_kernel");
   randn_tick_kernel<<<1, 1, 0, (cudaStream_t)s>>>(reinterpret_cast<uint64_t*>(state), (uint64_t)groups);
   CDAE_CHECK_LAUNCH("randn_tick_kernel");
+  return CDAE_OK;
+}
+
+extern "C" int cdae_dropout(void* x, int64_t n, const void* state, int64_t layer_offset, const float* p, cdae_stream s) {
+  if (n == 0) return CDAE_OK;
+  CDAE_CHECK_ARG(x && state && p, "dropout: null pointer");
+  CDAE_CHECK_SHAPE(n % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "dropout: n %% 8 and 16-byte alignment required");
+  const int64_t groups = n / 8;
+  int64_t blocks = (groups + 255) / 256; if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  dropout_kernel<<<(int)blocks, 256, 0, (cudaStream_t)s>>>(reinterpret_cast<uint4*>(x), groups,
+                                                          reinterpret_cast<const uint64_t*>(state), (uint64_t)layer_offset, p);
+  CDAE_CHECK_LAUNCH("dropout_kernel");
   return CDAE_OK;
 }
 

@@ -87,6 +87,11 @@ class Plan:
         self.fwd_graph = self.bwd_graph = None
         self.runs = 0
         self.generation, self.pending = 0, False     # which forward the saved activations belong to / awaits backward
+        # nn.Dropout of the ResBlocks (ref unet.py:157): counter-based masks, {seed, base} on the device; the base moves on at
+        # the start of every forward, so the backward of the same step regenerates the same masks; p = 0 in eval mode
+        self.drop_state = th.tensor([int(th.initial_seed()) & 0x7fffffffffffffff, 0], device=self.dev, dtype=th.int64)
+        self.drop_p = th.zeros(1, device=self.dev)
+        self.drop_p_host, self.drop_groups = 0.0, 0
         self.n_fwd_launch = self.n_bwd_launch = 0
         # per-(image, channel) GroupNorm sums accumulated by conv epilogues: carved from a few big chunks that the
         # first node of the forward graph zeroes
@@ -112,6 +117,13 @@ class Plan:
     def _zero_stats(self):
         for c in self.stat_chunks:
             ops.zero_(c)
+        if self.drop_groups:
+            ops.step_tick(self.drop_state[1:], None, self.drop_groups)
+
+    def set_dropout(self, p):
+        if p != self.drop_p_host:
+            self.drop_p.fill_(p)
+            self.drop_p_host = p
 
     def alloc_bwd_ws(self, B, C):
         """zeroed-at-backward-start fp32 [B, C, 2] {sum du, sum du*x} accumulator of one fused GroupNorm backward"""
@@ -400,7 +412,7 @@ class Engine:
         return self.grad_of(p)
 
     def plan_conv(self, pl, cw, srcs, out, ksize, stride=1, resid=None, skip=None, skip_srcs=None, out_mode=0,
-                  need_dgrad=True, stats=False):
+                  need_dgrad=True, stats=False, bias_img=None):
         """out = conv_ksize(concat(srcs)) + bias [+ resid] [+ conv1x1_skip(concat(skip_srcs)) + bias_skip]
         stats: `out` feeds a GroupNorm - let the epilogue accumulate its per-(image, channel) sums (out.stats)."""
         chans = [s.shape[3] for s in srcs]
@@ -418,7 +430,7 @@ class Engine:
             st = out.stats = pl.alloc_stats(out.shape[0], cw.cout)
         d = ops.make_igemm_desc([s.t for s in all_srcs], segs, cw.fwd, out if out_mode == 1 else out.t, cw.cout,
                                 in_stride=stride, bias=cw.bias, bias2=bias2, resid=resid.t if resid is not None else None,
-                                out_mode=out_mode, stats=st)
+                                out_mode=out_mode, stats=st, bias_img=bias_img)
         pl.add_fwd(lambda: ops.igemm(d))
         return chans
 
@@ -513,9 +525,20 @@ class Engine:
         st1 = (pl.alloc((B, 32), th.float32), pl.alloc((B, 32), th.float32))
         st2 = (pl.alloc((B, 32), th.float32), pl.alloc((B, 32), th.float32))
         x1t = x1.t if x1 is not None else None
+        ssn = rb.use_scale_shift_norm
         self.plan_gn_fwd(pl, x0, x1, gn1, a1, st1)
-        self.plan_conv(pl, cw1, [a1], h1, 3, stats=True)
-        self.plan_gn_fwd(pl, h1, None, gn2, a2, st2, film=film, film_off=foff)
+        if ssn:      # h = GN(conv1(.)) * (1 + scale) + shift  (ref unet.py:190-194)
+            self.plan_conv(pl, cw1, [a1], h1, 3, stats=True)
+            self.plan_gn_fwd(pl, h1, None, gn2, a2, st2, film=film, film_off=foff)
+        else:        # h = GN(conv1(.) + emb_out[..., None, None])  (ref unet.py:195-197): the addend rides in conv1's epilogue
+            self.plan_conv(pl, cw1, [a1], h1, 3, stats=True, bias_img=film[:, foff:foff + cout])
+            self.plan_gn_fwd(pl, h1, None, gn2, a2, st2)
+        drop_off = None
+        if rb.dropout and pl.train:     # nn.Dropout between SiLU and conv2 (ref unet.py:157): in place on a2, masks regenerated in bwd
+            drop_off = pl.drop_groups
+            pl.drop_groups += a2.t.numel() // 8
+            a2.gnb = None               # d(a2) has to be masked before the norm's backward sees it
+            pl.add_fwd(lambda: ops.dropout_(a2.t, pl.drop_state, drop_off, pl.drop_p))
         srcs_x = [x0] + ([x1] if x1 is not None else [])
         if has_skip:
             self.plan_conv(pl, cw2, [a2], out, 3, skip=sk, skip_srcs=srcs_x, stats=True)
@@ -542,7 +565,15 @@ class Engine:
                         off += c
                 # GN2 (+FiLM) backward -> dh1
                 dh1 = h1.grad()
-                fns.append(self.plan_gn_bwd(a2, h1, None, gn2, st2, dh1, film=film, film_off=foff, dfilm=dfilm))
+                if drop_off is not None:
+                    da2 = a2.grad()
+                    fns.append(lambda: ops.dropout_(da2, pl.drop_state, drop_off, pl.drop_p))
+                if ssn:
+                    fns.append(self.plan_gn_bwd(a2, h1, None, gn2, st2, dh1, film=film, film_off=foff, dfilm=dfilm))
+                else:
+                    fns.append(self.plan_gn_bwd(a2, h1, None, gn2, st2, dh1))
+                    # d emb_out[b, c] = sum over pixels of d(conv1 output)[b, :, :, c]
+                    fns.append(lambda: ops.colsum_(dh1, dfilm[:, foff:foff + cout], c=cout, groups=B, out_ld=dfilm.shape[1]))
                 h1.g_written = True
                 # conv1
                 fns += self.plan_conv_bwd(pl, cw1, [a1], dh1, 3)
@@ -736,6 +767,8 @@ class _Torso(th.autograd.Function):
         B = x.shape[0]
         pl = eng.plan(B, train, fresh=True)
         eng.pack()
+        if pl.drop_groups:
+            pl.set_dropout(float(eng.model.dropout) if eng.model.training else 0.0)
         pl.x_in.copy_(x)
         pl.film_in.copy_(film)
         pl.forward()
@@ -805,7 +838,7 @@ def _channel_stats(t_bf16):
     return th.stack([f.sum(dim=(1, 2)), (f * f).sum(dim=(1, 2))], dim=-1).contiguous()
 
 
-def run_layer_train(mod, xs, emb=None, dout=None):
+def run_layer_train(mod, xs, emb=None, dout=None, dropout_p=None):
     """Teacher-forced forward AND backward of ONE torso layer through the same planned kernels (and the same kernel
     variants: statistics epilogue, streaming GroupNorm, two-source concat) the full torso launches.
     xs: NCHW fp32 tensor, or a tuple (h, skip) for the skip-concatenated ResBlocks of the output path; dout: NCHW fp32
@@ -841,6 +874,9 @@ def run_layer_train(mod, xs, emb=None, dout=None):
         out = eng.plan_downsample(pl, mod, tin[0])
     else:
         raise _lib.CdaeError(f"run_layer_train: unsupported module {type(mod)}")
+    if dropout_p is not None:
+        pl.set_dropout(float(dropout_p))
+    run_layer_train.last_plan = pl          # tests read the dropout state (to regenerate the masks) from here
     pl._run_fwd_eager()
     res = out.t.float().permute(0, 3, 1, 2).contiguous()
     if dout is None:

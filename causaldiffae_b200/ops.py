@@ -138,12 +138,22 @@ def zero_insert2x(x, out=None):
     return out
 
 
-def colsum_(x2d, out, c=None):
-    """out[c] += sum_rows x2d[:, c]  (bias gradients)."""
+def colsum_(x2d, out, c=None, groups=1, out_ld=0):
+    """out[c] += sum_rows x2d[:, c]  (bias gradients); groups > 1: x2d is `groups` consecutive row blocks and
+    out[g * out_ld + c] gets the sums of block g (per-image sums)."""
     _bf16c(x2d)
     rows, ld = x2d.reshape(-1, x2d.shape[-1]).shape
-    check(_lib.lib().cdae_colsum(ptr(x2d), ptr(out), rows, c if c is not None else ld, ld, stream()))
+    assert rows % groups == 0
+    check(_lib.lib().cdae_colsum(ptr(x2d), ptr(out), rows // groups, c if c is not None else ld, ld, groups, out_ld, stream()))
     return out
+
+
+def dropout_(x, state, layer_offset, p_dev):
+    """inverted dropout in place (bf16); the same call on the gradient is its backward.  state: device int64[2] {seed, base},
+    p_dev: device fp32[1] (0 = identity)"""
+    _bf16c(x)
+    check(_lib.lib().cdae_dropout(ptr(x), x.numel(), ptr(state), int(layer_offset), ptr(p_dev), stream()))
+    return x
 
 
 def gather_images(images_u8, idx, labels=None, mode=0, out=None, out_labels=None):
@@ -271,7 +281,7 @@ def conv_segments(chans, ksize=3, transposed=False, wk0=0, src0=0):
 
 
 def make_igemm_desc(srcs, segs, wgt, out, cout, in_stride=1, bias=None, resid=None, out_mode=0, sps=1, ooh=0, oow=0,
-                    bn=0, out_hw=None, bias2=None, stats=None, gnb=None):
+                    bn=0, out_hw=None, bias2=None, stats=None, gnb=None, bias_img=None):
     """Fill a cdae_igemm_desc.  srcs: bf16 [N,H,W,C]; wgt: bf16 [rows, K]; out: bf16 NHWC or fp32 NCHW (out_mode 1).
     stats: optional fp32 [N, cout, 2] that the epilogue ACCUMULATES per-(image, channel) sum / sum of squares of the
     stored output into (zero it first) - the GroupNorm statistics of the consumer, see gn_apply_fwd."""
@@ -316,7 +326,10 @@ def make_igemm_desc(srcs, segs, wgt, out, cout, in_stride=1, bias=None, resid=No
         d.gnb_ws, d.gnb_ab, d.gnb_x0, d.gnb_x1 = ptr(ws), ptr(ab), ptr(x0), ptr(x1)
         d.gnb_c0, d.gnb_ld0, d.gnb_ld1 = x0.shape[3], x0.shape[3], (x1.shape[3] if x1 is not None else 0)
         d.gnb_silu = int(bool(gnb.get("silu", True)))
-    d._keep = (srcs, wgt, out, bias, bias2, resid, stats, gnb)   # keep tensors alive as long as the descriptor
+    if bias_img is not None:       # fp32 [N, >= cout] view (row pitch = stride(0)): + bias_img[n, co] in the epilogue
+        assert bias_img.dtype == torch.float32 and bias_img.stride(1) == 1 and bias_img.shape[0] == N
+        d.bias_img, d.bias_img_ld = bias_img.data_ptr(), bias_img.stride(0)
+    d._keep = (srcs, wgt, out, bias, bias2, resid, stats, gnb, bias_img)   # keep tensors alive as long as the descriptor
     return d
 
 

@@ -172,7 +172,8 @@ class EncoderRunner:
             return x, (ci * h * w, h * w, w, 1), None
         return st.raw[l - 1], (h * w * ci, 1, w * ci, ci), st.ab[l - 1]
 
-    def forward(self, st, x, train):
+    def features(self, st, x, train):
+        """the conv stack: [conv3x3 s2 -> BatchNorm2d -> LeakyReLU] x L -> th.flatten  (ref nn.py:100-104) -> st.hfeat [B, C*P]"""
         B = x.shape[0]
         for l, (ci, co, h, w, oh, ow) in enumerate(st.geo):
             conv, bn = self.enc.encoder[l][0], self.enc.encoder[l][1]
@@ -184,6 +185,10 @@ class EncoderRunner:
                       colstats=st.stats[l] if train else None, splits=1, geo=(*strides, ci, h, w, oh, ow, ab))
             ops.bn_finalize(st.stats[l], M, bn, train, st.ab[l], st.ms[l])
         ops.enc_head(st.raw[-1], st.ab[-1], st.hfeat, B, st.P, st.C)
+        return st.hfeat
+
+    def forward(self, st, x, train):
+        self.features(st, x, train)
         e = self.enc
         ops.linear_fwd(st.hfeat, e.fc_mu.weight, e.fc_mu.bias, st.mu)
         ops.linear_fwd(st.hfeat, e.fc_var.weight, e.fc_var.bias, st.var, act_out=1)
@@ -191,10 +196,15 @@ class EncoderRunner:
 
     def backward(self, st, x, dmu, dvar):
         """dmu / dvar: gradients w.r.t. mu and var = softplus(.) + 1e-8 (dvar is consumed: overwritten in place)"""
-        e, B = self.enc, x.shape[0]
+        e = self.enc
         ops.softplus_bwd_(dvar, st.var)
         ops.linear_bwd(st.hfeat, e.fc_mu.weight, dmu, _g(e.fc_mu.weight), _g(e.fc_mu.bias), dx=st.dh)
         ops.linear_bwd(st.hfeat, e.fc_var.weight, dvar, _g(e.fc_var.weight), _g(e.fc_var.bias), dx=st.dh, dx_accumulate=True)
+        self.features_backward(st, x)
+
+    def features_backward(self, st, x):
+        """st.dh (gradient w.r.t. the flattened features) -> every conv / BatchNorm parameter gradient of the stack"""
+        e, B = self.enc, x.shape[0]
         ops.enc_head(st.dh, None, st.dact[-1], B, st.P, st.C, backward=True)
         for l in reversed(range(len(st.geo))):
             ci, co, h, w, oh, ow = st.geo[l]

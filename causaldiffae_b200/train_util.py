@@ -208,6 +208,8 @@ class FusedStep:
         from .engine import USE_GRAPHS, _capture
         self.pl.generation += 1            # a pending autograd backward on this plan must fail loudly, not read these buffers
         self.pl.pending = False
+        if self.pl.drop_groups:
+            self.pl.set_dropout(float(self.m.dropout))
         if USE_GRAPHS and self.runs >= 2:
             if self.graph is None:
                 from . import _lib

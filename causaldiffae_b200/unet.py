@@ -78,14 +78,10 @@ class ResBlock(TimestepBlock):
         self.channels, self.emb_channels, self.dropout = channels, emb_channels, dropout
         self.out_channels = out_channels or channels
         self.use_conv, self.use_checkpoint, self.use_scale_shift_norm = use_conv, use_checkpoint, use_scale_shift_norm
-        if dropout:
-            raise NotImplementedError("dropout > 0 is not built (every reference launch line uses dropout 0.0)")
-        if not use_scale_shift_norm:
-            raise NotImplementedError("additive timestep conditioning is not built (reference default/launch lines use "
-                                      "use_scale_shift_norm=True)")
         self.in_layers = nn.Sequential(normalization(channels), SiLU(),
                                        conv_nd(dims, channels, self.out_channels, 3, padding=1))
-        self.emb_layers = nn.Sequential(SiLU(), linear(emb_channels, 2 * self.out_channels))
+        self.emb_layers = nn.Sequential(SiLU(), linear(emb_channels, 2 * self.out_channels if use_scale_shift_norm
+                                                       else self.out_channels))
         self.out_layers = nn.Sequential(normalization(self.out_channels), SiLU(), nn.Dropout(p=dropout),
                                         zero_module(conv_nd(dims, self.out_channels, self.out_channels, 3, padding=1)))
         if self.out_channels == channels:

@@ -88,8 +88,14 @@ int cdae_upsample2x(const void* x, void* out, int N, int H, int W, int C, cdae_s
 int cdae_sumpool2x(const void* dy, void* dx, int N, int H, int W, int C, int accumulate, cdae_stream s);
 /* zero-insertion (adjoint gather of a stride-2 conv): out[n,2h,2w,:] = x[n,h,w,:], zeros elsewhere */
 int cdae_zero_insert2x(const void* x, void* out, int N, int H, int W, int C, cdae_stream s);
-/* column sums of a [rows, C] bf16 matrix accumulated into fp32 (bias gradients) */
-int cdae_colsum(const void* x_bf16, float* out, int64_t rows, int C, int ld, cdae_stream s);
+/* column sums of `groups` consecutive [rows, C] bf16 matrices (pitch ld) accumulated into fp32 out[g * out_ld + c]
+ * (bias gradients; per-image sums = the gradient of the additive timestep conditioning) */
+int cdae_colsum(const void* x_bf16, float* out, int64_t rows, int C, int ld, int groups, int out_ld, cdae_stream s);
+/* inverted dropout in place on a bf16 tensor (unet.py:157 nn.Dropout between SiLU and the ResBlock's second conv): element i
+ * is kept (and scaled by 1/(1-p)) iff the counter-based generator says so for (seed, base + layer_offset, i); p is read from
+ * device memory (0 = identity: eval mode) and the SAME launch on the gradient is the backward.  state: device uint64
+ * {seed, base}; n % 8 == 0. */
+int cdae_dropout(void* x_bf16, int64_t n, const void* state, int64_t layer_offset, const float* p, cdae_stream s);
 
 /* ------------------------------------------------------------------ GroupNorm32 (+FiLM) (+SiLU)   nn.py:430-437, unet.py:185-198 */
 /* x = concat(x0[C0], x1[C1]) NHWC bf16 per sample (x1 may be NULL). y = act(GN(x)*gamma+beta)*(1+scale)+shift ...
@@ -156,6 +162,9 @@ typedef struct {
    * streaming pass.  Needs out_mode 0, no bias / residual / stats, cout and gnb_c0 % 64 == 0, OH*OW >= 32. */
   float* gnb_ws; const float* gnb_ab; const void* gnb_x0; const void* gnb_x1;
   int32_t gnb_c0, gnb_ld0, gnb_ld1, gnb_silu;
+  /* per-(image, channel) additive term of the epilogue: out += bias_img[n * bias_img_ld + co] - the ResBlock's additive
+   * timestep conditioning `h + emb_out[..., None, None]` (unet.py:196, use_scale_shift_norm=False).  NHWC output only. */
+  const float* bias_img; int32_t bias_img_ld;
 } cdae_igemm_desc;
 int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s);
 

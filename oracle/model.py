@@ -84,8 +84,10 @@ def timestep_embedding(t, dim, max_period=10000):
     return emb
 
 
-def resblock(sd, p, x, emb, use_scale_shift_norm=True):
-    """ResBlock._forward (ref unet.py:185-198). `p` is the key prefix, e.g. 'input_blocks.1.0.'."""
+def resblock(sd, p, x, emb, use_scale_shift_norm=True, drop=None):
+    """ResBlock._forward (ref unet.py:185-198). `p` is the key prefix, e.g. 'input_blocks.1.0.'.  `drop`: the multiplier
+    nn.Dropout applies between SiLU and the second conv (mask / (1 - p)), injected so that a test can use the masks of the
+    implementation under test (torch's own dropout stream cannot be reproduced by another generator)."""
     h = group_norm32(x, sd[p + "in_layers.0.weight"], sd[p + "in_layers.0.bias"])
     h = F.conv2d(silu(h), sd[p + "in_layers.2.weight"], sd[p + "in_layers.2.bias"], padding=1)
     e = F.linear(silu(emb), sd[p + "emb_layers.1.weight"], sd[p + "emb_layers.1.bias"]).type(h.dtype)[..., None, None]
@@ -94,7 +96,10 @@ def resblock(sd, p, x, emb, use_scale_shift_norm=True):
         h = group_norm32(h, sd[p + "out_layers.0.weight"], sd[p + "out_layers.0.bias"]) * (1 + scale) + shift
     else:
         h = group_norm32(h + e, sd[p + "out_layers.0.weight"], sd[p + "out_layers.0.bias"])
-    h = F.conv2d(silu(h), sd[p + "out_layers.3.weight"], sd[p + "out_layers.3.bias"], padding=1)
+    h = silu(h)
+    if drop is not None:
+        h = h * drop
+    h = F.conv2d(h, sd[p + "out_layers.3.weight"], sd[p + "out_layers.3.bias"], padding=1)
     if p + "skip_connection.weight" in sd:
         w = sd[p + "skip_connection.weight"]
         x = F.conv2d(x, w, sd[p + "skip_connection.bias"], padding=w.shape[-1] // 2)
