@@ -715,6 +715,295 @@ static int launch_igemm3(const IgemmKParams& kp, cudaStream_t st) {
   return CDAE_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ transposed halo kernel
+// igemm3t_kernel: the 3x3 stride-1 conv for layers whose output-channel tile is 128 (the 64x64 level of the UNet: 28 % of the
+// forward FLOPs).  igemm3_kernel runs them as M = 128 pixels x N = 128 channels: every 64-cycle MMA reads 4 KB of A and 4 KB
+// of B - the whole 128 B/clk shared-memory port, which TMA fills and the epilogue staging share (tensor pipe 53 %, r1 ncu).
+// Here the roles are swapped:   D[co (M = 128), pixel (N = 256)] = W[co, k] . X[pixel, k]
+//   A = weight tile (128 rows x 64 k, K-major, plain SBO 1024)             16 KB per (tap, chunk)
+//   B = the halo tile, now 8 wide x 32 high output pixels = 10 x 34 input pixels x 64 channels (340 rows, 42.5 KB per
+//       chunk), tap (dh, dw) = the same row-shifted descriptor with SBO 1280 as in igemm3_kernel, 32 row groups
+// so an MMA is 128 x 256 x 16: 4 KB + 8 KB of operands per 128 cycles = 96 B/clk, like the N = 256 tiles that reach 92 %.
+// The accumulator has CHANNELS on the TMEM lanes: an epilogue thread owns one channel and walks 128 pixels of a slab, so the
+// bias is a register, the GroupNorm statistics of the consumer (stats) and of the backward (gnb: sum du, sum du*x with the
+// {a, b} constants in two registers) are plain per-thread sums - no transposed shared-memory pass, no shuffles.  The price is
+// the transposing store: 16-bit writes into the [pixel][64 ch] slab (conflict-free: a warp writes 64 contiguous bytes).
+// Roles: warp 0 halo producer | warp 1 MMA | warps 2-5 epilogue (lane quarter = warp % 4; quarters {0,1} / {2,3} form two
+// PAIRS, each owning one 64-channel slab at a time) | warp 6 staging manager | warp 7 weight producer.
+constexpr int kHaloTRows = 340;
+constexpr int kHaloTBytes = kHaloTRows * 128;          // 43520
+constexpr int kHaloTStride = 43 * 1024;                // 1024 B aligned
+
+__device__ __forceinline__ uint32_t lds16(uint32_t addr) {
+  uint16_t u;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(u) : "r"(addr));
+  return (uint32_t)u;
+}
+__device__ __forceinline__ void sts16(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v));
+}
+__device__ __forceinline__ uint32_t bf16_bits(float f) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(f);
+  return (uint32_t)(*reinterpret_cast<const uint16_t*>(&h));
+}
+
+template <int AST, int BST, int NS>
+__global__ void __launch_bounds__(256, 1) igemm3t_kernel(const __grid_constant__ IgemmKParams p) {
+  constexpr int kWTileBytes = 128 * 128;                 // 128 output channels x 64 k
+  constexpr int kSlabStride = 128 * 128;
+  constexpr uint32_t kAccCols = 256;
+  constexpr uint32_t kIdesc = make_idesc_bf16(128, 256, 0, 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wsm = smem + AST * kHaloTStride;
+  uint8_t* stg = wsm + BST * kWTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + NS * kSlabStride);
+  // bars: hfull[AST] hempty[AST] wfull[BST] wempty[BST] tfull[2] tempty[2] sready[NS] sfree[NS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * AST + 2 * BST + 4 + 2 * NS);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t h_base = smem_u32(smem), w_base = smem_u32(wsm), stg_base = smem_u32(stg);
+  const uint32_t bar_base = smem_u32(bars);
+  auto hfull = [&](int s) { return bar_base + 8u * s; };
+  auto hempty = [&](int s) { return bar_base + 8u * (AST + s); };
+  auto wfull = [&](int s) { return bar_base + 8u * (2 * AST + s); };
+  auto wempty = [&](int s) { return bar_base + 8u * (2 * AST + BST + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * AST + 2 * BST + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * AST + 2 * BST + 2 + a); };
+  auto sready_bar = [&](int b) { return bar_base + 8u * (2 * AST + 2 * BST + 4 + b); };
+  auto sfree_bar = [&](int b) { return bar_base + 8u * (2 * AST + 2 * BST + 4 + NS + b); };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < AST; ++s) { mbar_init(hfull(s), 1); mbar_init(hempty(s), 1); }
+    for (int s = 0; s < BST; ++s) { mbar_init(wfull(s), 1); mbar_init(wempty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int b = 0; b < NS; ++b) { mbar_init(sready_bar(b), 1); mbar_init(sfree_bar(b), 1); }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile = (8 x 32 pixel box) x (128-channel block); boxes walk w fastest, then h, then the image
+  const int tilesH = p.OHt / 32;
+  const int boxes_per_img = p.tilesW * tilesH;
+  const int nbox = boxes_per_img * p.Nimg;
+  const int total_tiles = nbox * p.ntn;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int ca = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int box = tile / p.ntn;
+        const int cw = (box % p.tilesW) * 8 - 1, chh = ((box / p.tilesW) % tilesH) * 32 - 1, cn = box / boxes_per_img;
+        for (int h = 0; h < p.nhs; ++h) {
+          const CUtensorMap* tma = &p.tmA[p.hs[h].src];
+          const int c0 = p.hs[h].c0, nch = p.hs[h].nchunk;
+          for (int j = 0; j < nch; ++j, ++ca) {
+            const int s = ca % AST;
+            mbar_wait(hempty(s), ((ca / AST) & 1) ^ 1);
+            mbar_expect_tx(hfull(s), kHaloTBytes);
+            tma_load_4d(h_base + s * kHaloTStride, tma, hfull(s), c0 + j * 64, cw, chh, cn);
+          }
+        }
+      }
+    }
+  } else if (warp == 7) {
+    if (lane == 0) {
+      int cb = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.ntn) * 128;
+        for (int h = 0; h < p.nhs; ++h) {
+          const int nch = p.hs[h].nchunk, ntap = p.hs[h].ntap, wk0 = p.hs[h].wk0;
+          for (int j = 0; j < nch; ++j) {
+            for (int t = 0; t < ntap; ++t, ++cb) {
+              const int s = cb % BST;
+              mbar_wait(wempty(s), ((cb / BST) & 1) ^ 1);
+              mbar_expect_tx(wfull(s), kWTileBytes);
+              tma_load_2d(w_base + s * kWTileBytes, &p.tmB, wfull(s), wk0 + t * p.tap_stride + j * 64, n0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    int ca = 0, cb = 0, it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      mbar_wait(tempty_bar(as), ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      uint32_t first = 1;
+      for (int h = 0; h < p.nhs; ++h) {
+        const int nch = p.hs[h].nchunk, ntap = p.hs[h].ntap;
+        for (int j = 0; j < nch; ++j, ++ca) {
+          const int sa = ca % AST;
+          mbar_wait(hfull(sa), (ca / AST) & 1);
+          for (int t = 0; t < ntap; ++t, ++cb) {
+            const int ti = ntap == 9 ? (p.flip ? 8 - t : t) : 4;
+            const uint32_t row0 = (uint32_t)((ti / 3) * 10 + (ti % 3));
+            const int sb = cb % BST;
+            mbar_wait(wfull(sb), (cb / BST) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+              const uint64_t adesc = smem_desc_kmajor_sw128(w_base + sb * kWTileBytes);
+              const uint64_t bdesc = smem_desc_kmajor_sw128_sbo(h_base + sa * kHaloTStride + row0 * 128, 1280);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16(tmem_base + (uint32_t)(as * kAccCols), adesc + 2 * k, bdesc + 2 * k, kIdesc, (first && k == 0) ? 0u : 1u);
+              umma_commit(wempty(sb));
+            }
+            first = 0;
+            __syncwarp();
+          }
+          if (lane == 0) umma_commit(hempty(sa));
+          __syncwarp();
+        }
+      }
+      if (lane == 0) umma_commit(tfull_bar(as));
+      __syncwarp();
+    }
+  } else if (warp < 6) {
+    // ---------------------------------------------------------------- epilogue: thread = output channel
+    const int q = warp & 3, hp = q >> 1;                  // TMEM lane quarter; pair (= 64-channel slab half) of this warp
+    const int cl = (q & 1) * 32 + lane;                   // channel inside the slab
+    const bool elected = ((q & 1) == 0) && lane == 0;     // one thread per pair issues the stores
+    const bool gnb = p.gnb_ws != nullptr;
+    const bool need_x = gnb || p.has_resid;
+    const uint32_t chunk = (uint32_t)(cl >> 3), sub = (uint32_t)(cl & 7) * 2u;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const int box = tile / p.ntn, n0 = (tile % p.ntn) * 128;
+      const int w0 = (box % p.tilesW) * 8, h0 = ((box / p.tilesW) % tilesH) * 32, nimg = box / boxes_per_img;
+      const int c = n0 + 64 * hp + cl;
+      const bool cvalid = c < p.cout;
+      float bsum = 0.f;
+      if (cvalid) {
+        if (p.bias) bsum += __ldg(p.bias + c);
+        if (p.bias2) bsum += __ldg(p.bias2 + c);
+        if (p.bias_img) bsum += __ldg(p.bias_img + (size_t)nimg * p.bias_img_ld + c);
+      }
+      float ga = 0.f, gb = 0.f;
+      const __nv_bfloat16* dummy = nullptr; (void)dummy;
+      if (gnb && p.gnb_silu && cvalid) {
+        const float2 t2 = __ldg(reinterpret_cast<const float2*>(p.gnb_ab) + (size_t)nimg * p.cout + c);
+        ga = t2.x; gb = t2.y;
+      }
+      mbar_wait(tfull_bar(as), (it >> 1) & 1);
+      tc_fence_after();
+      float s1 = 0.f, s2 = 0.f;                           // {sum, sumsq} (stats) or {sum du, sum du*x} (gnb) of this channel
+#pragma unroll 1
+      for (int sb = 0; sb < 2; ++sb) {                    // 16-row sub-box = one [128 pixels][64 channels] slab per pair
+        const int sidx = it * 4 + sb * 2 + hp;
+        const int buf = sidx % NS;
+        mbar_wait(sready_bar(buf), (sidx / NS) & 1);
+        const uint32_t slab = stg_base + buf * kSlabStride;
+#pragma unroll 1
+        for (int cb4 = 0; cb4 < 4; ++cb4) {
+          uint32_t acc[32];
+          __syncwarp();
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccCols + sb * 128 + cb4 * 32), acc);
+          tmem_ld_wait();
+          // three passes over the 32 pixels so that the shared-memory reads are all in flight before the first use and the
+          // 16-bit stores go out back to back (one pass per pixel serialises on the LDS latency: 36k cycles per tile, ncu r2)
+          const uint32_t rowbase = slab + (uint32_t)(cb4 * 32) * 128u + sub;
+          uint32_t xr[32];
+          if (need_x) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) xr[i] = lds16(rowbase + (uint32_t)i * 128u + ((chunk ^ (uint32_t)(i & 7)) << 4));
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float v = __uint_as_float(acc[i]) + bsum;
+            if (gnb) {
+              const float x = __uint_as_float(xr[i] << 16);
+              if (p.gnb_silu) {
+                const float hh = fmaf(x, ga, gb), t = tanh_fast(hh);
+                v *= 0.5f * (1.f + t + hh * (1.f - t * t));
+              }
+              const uint32_t vb = bf16_bits(v);
+              const float vr = __uint_as_float(vb << 16);
+              s1 += vr; s2 = fmaf(vr, x, s2);
+              acc[i] = vb;
+            } else {
+              if (p.has_resid) v += __uint_as_float(xr[i] << 16);
+              const uint32_t vb = bf16_bits(v);
+              if (p.stats) { const float vr = __uint_as_float(vb << 16); s1 += vr; s2 = fmaf(vr, vr, s2); }
+              acc[i] = vb;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sts16(rowbase + (uint32_t)i * 128u + ((chunk ^ (uint32_t)(i & 7)) << 4), acc[i]);
+        }
+        fence_proxy_async();
+        named_bar_sync(1 + hp, 64);
+        if (elected) {
+          tma_store_4d(&p.tmO, slab, n0 + 64 * hp, w0, h0 + 16 * sb, nimg);
+          bulk_commit();
+          bulk_wait_read<0>();
+          mbar_arrive(sfree_bar(buf));
+        }
+      }
+      if (cvalid && (gnb || p.stats)) {
+        float* dst = (gnb ? p.gnb_ws : p.stats) + ((size_t)nimg * p.cout + c) * 2;
+        atomicAdd(reinterpret_cast<float2*>(dst), make_float2(s1, s2));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+    }
+    if (elected) bulk_wait_all();
+  } else if (warp == 6) {
+    // ---------------------------------------------------------------- staging manager: residual / GroupNorm-input slabs
+    if (lane == 0) {
+      const bool gnb = p.gnb_ws != nullptr;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int box = tile / p.ntn, n0 = (tile % p.ntn) * 128;
+        const int w0 = (box % p.tilesW) * 8, h0 = ((box / p.tilesW) % tilesH) * 32, nimg = box / boxes_per_img;
+        for (int k = 0; k < 4; ++k) {
+          const int sidx = it * 4 + k, sb = k >> 1, hp = k & 1;
+          const int buf = sidx % NS;
+          const int co0 = n0 + 64 * hp;
+          mbar_wait(sfree_bar(buf), ((sidx / NS) & 1) ^ 1);
+          if (gnb) {
+            const bool in1 = co0 >= p.gnb_c0;
+            mbar_expect_tx(sready_bar(buf), kSlabStride);
+            tma_load_4d(stg_base + buf * kSlabStride, in1 ? &p.tmR2 : &p.tmR, sready_bar(buf), in1 ? co0 - p.gnb_c0 : co0, w0,
+                        h0 + 16 * sb, nimg);
+          } else if (p.has_resid) {
+            mbar_expect_tx(sready_bar(buf), kSlabStride);
+            tma_load_4d(stg_base + buf * kSlabStride, &p.tmR, sready_bar(buf), co0, w0, h0 + 16 * sb, nimg);
+          } else {
+            mbar_arrive(sready_bar(buf));
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+template <int AST, int BST, int NS>
+static int launch_igemm3t(const IgemmKParams& kp, cudaStream_t st) {
+  constexpr int smem = AST * kHaloTStride + BST * 128 * 128 + NS * 128 * 128 + 1024 + 512;
+  static_assert(smem <= 227 * 1024, "igemm3t: shared memory budget");
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(igemm3t_kernel<AST, BST, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  });
+  if (attr_err != cudaSuccess) { set_error("igemm3t smem attribute: %s", cudaGetErrorString(attr_err)); return CDAE_ERR_CUDA; }
+  const int total = kp.tilesW * (kp.OHt / 32) * kp.Nimg * kp.ntn;
+  const int grid = total < kNumSMs ? total : kNumSMs;
+  igemm3t_kernel<AST, BST, NS><<<grid, 256, smem, st>>>(kp);
+  CDAE_CHECK_LAUNCH("igemm3t_kernel");
+  return CDAE_OK;
+}
+
 // Does the segment list describe "3x3 stride-1 conv over some sources (+ optional 1x1 taps over others)" in the packing
 // the engine uses (weight column = wk0 + tap*stride + channel)?  Fills kp.hs / tap_stride / flip when it does.
 static bool halo_plan(const cdae_igemm_desc* d, IgemmKParams& kp) {
@@ -816,18 +1105,6 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
   CDAE_CHECK_SHAPE(kp.out_mode == 1 || (d->OH == OHt && d->OW == OWt), "igemm: output dims %dx%d do not match the tile grid %dx%d",
                    d->OH, d->OW, OHt, OWt);
   CDAE_CHECK_SHAPE(!d->resid || (d->ldr % 8 == 0 && kp.out_mode == 0), "igemm: residual needs NHWC output and pitch %% 8");
-  for (int i = 0; i < d->nsrc; ++i) {
-    CDAE_CHECK_ARG(d->src[i], "igemm: null source %d", i);
-    CDAE_CHECK_SHAPE(d->src_c[i] % 8 == 0, "igemm: source %d channels %d must be a multiple of 8", i, d->src_c[i]);
-    const uint64_t C = d->src_c[i];
-    uint64_t dims[4] = {C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
-    uint64_t str[3] = {C * 2, C * 2 * d->W, C * 2 * (uint64_t)d->W * d->H};
-    uint32_t box[4] = {64, (uint32_t)(kp.BW * es), (uint32_t)(kp.BH * es), (uint32_t)kp.BNI};
-    if (halo) { box[1] = 10; box[2] = 18; box[3] = 1; }     // 8x16 output pixels + one pixel of halo on every side
-    uint32_t est[4] = {1, (uint32_t)es, (uint32_t)es, 1};
-    int rc = make_tmap_bf16(&kp.tmA[i], d->src[i], 4, dims, str, box, est);
-    if (rc) return rc;
-  }
   const int nboxes = kp.tilesW * kp.tilesH * tilesN;
   int bn = d->bn, mt = 1;
   if (bn == 0) {
@@ -835,6 +1112,25 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
     if (c >= 256 && c % 256 == 0 && (int64_t)nboxes * (c / 256) >= kNumSMs) bn = 256;
     else if (c >= 192 && c % 192 == 0 && (int64_t)nboxes * (c / 192) >= kNumSMs) bn = 192;
     else bn = c >= 128 ? 128 : c >= 64 ? 64 : c > 16 ? 32 : 16;
+  }
+  // 128-channel tiles of the halo kernel are shared-memory bound (M = N = 128): run them transposed (channels on the TMEM
+  // lanes, 256 pixels per MMA) when the image tiles into 8 x 32 boxes
+  static const bool no_t = getenv("CDAE_NO_IGEMM3T") != nullptr;
+  // (measured, profiles/r2_igemm_bench_t*.log: never slower than the pixel-major N = 256 / 192 tiles either, and the
+  // statistics epilogue is free in this orientation, so every eligible layer takes it)
+  const bool use_t = halo && !no_t && d->cout % 128 == 0 && kp.out_mode == 0 && OHt % 32 == 0 && OWt % 8 == 0 && d->bn == 0;
+  if (use_t) bn = 128;
+  for (int i = 0; i < d->nsrc; ++i) {
+    CDAE_CHECK_ARG(d->src[i], "igemm: null source %d", i);
+    CDAE_CHECK_SHAPE(d->src_c[i] % 8 == 0, "igemm: source %d channels %d must be a multiple of 8", i, d->src_c[i]);
+    const uint64_t C = d->src_c[i];
+    uint64_t dims[4] = {C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
+    uint64_t str[3] = {C * 2, C * 2 * d->W, C * 2 * (uint64_t)d->W * d->H};
+    uint32_t box[4] = {64, (uint32_t)(kp.BW * es), (uint32_t)(kp.BH * es), (uint32_t)kp.BNI};
+    if (halo) { box[1] = 10; box[2] = use_t ? 34 : 18; box[3] = 1; }     // output box + one pixel of halo on every side
+    uint32_t est[4] = {1, (uint32_t)es, (uint32_t)es, 1};
+    int rc = make_tmap_bf16(&kp.tmA[i], d->src[i], 4, dims, str, box, est);
+    if (rc) return rc;
   }
   CDAE_CHECK_SHAPE(!(d->stats || d->gnb_ws) || bn >= 64, "igemm: channel statistics need an N tile of at least 64 (bn %d)", bn);
   const int ntn = (d->cout + bn - 1) / bn;
@@ -884,6 +1180,11 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
   }
   kp.nseg = d->nseg; kp.nkb = nkb; kp.nboxes = nboxes; kp.ntn = ntn;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
+  if (use_t) {
+    static const char* tcfg = getenv("CDAE_T_CFG");
+    if (tcfg && tcfg[0] == '3') return launch_igemm3t<3, 3, 3>(kp, st);
+    return launch_igemm3t<2, 4, 4>(kp, st);
+  }
   if (halo) {
     switch (bn) {
       case 16: return launch_igemm3<16, 2, 2, 8, 3>(kp, st);

@@ -244,6 +244,9 @@ def _conv_case(N, H, chans, cout, ksize=3, stride=1, bias=True, resid=False, see
     (2, 48, [64, 128], 192, 3, 1, True),      # halo kernel: non-power-of-two image, concat, residual, N tile 192
     (3, 24, [64], 64, 3, 1, False),           # 24 % 16 != 0: falls back to the tap-streaming kernel
     (67, 16, [128], 128, 3, 1, True),         # many boxes, odd box count (MT = 2 tail)
+    (3, 64, [128, 256], 128, 3, 1, True),     # transposed halo kernel (cout 128, 8 x 32 boxes): concat sources + residual
+    (5, 32, [64], 384, 3, 1, False),          # transposed kernel, three 128-channel tiles per box, ragged batch
+    (150, 32, [128], 128, 3, 1, True),        # transposed kernel: more tiles than SMs (persistent loop, both TMEM sets)
 ])
 def test_igemm_conv_forward(N, H, chans, cout, ksize, stride, resid):
     err = _conv_case(N, H, chans, cout, ksize, stride, True, resid, seed=H + cout)
@@ -331,6 +334,8 @@ def test_wgrad_matches_autograd(N, H, cin, cout, ksize, stride):
     (2, 48, [64, 128], 192, 3, 1, True),      # non-power-of-two image: partial boxes must be masked out of the sums
     (3, 24, [64], 64, 3, 1, False),           # tap-streaming kernel with partial boxes
     (67, 16, [128], 128, 3, 1, True),         # many boxes (MT = 2 tail)
+    (3, 32, [128, 64], 128, 3, 1, True),      # transposed halo kernel: per-thread channel sums
+    (70, 64, [64], 128, 3, 1, False),         # transposed kernel, persistent loop over > 148 tiles
 ])
 def test_igemm_channel_stats(N, H, chans, cout, ksize, stride, resid):
     """cdae_igemm_desc.stats: per-(image, channel) sum / sum of squares of the bf16 output, accumulated by the epilogue"""
@@ -378,6 +383,8 @@ def test_igemm_channel_stats_rejects_unsupported():
     (2, 16, 384, 0, 1152, 1, False, False),     # attention norm: 1x1 qkv data gradient, no SiLU
     (2, 48, 64, 64, 64, 3, True, True),         # non-power-of-two image: partial boxes masked out of the sums
     (67, 16, 128, 0, 128, 3, True, True),       # many boxes (MT = 2 tail)
+    (3, 32, 64, 64, 256, 3, True, True),        # transposed halo kernel (128 output channels of the data gradient), concat x
+    (40, 64, 128, 0, 128, 3, False, False),     # transposed kernel, no SiLU, persistent loop
 ])
 def test_groupnorm_backward_from_dgrad_epilogue(N, H, C0, C1, cin, ksize, film, silu):
     """The fused GroupNorm backward: y = act(FiLM(GN(x))) feeds a conv; that conv's DATA-GRADIENT launch (gnb_*) stores
