@@ -103,6 +103,7 @@ _SIGS = {
     "cdae_step_tick": ([P, P, I32, P], C.c_int),
     "cdae_randn": ([P, I64, P, I32, F32, P], C.c_int),
     "cdae_silu_bwd": ([P, P, I64, P], C.c_int),
+    "cdae_silu_cast": ([P, P, I64, I32, P], C.c_int),
     "cdae_softplus_bwd": ([P, P, I64, P], C.c_int),
     "cdae_embed_rows": ([P, P, P, I32, I32, I32, P, P], C.c_int),
     "cdae_bn_finalize": ([P, F64, P, P, P, P, P, I32, P, P, I32, P], C.c_int),

@@ -71,7 +71,7 @@ struct alignas(64) IgemmKParams {
   int BW, BH, BNI, tilesW, tilesH;
   int in_stride;
   int Nimg, OHt, OWt;
-  int OH, OW, cout, out_mode, has_resid;
+  int OH, OW, cout, out_mode, has_resid, ldo;
   void* out;
   const float* bias;
   const float* bias2;
@@ -310,11 +310,28 @@ __device__ __forceinline__ void igemm_epilogue(const IgemmKParams& p, const EpiC
           tmem_ld_wait();
           const int co0 = n0 + c;
           if (row_ok && co0 < p.cout) {
+            if (p.out_mode == 2) {
+              // fp32 row-major [pixel][ldo]: GEMM-shaped outputs that stay fp32 (the FiLM vectors, their gradient)
+              float* orow = o + (((size_t)n * p.OH + oy) * p.OW + ox) * p.ldo + co0;
 #pragma unroll
-            for (int j = 0; j < CH; ++j) {
-              const int co = co0 + j;
-              if (co < p.cout)
-                o[(((size_t)n * p.cout + co) * p.OH + oy) * p.OW + ox] = __uint_as_float(acc[j]) + (bias ? __ldg(bias + co) : 0.f);
+              for (int j = 0; j < CH; j += 4) {
+                if (co0 + j + 3 < p.cout) {
+                  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + co0 + j));
+                  *reinterpret_cast<float4*>(orow + j) = make_float4(__uint_as_float(acc[j]) + b4.x, __uint_as_float(acc[j + 1]) + b4.y,
+                                                                     __uint_as_float(acc[j + 2]) + b4.z, __uint_as_float(acc[j + 3]) + b4.w);
+                } else {
+                  for (int e = 0; e < 4 && co0 + j + e < p.cout; ++e)
+                    orow[j + e] = __uint_as_float(acc[j + e]) + (bias ? __ldg(bias + co0 + j + e) : 0.f);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < CH; ++j) {
+                const int co = co0 + j;
+                if (co < p.cout)
+                  o[(((size_t)n * p.cout + co) * p.OH + oy) * p.OW + ox] = __uint_as_float(acc[j]) + (bias ? __ldg(bias + co) : 0.f);
+              }
             }
           }
         }
@@ -1078,7 +1095,11 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
   kp.tilesH = (OHt + kp.BH - 1) / kp.BH;
   const int tilesN = (d->N + kp.BNI - 1) / kp.BNI;
   kp.in_stride = es; kp.Nimg = d->N; kp.OHt = OHt; kp.OWt = OWt;
-  kp.OH = d->OH; kp.OW = d->OW; kp.cout = d->cout; kp.out_mode = d->out_mode;
+  kp.OH = d->OH; kp.OW = d->OW; kp.cout = d->cout; kp.out_mode = d->out_mode; kp.ldo = d->ldo;
+  CDAE_CHECK_SHAPE(d->out_mode >= 0 && d->out_mode <= 2, "igemm: out_mode %d", d->out_mode);
+  CDAE_CHECK_SHAPE(d->out_mode != 2 || (d->ldo % 4 == 0 && d->ldo >= d->cout && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0 &&
+                                        (!d->bias || (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0)),
+                   "igemm: fp32 row-major output needs ldo %% 4 == 0, ldo >= cout and 16-byte aligned out / bias");
   kp.out = d->out; kp.bias = d->bias; kp.bias2 = d->bias2; kp.has_resid = d->resid != nullptr;
   kp.bias_img = d->bias_img; kp.bias_img_ld = d->bias_img_ld;
   CDAE_CHECK_SHAPE(!d->bias_img || (d->out_mode == 0 && d->bias_img_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(d->bias_img) & 15) == 0),
@@ -1101,7 +1122,7 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
   CDAE_CHECK_SHAPE(!d->stats || (kp.out_mode == 0 && d->cout % 64 == 0 && kp.BW * kp.BH >= 32 &&
                                  (reinterpret_cast<uintptr_t>(d->stats) & 15) == 0),
                    "igemm: channel statistics need NHWC output, cout %% 64 == 0 and >= 32 output pixels per image");
-  CDAE_CHECK_SHAPE(kp.out_mode == 1 || (d->cout % 8 == 0 && d->ldo % 8 == 0), "igemm: NHWC output needs cout, ldo %% 8 == 0");
+  CDAE_CHECK_SHAPE(kp.out_mode != 0 || (d->cout % 8 == 0 && d->ldo % 8 == 0), "igemm: NHWC output needs cout, ldo %% 8 == 0");
   CDAE_CHECK_SHAPE(kp.out_mode == 1 || (d->OH == OHt && d->OW == OWt), "igemm: output dims %dx%d do not match the tile grid %dx%d",
                    d->OH, d->OW, OHt, OWt);
   CDAE_CHECK_SHAPE(!d->resid || (d->ldr % 8 == 0 && kp.out_mode == 0), "igemm: residual needs NHWC output and pitch %% 8");

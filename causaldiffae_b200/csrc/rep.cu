@@ -228,6 +228,14 @@ __global__ void temb_kernel(const void* t, int t_is_float, int t_stride, const i
   out[idx] = v;
 }
 
+// y (bf16) = silu(x) (or x): the A operand of the tensor-core FiLM projection
+__global__ void silu_cast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n, int silu) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    y[i] = __float2bfloat16_rn(silu ? silu_exact(v) : v);
+  }
+}
+
 // g *= silu'(x)
 __global__ void silu_bwd_kernel(float* __restrict__ g, const float* __restrict__ x, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -615,6 +623,15 @@ extern "C" int cdae_timestep_embedding(const void* t, int t_is_float, int t_stri
   const int n = B * dim;
   temb_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)s>>>(t, t_is_float, t_stride, map, scale, freqs, out, B, dim / 2, dim);
   CDAE_CHECK_LAUNCH("temb_kernel");
+  return CDAE_OK;
+}
+
+extern "C" int cdae_silu_cast(const float* x, void* y_bf16, int64_t n, int silu, cdae_stream s) {
+  if (n == 0) return CDAE_OK;
+  CDAE_CHECK_ARG(x && y_bf16, "silu_cast: null pointer");
+  int64_t blocks = (n + 255) / 256; if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  silu_cast_kernel<<<(int)blocks, 256, 0, (cudaStream_t)s>>>(x, reinterpret_cast<__nv_bfloat16*>(y_bf16), n, silu);
+  CDAE_CHECK_LAUNCH("silu_cast_kernel");
   return CDAE_OK;
 }
 

@@ -372,6 +372,18 @@ class Engine:
                     reg(id(mod.conv), mod.conv.weight, mod.conv.bias, mod.conv.out_channels, mod.conv.in_channels, 9)
         oc = m.out[2]
         reg(id(oc), oc.weight, oc.bias, oc.out_channels, oc.in_channels, 9)
+        # all emb_layers weights (adjacent in the arena) as ONE [film_width, time_embed_dim] matrix: the FiLM projection and
+        # its two backward GEMMs run on the tensor cores too (bf16 operands, fp32 accumulate and fp32 results)
+        ted = m.model_channels * 4
+        if self.film_width % 64 == 0 and ted % 64 == 0:
+            fw = _ConvW(self.film_w, self.film_b, self.film_width, ted, 1)
+            fw.K = fw.Ktot = ted
+            fw.fwd_off, fw.fwd_shape = off, (self.film_width, ted)
+            off += _round_up(self.film_width * ted, 64)
+            fw.tr_off, fw.tr_shape = off, (ted, self.film_width)
+            off += _round_up(ted * self.film_width, 64)
+            entries.append(PackEntry(0, fw.fwd_off, fw.tr_off, self.film_width, ted, 1, self.film_width, ted, ted, 0, 0))
+            self.convs["film"] = fw
         self.bf16_arena = th.zeros(off, device=self.device, dtype=bf16)
         for cw in self.convs.values():
             if getattr(cw, "fwd_off", None) is not None and cw.fwd is None and hasattr(cw, "fwd_shape"):
@@ -744,7 +756,39 @@ class Engine:
         standalone layer calls; the model path goes through rep.TrunkRunner)"""
         e = emb.detach().float().contiguous()
         out = th.empty(e.shape[0], self.film_width, device=e.device, dtype=th.float32)
-        return ops.linear_fwd(e, self.film_w, self.film_b, out, silu_in=True)
+        self.pack()
+        return self.film_fwd(e, out, th.empty(e.shape, device=e.device, dtype=bf16))
+
+    def film_fwd(self, emb, out, a_bf):
+        """out [B, film_width] fp32 = emb_layers(SiLU(emb)) for all ResBlocks: one tcgen05 GEMM (bf16 operands from the packed
+        arena, fp32 accumulate / result); a_bf: bf16 [B, ted] scratch that receives SiLU(emb) (kept for the backward)"""
+        fw = self.convs.get("film")
+        if fw is None:
+            return ops.linear_fwd(emb, self.film_w, self.film_b, out, silu_in=True)
+        B, ted = emb.shape
+        ops.silu_cast(emb, a_bf, silu=True)
+        d = ops.make_igemm_desc([a_bf.view(1, 1, B, ted)], [(0, 0, 0, 0, ted // 64, 0)], fw.fwd, out.view(1, 1, B, self.film_width),
+                                self.film_width, bias=self.film_b, out_mode=2)
+        ops.igemm(d)
+        return out
+
+    def film_bwd(self, emb, a_bf, dfilm, dfilm_bf, demb):
+        """gradients of the FiLM projection: film_w.grad / film_b.grad += (tensor-core weight gradient, K = batch), demb [B, ted]
+        fp32 = (dfilm Wf) * silu'(emb)"""
+        fw = self.convs.get("film")
+        if fw is None:
+            ops.linear_bwd(emb, self.film_w, dfilm, self.film_w.grad, self.film_b.grad, dx=demb, silu_in=True)
+            return ops.silu_bwd_(demb, emb)
+        B, ted = emb.shape
+        W = self.film_width
+        ops.cast_bf16(dfilm, out=dfilm_bf)
+        wd = ops.make_wgrad_desc(dfilm_bf.view(1, 1, B, W), a_bf.view(1, 1, B, ted), self.film_w.grad, W, ted, ksize=1,
+                                 dbias=self.film_b.grad)
+        ops.wgrad(wd)
+        d = ops.make_igemm_desc([dfilm_bf.view(1, 1, B, W)], [(0, 0, 0, 0, W // 64, 0)], fw.tr, demb.view(1, 1, B, ted), ted,
+                                out_mode=2)
+        ops.igemm(d)
+        return ops.silu_bwd_(demb, emb)
 
     @property
     def trunk(self):

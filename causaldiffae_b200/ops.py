@@ -303,6 +303,10 @@ def make_igemm_desc(srcs, segs, wgt, out, cout, in_stride=1, bias=None, resid=No
     if out_mode == 0:
         OH, OW = (out.shape[1], out.shape[2]) if out_hw is None else out_hw
         d.ldo = out.shape[-1]
+    elif out_mode == 2:         # fp32 [N, OH, OW, ldo] row-major
+        assert out.dtype == torch.float32 and out.is_contiguous()
+        OH, OW = out.shape[1], out.shape[2]
+        d.ldo = out.shape[-1]
     else:
         OH, OW = out.shape[2], out.shape[3]
         d.ldo = 0
@@ -496,6 +500,12 @@ def step_tick(step64, step32, delta):
 def randn_(out, state, bernoulli=False, keep_prob=0.5):
     """fill `out` (fp32) with N(0,1) draws, or Bernoulli(keep_prob) 0/1; state: device int64[2] {seed, offset}"""
     check(_lib.lib().cdae_randn(ptr(_f32c(out)), out.numel(), ptr(state), int(bernoulli), float(keep_prob), stream()))
+    return out
+
+
+def silu_cast(x, out, silu=True):
+    """out (bf16) = SiLU(x) (or x)"""
+    check(_lib.lib().cdae_silu_cast(ptr(_f32c(x)), ptr(_bf16c(out)), x.numel(), int(silu), stream()))
     return out
 
 

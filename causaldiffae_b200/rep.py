@@ -65,9 +65,11 @@ class TrunkRunner:
         ted = m.model_channels * 4
         f = lambda *s: th.empty(*s, device=device, dtype=th.float32)   # noqa: E731
         st.temb, st.h1, st.emb = f(B, m.model_channels), f(B, ted), f(B, ted)
+        st.a_bf = th.empty(B, ted, device=device, dtype=th.bfloat16)          # SiLU(emb): A operand of the FiLM GEMM
         st.hc = f(B, 256) if m.c_dim is not None else None
         if train:
             st.demb, st.dh1 = f(B, ted), f(B, ted)
+            st.dfilm_bf = th.empty(B, m.engine.film_width, device=device, dtype=th.bfloat16)
             st.dhc = f(B, 256) if m.c_dim is not None else None
         return st
 
@@ -84,13 +86,12 @@ class TrunkRunner:
             ops.linear_fwd(st.hc, m.c_emb[2].weight, m.c_emb[2].bias, st.emb, silu_in=True, accumulate=True)
         if z is not None:
             ops.linear_fwd(z, m.up_emb.weight, m.up_emb.bias, st.emb, accumulate=True)
-        ops.linear_fwd(st.emb, eng.film_w, eng.film_b, film_out, silu_in=True)
+        eng.film_fwd(st.emb, film_out, st.a_bf)
         return film_out
 
     def backward(self, st, y, c, z, dfilm, dz_out=None):
         m, eng = self.m, self.m.engine
-        ops.linear_bwd(st.emb, eng.film_w, dfilm, eng.film_w.grad, eng.film_b.grad, dx=st.demb, silu_in=True)
-        ops.silu_bwd_(st.demb, st.emb)
+        eng.film_bwd(st.emb, st.a_bf, dfilm, st.dfilm_bf, st.demb)
         if z is not None:
             ops.linear_bwd(z, m.up_emb.weight, st.demb, _g(m.up_emb.weight), _g(m.up_emb.bias), dx=dz_out)
         if m.c_dim is not None:
@@ -111,6 +112,7 @@ class _FilmFn(th.autograd.Function):
     @staticmethod
     def forward(ctx, model, _anchor, t, y, c, z, tmap, scale, train):
         run = model.engine.trunk                   # train = th.is_grad_enabled() at the call site (it is off in here)
+        model.engine.pack()                        # the FiLM projection reads the packed bf16 weights
         B = t.shape[0]
         if t.dtype not in (th.int64, th.float32):
             t = t.float() if t.is_floating_point() else t.long()

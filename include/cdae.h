@@ -143,7 +143,7 @@ typedef struct {
   int32_t in_stride;                       /* 1, or 2: output pixel p reads input pixel 2p+tap (TMA element stride) */
   int32_t nseg; cdae_seg seg[CDAE_MAX_SEG];
   const void* wgt; int32_t wrows, wk;      /* bf16 [wrows][wk] */
-  void* out; int32_t out_mode;             /* 0: NHWC bf16, 1: NCHW fp32 */
+  void* out; int32_t out_mode;             /* 0: NHWC bf16, 1: NCHW fp32, 2: fp32 row-major [pixel][ldo] (GEMM-shaped fp32 results) */
   int32_t OH, OW, ldo, cout;               /* full output dims, row pitch (NHWC), number of real output channels */
   int32_t sps, ooh, oow;                   /* output pixel = (tile_y*sps + ooh, tile_x*sps + oow) */
   const float* bias;                       /* fp32 [cout] or NULL */
@@ -243,6 +243,8 @@ int cdae_step_tick(int64_t* step64, int32_t* step32, int delta, cdae_stream s);
  * uint64 {seed, offset}; the launch advances the offset.  Replaces th.randn_like / th.bernoulli at gaussian_diffusion.py:790,
  * nn.py:464, unet.py:601 in throughput runs (parity runs inject the reference's CPU-generator draws instead). */
 int cdae_randn(float* out, int64_t n, void* state, int bernoulli, float keep_prob, cdae_stream s);
+/* y (bf16) = silu ? SiLU(x) : x  - the bf16 A operand of the tensor-core FiLM projection (unet.py:148-154 emb_layers) */
+int cdae_silu_cast(const float* x, void* y_bf16, int64_t n, int silu, cdae_stream s);
 /* g *= silu'(x)  (backward of the SiLU-on-load operand views) ; g *= softplus'(pre) given var = softplus(pre) + 1e-8 */
 int cdae_silu_bwd(float* g, const float* x, int64_t n, cdae_stream s);
 int cdae_softplus_bwd(float* g, const float* var, int64_t n, cdae_stream s);

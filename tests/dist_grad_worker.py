@@ -69,11 +69,7 @@ def main():
     x, c, noise = shard(rank)
     np.random.seed(50 + rank)
     torch.manual_seed(900 + rank)
-    orig = diff.training_losses
-
-    def with_noise(model_, x_, t_, **kw):          # inject the shard's noise; everything else is TrainLoop's own path
-        return orig(model_, x_, t_, noise=noise.to(dev), **kw)
-    diff.training_losses = with_noise
+    loop.noise_override = noise.to(dev)            # the shard's noise; everything else is TrainLoop's own (fused) path
     loop.forward_backward(x, {"c": c})
     named = dict(model.named_parameters())
     if getattr(loop, "_reduced_grads", None) is not None:

@@ -139,11 +139,13 @@ def test_trunk_and_film_vs_oracle(class_cond, context_cond):
     zz = z.clone().requires_grad_(True)
     film = _FilmFn.apply(model, anchor(z.device), t, y, c, zz, None, 0.0, True)
     (film * gf).sum().backward()
-    assert relerr(film, film_ref) < 1e-5, relerr(film, film_ref)
-    assert relerr(zz.grad, zr.grad) < 1e-4
+    # the trunk (time_embed, label_emb, c_emb, up_emb) is fp32; the FiLM projection itself (a [B,256] x [256, sum 2C] GEMM and
+    # its two backward GEMMs) runs on the tensor cores with bf16 operands and fp32 accumulation, like the torso it feeds
+    assert relerr(film, film_ref) < 5e-3, relerr(film, film_ref)
+    assert relerr(zz.grad, zr.grad) < 1e-2
     named = dict(model.named_parameters())
     for n in names:
-        assert relerr(named[n].grad, sd[n].grad) < 1e-4, (n, relerr(named[n].grad, sd[n].grad))
+        assert relerr(named[n].grad, sd[n].grad) < 1e-2, (n, relerr(named[n].grad, sd[n].grad))
     assert len(rbs) == len(prefixes)
     # respaced / rescaled model timesteps (ref respace.py:119-124) folded into the embedding kernel
     tmap = torch.arange(0, 1000, 20, device="cuda")
