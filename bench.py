@@ -245,6 +245,47 @@ def cpu_baseline_sample(batch):
                       f"(workload batch {batch}), fp32 torch CPU"}
 
 
+def cuda_cfg1_workload(dev):
+    """BASELINE.json configs[0] on this build (the reference arm times the same workload on the CPU, `cfg1_workload` there):
+    MorphoMNIST-shaped 1x32x32, 2-variable graph, 64 ch x 2 res blocks, batch 16: 100 `TrainLoop.run_step` from host batches with a
+    loss read back per step, then one 10-step DDIM counterfactual - wall clock, like the reference arm."""
+    from causaldiffae_b200 import script_util as su
+    from causaldiffae_b200.train_util import TrainLoop
+    from causaldiffae_b200.sampling import counterfactual
+    B = 16
+    torch.manual_seed(0)
+    model, diff = su.create_model_and_diffusion(**{**su.model_and_diffusion_defaults(), **CFG1})
+    _dezero(model)
+    model.to(dev)
+    loop = TrainLoop(model=model, diffusion=diff, data=None, batch_size=B, microbatch=-1, lr=1e-4, ema_rate="0.9999",
+                     log_interval=10 ** 9, save_interval=10 ** 9, resume_checkpoint="", rep_cond=True, n_vars=2,
+                     causal_modeling=True, in_channels=1)
+    g = torch.Generator().manual_seed(0)
+    x, c, y = torch.rand(B, 1, 32, 32, generator=g).pin_memory(), torch.rand(B, 2, generator=g).pin_memory(), \
+        torch.randint(0, 10, (B,), generator=g).pin_memory()
+    np.random.seed(0)
+    for _ in range(4):
+        loop.run_step(x, {"c": c, "y": y})
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(100):
+        loop.run_step(x, {"c": c, "y": y})
+        float(loop.last_loss)
+    torch.cuda.synchronize()
+    dt_train = time.perf_counter() - t0
+    _, d10 = su.create_model_and_diffusion(**{**su.model_and_diffusion_defaults(), **CFG1, "timestep_respacing": "ddim10"})
+    model.eval()
+    xd, yd = x.to(dev), y.to(dev)
+    counterfactual(model, d10, xd, do_var=0, do_value=0.2, y=yd)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    img = counterfactual(model, d10, xd, do_var=0, do_value=-0.1, y=yd)
+    img.cpu()
+    dt_ddim = time.perf_counter() - t0
+    return {"workload": "cfg1 morphomnist32: 100 TrainLoop.run_step (host batches, loss read per step) + DDIM-10 counterfactual, batch 16",
+            "train_img_per_s": B * 100 / dt_train, "train_s": dt_train, "ddim10_img_per_s": B / dt_ddim, "ddim10_s": dt_ddim}
+
+
 def gpu_reference_sample(B, steps=3):
     """the same algorithm (the oracle restatement of the reference, same weights / batch) executed by EAGER PyTorch on this
     GPU - cuDNN / cuBLAS through ATen, bf16 autocast: the 'existing Blackwell library kernels' bar this build is measured
@@ -541,6 +582,11 @@ def run_cuda(args):
             res["hbm_kernels"] = hbm_kernels(peaks)
         except Exception as ex:
             res["hbm_kernels"] = {"error": repr(ex)}
+        if world == 1 and not args.no_cfg1:
+            try:
+                res["cfg1_workload"] = cuda_cfg1_workload(dev)
+            except Exception as ex:
+                res["cfg1_workload"] = {"error": repr(ex)}
         if world == 1 and not args.no_gpu_ref:
             try:
                 res["gpu_reference"] = gpu_reference_sample(B)
@@ -628,7 +674,7 @@ def main():
     ap.add_argument("--no-ddim", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gpu-ref", action="store_true", help="skip the eager-PyTorch-on-this-GPU reference leg")
-    ap.add_argument("--no-cfg1", action="store_true", help="reference arm: skip the cfg1 (100 steps + DDIM-10) workload")
+    ap.add_argument("--no-cfg1", action="store_true", help="skip the cfg1 (100 steps + DDIM-10, batch 16) workload")
     args = ap.parse_args()
     if args.impl == "reference":
         # every step is a bounded sample (batch --ref-batch, ~0.5 s of CPU work): K and W are honoured as given
