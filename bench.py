@@ -211,38 +211,18 @@ def run_reference(args):
 
 
 def cpu_baseline_sample(batch):
-    """the reference (or, without it, the oracle port) timed on the host cores for ~10-30 s (rank 0, N=1 only)"""
-    from oracle import refshim
-    cores = os.cpu_count()
-    torch.set_num_threads(cores)
-    Bs, n = 4, 16
-    x, cond = synth_batch(Bs, 0)
-    np.random.seed(0); torch.manual_seed(0)
-    if refshim.available():
-        kind = "reference"
-        ns, model, diff, tl = _reference_trainloop(FLAGS, PENDULUM, Bs, 4, 3)
-
-        def step():
-            tl.run_step(x, dict(cond))
-    else:
-        kind = "port"
-        from oracle import model as om, diffusion as od, schedules
-        cfg = om.config_from_flags(**FLAGS, A=PENDULUM)
-        sd = om.seeded_state_dict(cfg, seed=0)
-        tr = od.RefTrainer(sd, cfg, od.Diffusion(steps=1000), lr=1e-4)
-
-        def step():
-            t, w = schedules.uniform_sample_t(1000, Bs)
-            tr.run_step(x, torch.from_numpy(t), torch.randn_like(x), torch.from_numpy(w), c=cond["c"])
-
-    step()
-    t0 = time.perf_counter()
-    for _ in range(n):
-        step()
-    dt = time.perf_counter() - t0
-    return {"value": Bs * n / dt, "unit": "img/s", "cores": cores, "kind": kind,
-            "sample": f"{n} TrainLoop.run_step of the {'unmodified reference' if kind == 'reference' else 'oracle port'} at batch {Bs} "
-                      f"(workload batch {batch}), fp32 torch CPU"}
+    """the reference arm (the unmodified reference on the host cores, or the oracle port without it) on a bounded sample,
+    in a child process that cannot see the GPU: the reference's TrainLoop wraps the model in a CUDA DistributedDataParallel
+    whenever torch.cuda.is_available() (ref train_util.py:107-118), and this baseline is its CPU path"""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_PORT"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "8", "--warmup", "1",
+                        "--no-cfg1", "--batch", str(batch)], capture_output=True, text=True, env=env, timeout=900)
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    if not line:
+        raise RuntimeError("reference arm failed: " + r.stderr[-400:])
+    return json.loads(line[-1])["cpu_baseline"]
 
 
 def cuda_cfg1_workload(dev):
@@ -593,7 +573,10 @@ def run_cuda(args):
             except Exception as ex:
                 res["gpu_reference"] = {"error": repr(ex)}
         if world == 1 and not args.no_cpu:
-            res["cpu_baseline"] = cpu_baseline_sample(B)
+            try:
+                res["cpu_baseline"] = cpu_baseline_sample(B)
+            except Exception as ex:
+                res["cpu_baseline"] = {"error": repr(ex)}
         if not args.no_ddim:
             try:
                 res["ddim"] = ddim_bench(model, world, dev, args)
@@ -677,7 +660,10 @@ def main():
     ap.add_argument("--no-cfg1", action="store_true", help="skip the cfg1 (100 steps + DDIM-10, batch 16) workload")
     args = ap.parse_args()
     if args.impl == "reference":
-        # every step is a bounded sample (batch --ref-batch, ~0.5 s of CPU work): K and W are honoured as given
+        # the reference's CPU path: hide the GPUs before anything initialises CUDA (its TrainLoop would otherwise build a CUDA
+        # DistributedDataParallel around the CPU model).  Every step is a bounded sample (batch --ref-batch): K and W are
+        # honoured as given
+        os.environ["CUDA_VISIBLE_DEVICES"] = ""
         run_reference(args)
     else:
         run_cuda(args)

@@ -1202,8 +1202,9 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
   kp.nseg = d->nseg; kp.nkb = nkb; kp.nboxes = nboxes; kp.ntn = ntn;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
   if (use_t) {
-    static const char* tcfg = getenv("CDAE_T_CFG");
+    static const char* tcfg = getenv("CDAE_T_CFG");           // staging experiments: halo stages / weight stages / slabs
     if (tcfg && tcfg[0] == '3') return launch_igemm3t<3, 3, 3>(kp, st);
+    if (tcfg && tcfg[0] == '5') return launch_igemm3t<2, 5, 3>(kp, st);
     return launch_igemm3t<2, 4, 4>(kp, st);
   }
   if (halo) {
