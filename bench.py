@@ -111,10 +111,11 @@ def _reference_trainloop(flags, A, B, n_vars, in_channels):
     model, diff = refshim.build({**ns.su.model_and_diffusion_defaults(), **flags}, rep_dim=512, A=A)
     _dezero(model)
     model.train()
-    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    os.environ.setdefault("MASTER_PORT", "29577")
     if not torch.distributed.is_initialized():
-        torch.distributed.init_process_group(backend="gloo", rank=0, world_size=1)
+        # a private single-process gloo group (under torchrun MASTER_PORT belongs to the launcher's store)
+        import socket
+        sk = socket.socket(); sk.bind(("127.0.0.1", 0)); port = sk.getsockname()[1]; sk.close()
+        torch.distributed.init_process_group(backend="gloo", rank=0, world_size=1, init_method=f"tcp://127.0.0.1:{port}")
     ns.logger.configure(dir=os.path.join("/tmp", f"cdae_ref_{os.getpid()}"), format_strs=[])
     tl = ns.train.TrainLoop(model=model, diffusion=diff, data=None, batch_size=B, microbatch=-1, lr=1e-4, ema_rate="0.9999",
                             log_interval=10 ** 9, save_interval=10 ** 9, resume_checkpoint="", rep_cond=True, n_vars=n_vars,
@@ -350,7 +351,7 @@ def conv_roofline(peaks, B):
         traffic, tsrc = (cap["dram_read_MB"] + cap["dram_write_MB"]) * 1e6, "profiles/r2_ncu_igemm3t_summary.json"
     except Exception:
         pass
-    return {"bound": "tensor", "kernel": "igemm3t_kernel<2,4,4> (3x3 conv 128->128 @64x64, batch %d)" % B,
+    return {"bound": "tensor", "kernel": "igemm3t_kernel<2,5,3> (3x3 conv 128->128 @64x64, batch %d)" % B,
             "achieved": top["tflops"], "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": top["tflops"] / peaks["tf_burst"],
             "traffic": traffic, "traffic_unit": "bytes/launch", "traffic_source": tsrc,
             "peak_source": peaks["src"] + " bf16 burst",

@@ -1204,8 +1204,8 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
   if (use_t) {
     static const char* tcfg = getenv("CDAE_T_CFG");           // staging experiments: halo stages / weight stages / slabs
     if (tcfg && tcfg[0] == '3') return launch_igemm3t<3, 3, 3>(kp, st);
-    if (tcfg && tcfg[0] == '5') return launch_igemm3t<2, 5, 3>(kp, st);
-    return launch_igemm3t<2, 4, 4>(kp, st);
+    if (tcfg && tcfg[0] == '4') return launch_igemm3t<2, 4, 4>(kp, st);
+    return launch_igemm3t<2, 5, 3>(kp, st);        // measured best on every cfg2 shape (profiles/r2_igemm_bench_t253_stats.log)
   }
   if (halo) {
     switch (bn) {

@@ -36,6 +36,11 @@ FUSED_GN_STATS = os.environ.get("CDAE_FUSED_GN_STATS", "1") != "0"
 # epilogue warp per scheduler, which cannot hide its own latencies (tensor pipe 53 % -> 28 %).  Whole step 19.25 -> 20.3 ms.
 # Off by default until the epilogue runs two warps per scheduler.
 FUSED_GN_BWD = os.environ.get("CDAE_FUSED_GN_BWD", "0") != "0"
+# Weight-gradient kernels on a second stream: nothing in the backward chain (data gradients, GroupNorm / attention backward)
+# reads a weight gradient, so every wgrad launch only has to wait for the kernel that produced its dY and has to be done by
+# the end of the backward.  In the captured graph this becomes a side branch: its CTAs fill the tail waves and launch gaps of
+# the chain (both kinds of kernel occupy a whole SM per CTA, so this is interleaving, not co-residency).
+WGRAD_SIDE_STREAM = os.environ.get("CDAE_WGRAD_SIDE_STREAM", "1") != "0"
 
 
 def _round_up(v, m):
@@ -152,9 +157,27 @@ class Plan:
             f()
 
     def _run_bwd_eager(self):
+        if not WGRAD_SIDE_STREAM:
+            for layer in reversed(self.bwd):
+                for f in layer:
+                    f()
+            return
+        main = th.cuda.current_stream()
+        if getattr(self, "_side", None) is None:
+            self._side = th.cuda.Stream()
+        side = self._side
+        used = False
         for layer in reversed(self.bwd):
             for f in layer:
-                f()
+                if getattr(f, "side", False):
+                    side.wait_stream(main)           # after everything issued so far: in particular the producer of its dY
+                    with th.cuda.stream(side):
+                        f()
+                    used = True
+                else:
+                    f()
+        if used:
+            main.wait_stream(side)                   # the optimizer (and the next step's zeroing) come after every wgrad
 
     def forward(self):
         if USE_GRAPHS and self.runs >= 1:
@@ -172,6 +195,12 @@ class Plan:
             self.bwd_graph.replay()
         else:
             self._run_bwd_eager()
+
+
+def _side(fn):
+    """mark a backward launch as independent of the chain (see WGRAD_SIDE_STREAM)"""
+    fn.side = True
+    return fn
 
 
 def _capture(fn):
@@ -469,7 +498,7 @@ class Engine:
             real = max(0, min(c, cw.cin - off))
             wd = ops.make_wgrad_desc(dy, s.t, gw, cw.cout, c, ksize=ksize, in_stride=stride, ci_off=off, cin_real=real,
                                      dw_ld=cw.cin, dbias=gb if (fused_bias and si == 0) else None)
-            fns.append(lambda wd=wd: ops.wgrad(wd))
+            fns.append(_side(lambda wd=wd: ops.wgrad(wd)))
             off += c
         if need_dgrad:
             dyz = dy
@@ -569,7 +598,7 @@ class Engine:
                         c = s.shape[3]
                         wd = ops.make_wgrad_desc(dout, s.t, gsk_w, cout, c, ksize=1, ci_off=off, dw_ld=cin,
                                                  dbias=gsk_b if off == 0 else None)
-                        fns.append(lambda wd=wd: ops.wgrad(wd))
+                        fns.append(_side(lambda wd=wd: ops.wgrad(wd)))
                         acc, g = s.grad_acc(), s.grad()
                         segs, _ = ops.conv_segments([cout], 1)
                         d = ops.make_igemm_desc([dout], segs, sk.tr[off:off + c], g, c, resid=g if acc else None)
