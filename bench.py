@@ -589,8 +589,11 @@ def run_cuda(args):
         except Exception:
             pass
     if rank == 0:
-        print(json.dumps(res))
+        print(json.dumps(res), flush=True)
     barrier()
+    import torch.distributed as dist
+    if dist.is_initialized():
+        dist.destroy_process_group()
 
 
 def ddim_bench(model, world, dev, args):
