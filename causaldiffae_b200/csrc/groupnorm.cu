@@ -389,6 +389,12 @@ __device__ __forceinline__ void load8f(const float* q, bool v4, float* o) {
   }
 }
 
+// NOTE (r2 experiment, rejected): replacing cluster.sync() below by  __syncthreads(); barrier.cluster.arrive.relaxed;
+// barrier.cluster.wait.acquire  removes the MEMBAR.ALL.GPU that the .release arrive compiles to (it drains the cp.async prefetch
+// of the next unit: -3 % on this kernel) - but it is WRONG on B200: peers' ld.shared::cluster then occasionally read stale
+// partial sums (the 500-step loss-parity run diverged; tools/r2_optgraph_debug.py reproduces it in 4 of 5 runs).  The release
+// at cluster scope is required for DSMEM visibility even when every STS of the CTA precedes a __syncthreads().
+
 // Per-thread partial sums a[8], q[8] (channels cl..cl+7 of the chunk) -> wsum[warp][0][CC], wsum[warp][1][CC].
 // Lanes with equal (lane % nvp) own the same channels (nvp is a power of two): xor-shuffle them together and let the
 // first min(nvp, 32) lanes store - plain stores, no atomics.  When nvp > 32 a warp owns a fixed subset of the channels;

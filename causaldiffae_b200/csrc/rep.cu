@@ -129,27 +129,37 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmP p) {
     }
   };
 
-  float ra[EA], rb[EB];
-  if (kb < ke) { load_a(kb, ra); load_b(kb, rb); }
-  for (int k0 = kb; k0 < ke; k0 += BK) {
-    __syncthreads();
+  // The tiles are small and the grids of this path often do not fill the chip, so one K step costs a global-load round
+  // trip, not its FMAs (ncu r2: ~1.2 us per step with ONE tile in flight).  kPD tiles are kept in flight in registers.
+  constexpr int kPD = 3;
+  float ra[kPD][EA], rb[kPD][EB];
 #pragma unroll
-    for (int j = 0; j < EA; ++j) As[a_k[j]][a_i[j]] = ra[j];
+  for (int s = 0; s < kPD; ++s)
+    if (kb + s * BK < ke) { load_a(kb + s * BK, ra[s]); load_b(kb + s * BK, rb[s]); }
+  for (int kbase = kb; kbase < ke; kbase += kPD * BK) {
 #pragma unroll
-    for (int j = 0; j < EB; ++j) Bs[b_k[j]][b_n[j]] = rb[j];
-    __syncthreads();
-    if (k0 + BK < ke) { load_a(k0 + BK, ra); load_b(k0 + BK, rb); }      // next tile's global loads overlap the FMAs
+    for (int s = 0; s < kPD; ++s) {
+      const int k0 = kbase + s * BK;
+      if (k0 >= ke) break;
+      __syncthreads();
 #pragma unroll
-    for (int kk = 0; kk < BK; ++kk) {
-      float a[TM], b[TN];
+      for (int j = 0; j < EA; ++j) As[a_k[j]][a_i[j]] = ra[s][j];
 #pragma unroll
-      for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+      for (int j = 0; j < EB; ++j) Bs[b_k[j]][b_n[j]] = rb[s][j];
+      __syncthreads();
+      if (k0 + kPD * BK < ke) { load_a(k0 + kPD * BK, ra[s]); load_b(k0 + kPD * BK, rb[s]); }
 #pragma unroll
-      for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
+      for (int kk = 0; kk < BK; ++kk) {
+        float a[TM], b[TN];
 #pragma unroll
-      for (int i = 0; i < TM; ++i)
+        for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
     }
   }
 

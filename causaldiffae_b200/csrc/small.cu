@@ -57,39 +57,72 @@ __global__ void __launch_bounds__(kDagThreads) dag_fwd_kernel(const float* __res
     zp[idx] = z;
   }
   __syncthreads();
-  for (int h = warp; h < D; h += kDagThreads / 32) {
-    float acc[kDagTB];
+  // kDagU output rows per warp and pass: their weight rows are requested together (the grid is 4 x B/8 CTAs, so a pass
+  // costs one L2 round trip whatever it computes - r2 ncu: 82 us with one row per pass)
+  constexpr int kDagU = 4, kWarps = kDagThreads / 32;
+  for (int hb = warp; hb < D; hb += kWarps * kDagU) {
+    float acc[kDagU][kDagTB];
 #pragma unroll
-    for (int s = 0; s < kDagTB; ++s) acc[s] = 0.f;
+    for (int q = 0; q < kDagU; ++q)
+#pragma unroll
+      for (int s = 0; s < kDagTB; ++s) acc[q][s] = 0.f;
     for (int k = lane * 4; k < d; k += 128) {
-      const float4 w = __ldg(reinterpret_cast<const float4*>(W1 + (size_t)h * d + k));
+      float4 w[kDagU];
+#pragma unroll
+      for (int q = 0; q < kDagU; ++q) {
+        const int h = hb + q * kWarps;
+        w[q] = h < D ? __ldg(reinterpret_cast<const float4*>(W1 + (size_t)h * d + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
       for (int s = 0; s < kDagTB; ++s) {
         const float4 z = *reinterpret_cast<const float4*>(zp + s * d + k);
-        acc[s] = fmaf(w.x, z.x, fmaf(w.y, z.y, fmaf(w.z, z.z, fmaf(w.w, z.w, acc[s]))));
+#pragma unroll
+        for (int q = 0; q < kDagU; ++q)
+          acc[q][s] = fmaf(w[q].x, z.x, fmaf(w[q].y, z.y, fmaf(w[q].z, z.z, fmaf(w[q].w, z.w, acc[q][s]))));
       }
     }
-    const float c = reduce8(acc, lane) + __ldg(b1 + h);
-    if ((lane & 3) == 0) hid[(lane >> 2) * D + h] = c > 0.f ? c : kLeaky * c;
+#pragma unroll
+    for (int q = 0; q < kDagU; ++q) {
+      const int h = hb + q * kWarps;
+      if (h < D) {
+        const float c = reduce8(acc[q], lane) + __ldg(b1 + h);
+        if ((lane & 3) == 0) hid[(lane >> 2) * D + h] = c > 0.f ? c : kLeaky * c;
+      }
+    }
   }
   __syncthreads();
-  for (int k = warp; k < d; k += kDagThreads / 32) {
-    float acc[kDagTB];
+  for (int kb = warp; kb < d; kb += kWarps * kDagU) {
+    float acc[kDagU][kDagTB];
 #pragma unroll
-    for (int s = 0; s < kDagTB; ++s) acc[s] = 0.f;
+    for (int q = 0; q < kDagU; ++q)
+#pragma unroll
+      for (int s = 0; s < kDagTB; ++s) acc[q][s] = 0.f;
     for (int h = lane * 4; h < D; h += 128) {
-      const float4 w = __ldg(reinterpret_cast<const float4*>(W2 + (size_t)k * D + h));
+      float4 w[kDagU];
+#pragma unroll
+      for (int q = 0; q < kDagU; ++q) {
+        const int k = kb + q * kWarps;
+        w[q] = k < d ? __ldg(reinterpret_cast<const float4*>(W2 + (size_t)k * D + h)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
       for (int s = 0; s < kDagTB; ++s) {
         const float4 z = *reinterpret_cast<const float4*>(hid + s * D + h);
-        acc[s] = fmaf(w.x, z.x, fmaf(w.y, z.y, fmaf(w.z, z.z, fmaf(w.w, z.w, acc[s]))));
+#pragma unroll
+        for (int q = 0; q < kDagU; ++q)
+          acc[q][s] = fmaf(w[q].x, z.x, fmaf(w[q].y, z.y, fmaf(w[q].z, z.z, fmaf(w[q].w, z.w, acc[q][s]))));
       }
     }
-    const float c = reduce8(acc, lane) + __ldg(b2 + k);
-    const int s = lane >> 2;
-    if ((lane & 3) == 0 && b0 + s < B) {
-      const size_t o = ((size_t)(b0 + s) * n + i) * d + k;
-      zpost[o] = c + u[o];
+#pragma unroll
+    for (int q = 0; q < kDagU; ++q) {
+      const int k = kb + q * kWarps;
+      if (k < d) {
+        const float c = reduce8(acc[q], lane) + __ldg(b2 + k);
+        const int s = lane >> 2;
+        if ((lane & 3) == 0 && b0 + s < B) {
+          const size_t o = ((size_t)(b0 + s) * n + i) * d + k;
+          zpost[o] = c + u[o];
+        }
+      }
     }
   }
 }

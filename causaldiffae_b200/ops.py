@@ -10,6 +10,42 @@ import torch
 from . import _lib
 from ._lib import IgemmDesc, WgradDesc, SgemmDesc, Seg, ptr, stream, check
 
+
+# ---------------------------------------------------------------------------------------------------- side stream
+# Launch sequences fork independent work (weight gradients, the bf16 weight pack) onto ONE extra stream per device; under
+# stream capture the wait_stream pairs become graph edges, so the branches run concurrently inside the replayed graph.
+_SIDE = {}
+
+
+def side_stream(which=0):
+    key = (torch.cuda.current_device(), which)
+    s = _SIDE.get(key)
+    if s is None:
+        s = _SIDE[key] = torch.cuda.Stream()
+    return s
+
+
+class on_side:
+    """with on_side(): launches inside run on the side stream, ordered after everything issued so far on the current one;
+    join_side() orders the current stream after them.  `which` selects one of several independent side streams."""
+
+    def __init__(self, which=0):
+        self.which = which
+
+    def __enter__(self):
+        self.side = side_stream(self.which)
+        self.side.wait_stream(torch.cuda.current_stream())
+        self.ctx = torch.cuda.stream(self.side)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        return self.ctx.__exit__(*exc)
+
+
+def join_side(which=0):
+    torch.cuda.current_stream().wait_stream(side_stream(which))
+
 bf16 = torch.bfloat16
 
 

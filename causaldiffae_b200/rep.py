@@ -12,10 +12,14 @@ Each runner has an explicit forward / backward over a state object of preallocat
 of the module API (`model(x, t, ...)`, `model.rep_emb.encode`).  Parameter gradients never pass through autograd: the
 backward launches accumulate straight into `param.grad` (views of the engine's flat gradient arena)."""
 import math
+import os
 
 import torch as th
 
 from . import ops
+
+# weight gradients of the conv encoder and the bf16 weight pack of the fused step run on the side stream (ops.on_side)
+REP_SIDE_STREAM = os.environ.get("CDAE_REP_SIDE_STREAM", "1") != "0"
 
 _FREQS = {}
 
@@ -214,14 +218,23 @@ class EncoderRunner:
             M, K = B * oh * ow, ci * 9
             ops.bn_lrelu_bwd_(st.dact[l], st.raw[l], st.ab[l], st.ms[l], bn.weight, st.sums, _g(bn.weight), _g(bn.bias), M, co)
             src, strides, ab = self._src(st, x, l)
-            # dW[co][k] += sum_pixels draw[m][co] * col[m][k]  (rows = conv k through the transposed im2col view)
-            ops.sgemm(_g(conv.weight), src, st.dact[l], K, co, M, (0, 0), (co, 1), (1, K), a_mode=3, c_mode=1,
-                      geo=(*strides, ci, h, w, oh, ow, ab))
+            # dW[co][k] += sum_pixels draw[m][co] * col[m][k]  (rows = conv k through the transposed im2col view); nothing
+            # on the chain reads it: it runs beside the data gradient of the same layer (both are small-grid launches)
+            gw = _g(conv.weight)
+            if REP_SIDE_STREAM:
+                with ops.on_side():
+                    ops.sgemm(gw, src, st.dact[l], K, co, M, (0, 0), (co, 1), (1, K), a_mode=3, c_mode=1,
+                              geo=(*strides, ci, h, w, oh, ow, ab))
+            else:
+                ops.sgemm(gw, src, st.dact[l], K, co, M, (0, 0), (co, 1), (1, K), a_mode=3, c_mode=1,
+                          geo=(*strides, ci, h, w, oh, ow, ab))
             _g(conv.bias)   # feeds a batch-statistics BatchNorm: its gradient is identically zero (sum of draw per channel)
             if l > 0:
                 ops.zero_(st.dact[l - 1])
                 ops.sgemm(st.dact[l - 1], st.dact[l], conv.weight, M, K, co, (co, 1), (K, 1), (0, 0), c_mode=2,
                           geo=(h * w * ci, 1, w * ci, ci, ci, h, w, oh, ow, None))
+        if REP_SIDE_STREAM:
+            ops.join_side()
 
 
 class _EncodeFn(th.autograd.Function):

@@ -163,7 +163,12 @@ class FusedStep:
                 ops.randn_(self.xi, self.rng)
                 if self.keep is not None:
                     ops.randn_(self.keep, self.rng, bernoulli=True, keep_prob=1 - m.drop_prob)
-        eng.pack(force=True)
+        from .rep import REP_SIDE_STREAM
+        if REP_SIDE_STREAM:
+            with ops.on_side():            # the bf16 weight pack (HBM-bound) runs beside the fp32 encoder (small grids)
+                eng.pack(force=True)
+        else:
+            eng.pack(force=True)
         ops.q_sample(self.x, self.noise, self.t, self.sqrt_ac, self.sqrt_1mac, out=pl.x_in)
         z = None
         if self.rep:
@@ -178,6 +183,8 @@ class FusedStep:
             ops.latent_fwd(mu, var, zp, self.xi, self.keep, self.c, self.z, self.zpm, self.kld, m.n_vars,
                            m.causal_modeling, 0.001)
             z = self.z
+        if REP_SIDE_STREAM:
+            ops.join_side()                # the FiLM projection and the torso read the packed weights
         eng.trunk.forward(self.trunk_st, self.t, self.y, self.c if m.c_dim is not None else None, z, pl.film_in,
                           self.tmap, self.tscale)
         pl._run_fwd_eager()

@@ -44,6 +44,17 @@ def main():
     data = rows[heads[k] + 1:end]
     base = int(data[0][0], 16)
     by, why = collections.Counter(), collections.defaultdict(collections.Counter)
+    if os.environ.get("BY_INSTRUCTIONS"):      # executed warp instructions per source line instead of stall samples
+        inst = collections.Counter()
+        for r in data:
+            inst[off2line.get(int(r[0], 16) - base)] += float(r[col["Instructions Executed"]] or 0)
+        tot = sum(inst.values())
+        text = open(src).read().split("\n")
+        print(f"# {rows[names[k]][1]}\n# {tot:.0f} warp instructions executed; source {src}")
+        for li, n in inst.most_common(top):
+            code = text[li - 1].strip()[:100] if li else "(no line info)"
+            print(f"{n:10.0f} {n / tot:6.1%}  L{li}: {code}")
+        return
     for r in data:
         s = float(r[col["# Samples"]] or 0)
         if not s:
