@@ -463,62 +463,66 @@ __global__ void __launch_bounds__(224, 1) igemm2_kernel(const __grid_constant__ 
                   abs_base, kABI};
 
   if (warp == 0) {
-    if (lane == 0) {
-      int kb = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int tm = tile / p.ntn, n0 = (tile % p.ntn) * BN;
-        int cw[MT], chh[MT], cn[MT];
+    // producer: the whole warp walks the loop, one elected lane issues the TMA loads (see elect_one)
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int tm = tile / p.ntn, n0 = (tile % p.ntn) * BN;
+      int cw[MT], chh[MT], cn[MT];
 #pragma unroll
-        for (int m = 0; m < MT; ++m) {
-          const int box = tm * MT + m;
-          cw[m] = (box % p.tilesW) * p.BW * p.in_stride;
-          chh[m] = ((box / p.tilesW) % p.tilesH) * p.BH * p.in_stride;
-          cn[m] = (box / boxes_per_img) * p.BNI;          // boxes past the end land beyond N: TMA zero-fills them
-        }
-        for (int sg = 0; sg < p.nseg; ++sg) {
-          const cdae_seg g = p.seg[sg];
-          const CUtensorMap* tma = &p.tmA[g.src];
-          for (int ch = 0; ch < g.nchunk; ++ch, ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
-            mbar_wait(empty_bar(s), ph ^ 1);
+      for (int m = 0; m < MT; ++m) {
+        const int box = tm * MT + m;
+        cw[m] = (box % p.tilesW) * p.BW * p.in_stride;
+        chh[m] = ((box / p.tilesW) % p.tilesH) * p.BH * p.in_stride;
+        cn[m] = (box / boxes_per_img) * p.BNI;          // boxes past the end land beyond N: TMA zero-fills them
+      }
+      for (int sg = 0; sg < p.nseg; ++sg) {
+        const cdae_seg g = p.seg[sg];
+        const CUtensorMap* tma = &p.tmA[g.src];
+        for (int ch = 0; ch < g.nchunk; ++ch) {
+          mbar_wait(empty_bar(s), ph ^ 1);
+          const uint32_t a_dst = smem_base + s * kStageBytes;
+          if (elect_one()) {
             mbar_expect_tx(full_bar(s), kStageBytes);
-            const uint32_t a_dst = smem_base + s * kStageBytes;
 #pragma unroll
             for (int m = 0; m < MT; ++m)
               tma_load_4d(a_dst + m * kATileBytes, tma, full_bar(s), g.c0 + ch * 64, cw[m] + g.dw, chh[m] + g.dh, cn[m]);
             tma_load_2d(a_dst + MT * kATileBytes, &p.tmB, full_bar(s), g.wk + ch * 64, n0);
           }
+          __syncwarp();
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    int kb = 0, it = 0;
+    // the whole warp walks the loop on warp-uniform values; one elected lane issues (see elect_one)
+    int s = 0, it = 0;
+    uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(tempty_bar(as), aph ^ 1);          // epilogue has drained this accumulator set
       tc_fence_after();
-      for (int kbl = 0; kbl < p.nkb; ++kbl, ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+      for (int kbl = 0; kbl < p.nkb; ++kbl) {
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_base + s * kStageBytes;
-          const uint64_t bdesc = smem_desc_kmajor_sw128(a_addr + MT * kATileBytes);
+        const uint32_t a_addr = smem_base + s * kStageBytes;
+        const uint64_t bdesc = smem_desc_kmajor_sw128(a_addr + MT * kATileBytes);
+        uint64_t adesc[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) adesc[m] = smem_desc_kmajor_sw128(a_addr + m * kATileBytes);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
 #pragma unroll
-            for (int m = 0; m < MT; ++m) {
-              const uint64_t adesc = smem_desc_kmajor_sw128(a_addr + m * kATileBytes);
-              umma_f16(tmem_base + (uint32_t)(as * kAccCols + m * BN), adesc + 2 * k, bdesc + 2 * k, kIdesc, (kbl | k) != 0);
-            }
+            for (int m = 0; m < MT; ++m)
+              umma_f16(tmem_base + (uint32_t)(as * kAccCols + m * BN), adesc[m] + 2 * k, bdesc + 2 * k, kIdesc, (kbl | k) != 0);
           }
           umma_commit(empty_bar(s));
           if (kbl == p.nkb - 1) umma_commit(tfull_bar(as));
         }
         __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp < 6) {
@@ -617,54 +621,60 @@ __global__ void __launch_bounds__(256, 1) igemm3_kernel(const __grid_constant__ 
                   abs_base, kABI};
 
   if (warp == 0) {
-    if (lane == 0) {
-      int ca = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int tm = tile / p.ntn;
-        int cw[MT], chh[MT], cn[MT];
+    // halo producer: the whole warp walks the loop, one elected lane issues the TMA loads (see elect_one)
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int tm = tile / p.ntn;
+      int cw[MT], chh[MT], cn[MT];
 #pragma unroll
-        for (int m = 0; m < MT; ++m) {
-          const int box = tm * MT + m;
-          cw[m] = (box % p.tilesW) * 8 - 1;
-          chh[m] = ((box / p.tilesW) % p.tilesH) * 16 - 1;
-          cn[m] = box / boxes_per_img;                    // boxes past the end land beyond N: TMA zero-fills them
-        }
-        for (int h = 0; h < p.nhs; ++h) {
-          const CUtensorMap* tma = &p.tmA[p.hs[h].src];
-          const int c0 = p.hs[h].c0, nch = p.hs[h].nchunk;
-          for (int j = 0; j < nch; ++j, ++ca) {
-            const int s = ca % AST;
-            const uint32_t ph = (ca / AST) & 1;
-            mbar_wait(aempty(s), ph ^ 1);
+      for (int m = 0; m < MT; ++m) {
+        const int box = tm * MT + m;
+        cw[m] = (box % p.tilesW) * 8 - 1;
+        chh[m] = ((box / p.tilesW) % p.tilesH) * 16 - 1;
+        cn[m] = box / boxes_per_img;                    // boxes past the end land beyond N: TMA zero-fills them
+      }
+      for (int h = 0; h < p.nhs; ++h) {
+        const CUtensorMap* tma = &p.tmA[p.hs[h].src];
+        const int c0 = p.hs[h].c0, nch = p.hs[h].nchunk;
+        for (int j = 0; j < nch; ++j) {
+          mbar_wait(aempty(s), ph ^ 1);
+          if (elect_one()) {
             mbar_expect_tx(afull(s), MT * kHaloBytes);
 #pragma unroll
             for (int m = 0; m < MT; ++m)
               tma_load_4d(a_base + s * kAStage + m * kHaloStride, tma, afull(s), c0 + j * 64, cw[m], chh[m], cn[m]);
           }
+          __syncwarp();
+          if (++s == AST) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 7) {
-    if (lane == 0) {
-      int cb = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n0 = (tile % p.ntn) * BN;
-        for (int h = 0; h < p.nhs; ++h) {
-          const int nch = p.hs[h].nchunk, ntap = p.hs[h].ntap, wk0 = p.hs[h].wk0;
-          for (int j = 0; j < nch; ++j) {
-            for (int t = 0; t < ntap; ++t, ++cb) {
-              const int s = cb % BST;
-              const uint32_t ph = (cb / BST) & 1;
-              mbar_wait(bempty(s), ph ^ 1);
+    // weight producer
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n0 = (tile % p.ntn) * BN;
+      for (int h = 0; h < p.nhs; ++h) {
+        const int nch = p.hs[h].nchunk, ntap = p.hs[h].ntap, wk0 = p.hs[h].wk0;
+        for (int j = 0; j < nch; ++j) {
+          for (int t = 0; t < ntap; ++t) {
+            mbar_wait(bempty(s), ph ^ 1);
+            if (elect_one()) {
               mbar_expect_tx(bfull(s), kBTileBytes);
               tma_load_2d(b_base + s * kBTileBytes, &p.tmB, bfull(s), wk0 + t * p.tap_stride + j * 64, n0);
             }
+            __syncwarp();
+            if (++s == BST) { s = 0; ph ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    int ca = 0, cb = 0, it = 0;
+    // the whole warp walks the loop on warp-uniform values; one elected lane issues (see elect_one)
+    int sa = 0, sb = 0, it = 0;
+    uint32_t pha = 0, phb = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aph = (it >> 1) & 1;
@@ -673,37 +683,38 @@ __global__ void __launch_bounds__(256, 1) igemm3_kernel(const __grid_constant__ 
       uint32_t first = 1;
       for (int h = 0; h < p.nhs; ++h) {
         const int nch = p.hs[h].nchunk, ntap = p.hs[h].ntap;
-        for (int j = 0; j < nch; ++j, ++ca) {
-          const int sa = ca % AST;
-          mbar_wait(afull(sa), (ca / AST) & 1);
-          for (int t = 0; t < ntap; ++t, ++cb) {
+        for (int j = 0; j < nch; ++j) {
+          mbar_wait(afull(sa), pha);
+          for (int t = 0; t < ntap; ++t) {
             // tap index -> window origin inside the halo tile (flip: data-gradient taps are negated)
             const int ti = ntap == 9 ? (p.flip ? 8 - t : t) : 4;
             const uint32_t row0 = (uint32_t)((ti / 3) * 10 + (ti % 3));
-            const int sb = cb % BST;
-            mbar_wait(bfull(sb), (cb / BST) & 1);
+            mbar_wait(bfull(sb), phb);
             tc_fence_after();
-            if (lane == 0) {
-              const uint64_t bdesc = smem_desc_kmajor_sw128(b_base + sb * kBTileBytes);
+            const uint64_t bdesc = smem_desc_kmajor_sw128(b_base + sb * kBTileBytes);
+            uint64_t adesc[MT];
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+              adesc[m] = smem_desc_kmajor_sw128_sbo(a_base + sa * kAStage + m * kHaloStride + row0 * 128, 1280);
+            if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
 #pragma unroll
-                for (int m = 0; m < MT; ++m) {
-                  const uint64_t adesc = smem_desc_kmajor_sw128_sbo(a_base + sa * kAStage + m * kHaloStride + row0 * 128, 1280);
-                  umma_f16(tmem_base + (uint32_t)(as * kAccCols + m * BN), adesc + 2 * k, bdesc + 2 * k, kIdesc,
+                for (int m = 0; m < MT; ++m)
+                  umma_f16(tmem_base + (uint32_t)(as * kAccCols + m * BN), adesc[m] + 2 * k, bdesc + 2 * k, kIdesc,
                            (first && k == 0) ? 0u : 1u);
-                }
               }
               umma_commit(bempty(sb));
+              if (t == ntap - 1) umma_commit(aempty(sa));
             }
             first = 0;
             __syncwarp();
+            if (++sb == BST) { sb = 0; phb ^= 1; }
           }
-          if (lane == 0) umma_commit(aempty(sa));
-          __syncwarp();
+          if (++sa == AST) { sa = 0; pha ^= 1; }
         }
       }
-      if (lane == 0) umma_commit(tfull_bar(as));
+      if (elect_one()) umma_commit(tfull_bar(as));
       __syncwarp();
     }
   } else if (warp < 6) {
@@ -810,43 +821,51 @@ __global__ void __launch_bounds__(256, 1) igemm3t_kernel(const __grid_constant__
   const int total_tiles = nbox * p.ntn;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int ca = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int box = tile / p.ntn;
-        const int cw = (box % p.tilesW) * 8 - 1, chh = ((box / p.tilesW) % tilesH) * 32 - 1, cn = box / boxes_per_img;
-        for (int h = 0; h < p.nhs; ++h) {
-          const CUtensorMap* tma = &p.tmA[p.hs[h].src];
-          const int c0 = p.hs[h].c0, nch = p.hs[h].nchunk;
-          for (int j = 0; j < nch; ++j, ++ca) {
-            const int s = ca % AST;
-            mbar_wait(hempty(s), ((ca / AST) & 1) ^ 1);
+    // halo producer: the whole warp walks the loop, one elected lane issues the TMA loads (see elect_one)
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int box = tile / p.ntn;
+      const int cw = (box % p.tilesW) * 8 - 1, chh = ((box / p.tilesW) % tilesH) * 32 - 1, cn = box / boxes_per_img;
+      for (int h = 0; h < p.nhs; ++h) {
+        const CUtensorMap* tma = &p.tmA[p.hs[h].src];
+        const int c0 = p.hs[h].c0, nch = p.hs[h].nchunk;
+        for (int j = 0; j < nch; ++j) {
+          mbar_wait(hempty(s), ph ^ 1);
+          if (elect_one()) {
             mbar_expect_tx(hfull(s), kHaloTBytes);
             tma_load_4d(h_base + s * kHaloTStride, tma, hfull(s), c0 + j * 64, cw, chh, cn);
           }
+          __syncwarp();
+          if (++s == AST) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 7) {
-    if (lane == 0) {
-      int cb = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n0 = (tile % p.ntn) * 128;
-        for (int h = 0; h < p.nhs; ++h) {
-          const int nch = p.hs[h].nchunk, ntap = p.hs[h].ntap, wk0 = p.hs[h].wk0;
-          for (int j = 0; j < nch; ++j) {
-            for (int t = 0; t < ntap; ++t, ++cb) {
-              const int s = cb % BST;
-              mbar_wait(wempty(s), ((cb / BST) & 1) ^ 1);
+    // weight producer
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n0 = (tile % p.ntn) * 128;
+      for (int h = 0; h < p.nhs; ++h) {
+        const int nch = p.hs[h].nchunk, ntap = p.hs[h].ntap, wk0 = p.hs[h].wk0;
+        for (int j = 0; j < nch; ++j) {
+          for (int t = 0; t < ntap; ++t) {
+            mbar_wait(wempty(s), ph ^ 1);
+            if (elect_one()) {
               mbar_expect_tx(wfull(s), kWTileBytes);
               tma_load_2d(w_base + s * kWTileBytes, &p.tmB, wfull(s), wk0 + t * p.tap_stride + j * 64, n0);
             }
+            __syncwarp();
+            if (++s == BST) { s = 0; ph ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    int ca = 0, cb = 0, it = 0;
+    // the whole warp walks the loop on warp-uniform values; one elected lane issues (see elect_one)
+    int sa = 0, sb = 0, it = 0;
+    uint32_t pha = 0, phb = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       mbar_wait(tempty_bar(as), ((it >> 1) & 1) ^ 1);
@@ -854,31 +873,30 @@ __global__ void __launch_bounds__(256, 1) igemm3t_kernel(const __grid_constant__
       uint32_t first = 1;
       for (int h = 0; h < p.nhs; ++h) {
         const int nch = p.hs[h].nchunk, ntap = p.hs[h].ntap;
-        for (int j = 0; j < nch; ++j, ++ca) {
-          const int sa = ca % AST;
-          mbar_wait(hfull(sa), (ca / AST) & 1);
-          for (int t = 0; t < ntap; ++t, ++cb) {
+        for (int j = 0; j < nch; ++j) {
+          mbar_wait(hfull(sa), pha);
+          for (int t = 0; t < ntap; ++t) {
             const int ti = ntap == 9 ? (p.flip ? 8 - t : t) : 4;
             const uint32_t row0 = (uint32_t)((ti / 3) * 10 + (ti % 3));
-            const int sb = cb % BST;
-            mbar_wait(wfull(sb), (cb / BST) & 1);
+            mbar_wait(wfull(sb), phb);
             tc_fence_after();
-            if (lane == 0) {
-              const uint64_t adesc = smem_desc_kmajor_sw128(w_base + sb * kWTileBytes);
-              const uint64_t bdesc = smem_desc_kmajor_sw128_sbo(h_base + sa * kHaloTStride + row0 * 128, 1280);
+            const uint64_t adesc = smem_desc_kmajor_sw128(w_base + sb * kWTileBytes);
+            const uint64_t bdesc = smem_desc_kmajor_sw128_sbo(h_base + sa * kHaloTStride + row0 * 128, 1280);
+            if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_f16(tmem_base + (uint32_t)(as * kAccCols), adesc + 2 * k, bdesc + 2 * k, kIdesc, (first && k == 0) ? 0u : 1u);
               umma_commit(wempty(sb));
+              if (t == ntap - 1) umma_commit(hempty(sa));
             }
             first = 0;
             __syncwarp();
+            if (++sb == BST) { sb = 0; phb ^= 1; }
           }
-          if (lane == 0) umma_commit(hempty(sa));
-          __syncwarp();
+          if (++sa == AST) { sa = 0; pha ^= 1; }
         }
       }
-      if (lane == 0) umma_commit(tfull_bar(as));
+      if (elect_one()) umma_commit(tfull_bar(as));
       __syncwarp();
     }
   } else if (warp < 6) {
@@ -1082,7 +1100,14 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
   CDAE_CHECK_ARG(d->nseg >= 1 && d->nseg <= CDAE_MAX_SEG, "igemm: nseg %d out of range", d->nseg);
   CDAE_CHECK_SHAPE(d->in_stride == 1 || d->in_stride == 2, "igemm: in_stride %d", d->in_stride);
   CDAE_CHECK_SHAPE(d->wk % 8 == 0, "igemm: weight K %d must be a multiple of 8", d->wk);
-  CDAE_CHECK_SHAPE((d->sps == 0 || d->sps == 1) && d->ooh == 0 && d->oow == 0, "igemm: strided output placement is not supported");
+  // strided output placement (sps = 2): tile pixel (y, x) is stored at (y*sps + ooh, x*sps + oow) of the [OH, OW] output - one
+  // parity class of a stride-2 data gradient (conv_transpose).  Expressed in the TMA maps of the output / residual alone.
+  const int sps = d->sps > 0 ? d->sps : 1;
+  CDAE_CHECK_SHAPE((sps == 1 && d->ooh == 0 && d->oow == 0) ||
+                       (sps == 2 && d->ooh >= 0 && d->ooh < 2 && d->oow >= 0 && d->oow < 2 && d->out_mode == 0 && !d->stats &&
+                        !d->gnb_ws && !d->bias_img),
+                   "igemm: output placement sps=%d ooh=%d oow=%d unsupported (stride 2 needs a plain NHWC launch)", d->sps, d->ooh,
+                   d->oow);
   IgemmKParams kp;
   memset(&kp, 0, sizeof(kp));
   const int es = d->in_stride;
@@ -1123,8 +1148,8 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
                                  (reinterpret_cast<uintptr_t>(d->stats) & 15) == 0),
                    "igemm: channel statistics need NHWC output, cout %% 64 == 0 and >= 32 output pixels per image");
   CDAE_CHECK_SHAPE(kp.out_mode != 0 || (d->cout % 8 == 0 && d->ldo % 8 == 0), "igemm: NHWC output needs cout, ldo %% 8 == 0");
-  CDAE_CHECK_SHAPE(kp.out_mode == 1 || (d->OH == OHt && d->OW == OWt), "igemm: output dims %dx%d do not match the tile grid %dx%d",
-                   d->OH, d->OW, OHt, OWt);
+  CDAE_CHECK_SHAPE(kp.out_mode == 1 || (d->OH == OHt * sps && d->OW == OWt * sps),
+                   "igemm: output dims %dx%d do not match the tile grid %dx%d", d->OH, d->OW, OHt, OWt);
   CDAE_CHECK_SHAPE(!d->resid || (d->ldr % 8 == 0 && kp.out_mode == 0), "igemm: residual needs NHWC output and pitch %% 8");
   const int nboxes = kp.tilesW * kp.tilesH * tilesN;
   int bn = d->bn, mt = 1;
@@ -1168,16 +1193,18 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
     uint32_t box[4] = {slabw, (uint32_t)kp.BW, (uint32_t)kp.BH, (uint32_t)kp.BNI};
     {
       const uint64_t L = d->ldo;
-      uint64_t dims[4] = {(uint64_t)d->cout, (uint64_t)d->OW, (uint64_t)d->OH, (uint64_t)d->N};
-      uint64_t str[3] = {L * 2, L * 2 * d->OW, L * 2 * (uint64_t)d->OW * d->OH};
-      int rc = make_tmap_bf16(&kp.tmO, d->out, 4, dims, str, box, nullptr, slabw == 64);
+      uint64_t dims[4] = {(uint64_t)d->cout, (uint64_t)OWt, (uint64_t)OHt, (uint64_t)d->N};
+      uint64_t str[3] = {L * 2 * sps, L * 2 * d->OW * sps, L * 2 * (uint64_t)d->OW * d->OH};
+      char* base = reinterpret_cast<char*>(d->out) + ((size_t)d->ooh * d->OW + d->oow) * L * 2;
+      int rc = make_tmap_bf16(&kp.tmO, base, 4, dims, str, box, nullptr, slabw == 64);
       if (rc) return rc;
     }
     if (d->resid) {
       const uint64_t L = d->ldr;
-      uint64_t dims[4] = {(uint64_t)d->cout, (uint64_t)d->OW, (uint64_t)d->OH, (uint64_t)d->N};
-      uint64_t str[3] = {L * 2, L * 2 * d->OW, L * 2 * (uint64_t)d->OW * d->OH};
-      int rc = make_tmap_bf16(&kp.tmR, d->resid, 4, dims, str, box, nullptr, slabw == 64);
+      uint64_t dims[4] = {(uint64_t)d->cout, (uint64_t)OWt, (uint64_t)OHt, (uint64_t)d->N};
+      uint64_t str[3] = {L * 2 * sps, L * 2 * d->OW * sps, L * 2 * (uint64_t)d->OW * d->OH};
+      const char* base = reinterpret_cast<const char*>(d->resid) + ((size_t)d->ooh * d->OW + d->oow) * L * 2;
+      int rc = make_tmap_bf16(&kp.tmR, base, 4, dims, str, box, nullptr, slabw == 64);
       if (rc) return rc;
     }
     if (d->gnb_ws) {      // x slabs of the GroupNorm input arrive over the residual path: one map per concatenated source
@@ -1292,16 +1319,17 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ Wgra
 
   if (nkb > 0) {
     if (warp == 0) {
-      if (lane == 0) {
-        for (int kb = 0; kb < nkb; ++kb) {
-          const int t = t_begin + kb;
-          const int tw = t % p.tilesW, th = (t / p.tilesW) % p.tilesH, tn = t / (p.tilesW * p.tilesH);
-          const int s = kb % STAGES;
-          const uint32_t ph = (kb / STAGES) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1);
+      // producer: the whole warp walks the loop, one elected lane issues the TMA loads (see elect_one)
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int t = t_begin + kb;
+        const int tw = t % p.tilesW, th = (t / p.tilesW) % p.tilesH, tn = t / (p.tilesW * p.tilesH);
+        mbar_wait(empty_bar(s), ph ^ 1);
+        const uint32_t a_dst = smem_base + s * kStageBytes;
+        const int ow = tw * p.bw, oh = th * p.bh, nn = tn * p.bni;
+        if (elect_one()) {
           mbar_expect_tx(full_bar(s), kStageBytes);
-          const uint32_t a_dst = smem_base + s * kStageBytes;
-          const int ow = tw * p.bw, oh = th * p.bh, nn = tn * p.bni;
           tma_load_4d(a_dst, &p.tmDy, full_bar(s), co0, ow, oh, nn);
           tma_load_4d(a_dst + kWgBoxBytes, &p.tmDy, full_bar(s), co0 + 64, ow, oh, nn);
 #pragma unroll
@@ -1309,32 +1337,36 @@ __global__ void __launch_bounds__(192) wgrad_kernel(const __grid_constant__ Wgra
             tma_load_4d(a_dst + kABytes + j * kWgBoxBytes, &p.tmX, full_bar(s), p.c0 + ci0 + j * 64, ow * p.es + dw,
                         oh * p.es + dh, nn);
         }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     } else if (warp == 1) {
-      int bias_started = 0;
+      // the whole warp walks the loop on warp-uniform values; one elected lane issues (see elect_one)
+      int bias_started = 0, s = 0;
+      uint32_t ph = 0;
+      const uint64_t odesc = smem_desc_mnmajor_sw128(smem_u32(ones), 0, 1024);
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_base + s * kStageBytes;
-          // MN-major: 64-channel blocks kWgBoxBytes apart (LBO), 8-pixel K groups 1024 B apart (SBO)
-          const uint64_t adesc = smem_desc_mnmajor_sw128(a_addr, kWgBoxBytes, 1024);
-          const uint64_t bdesc = smem_desc_mnmajor_sw128(a_addr + kABytes, kWgBoxBytes, 1024);
+        const uint32_t a_addr = smem_base + s * kStageBytes;
+        // MN-major: 64-channel blocks kWgBoxBytes apart (LBO), 8-pixel K groups 1024 B apart (SBO)
+        const uint64_t adesc = smem_desc_mnmajor_sw128(a_addr, kWgBoxBytes, 1024);
+        const uint64_t bdesc = smem_desc_mnmajor_sw128(a_addr + kABytes, kWgBoxBytes, 1024);
+        const bool with_bias = p.dbias && (t_begin + kb) % bcols == bcol;
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // K = 16 pixels = two 1024 B atoms = +128 in the >>4 address field
             umma_f16(tmem_base, adesc + 128 * k, bdesc + 128 * k, kIdesc, (kb | k) != 0);
-          if (p.dbias && (t_begin + kb) % bcols == bcol) {
-            const uint64_t odesc = smem_desc_mnmajor_sw128(smem_u32(ones), 0, 1024);
+          if (with_bias) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_f16(tmem_base + BN, adesc + 128 * k, odesc, kIdescOnes, (bias_started | k) != 0);
-            bias_started = 1;
           }
           umma_commit(empty_bar(s));
           if (kb == nkb - 1) umma_commit(tmem_full_bar);
         }
+        if (with_bias) bias_started = 1;
         __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     } else {
       const int q = warp & 3;
@@ -1454,15 +1486,16 @@ __global__ void __launch_bounds__(192) wgrad3_kernel(const __grid_constant__ Wgr
 
   if (nkb > 0) {
     if (warp == 0) {
-      if (lane == 0) {
-        for (int kb = 0; kb < nkb; ++kb) {
-          const int t = t_begin + kb;
-          const int tw = t % p.tilesW, th = (t / p.tilesW) % p.tilesH, tn = t / (p.tilesW * p.tilesH);
-          const int s = kb % STAGES;
-          const uint32_t ph = (kb / STAGES) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1);
+      // producer: the whole warp walks the loop, one elected lane issues the TMA loads (see elect_one)
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int t = t_begin + kb;
+        const int tw = t % p.tilesW, th = (t / p.tilesW) % p.tilesH, tn = t / (p.tilesW * p.tilesH);
+        mbar_wait(empty_bar(s), ph ^ 1);
+        const uint32_t a_dst = smem_base + s * kStageBytes;
+        if (elect_one()) {
           mbar_expect_tx(full_bar(s), kW3DyBytes + kXBytes);
-          const uint32_t a_dst = smem_base + s * kStageBytes;
           tma_load_4d(a_dst, &p.tmDy, full_bar(s), co0, tw * 8, th * 8, tn);
           tma_load_4d(a_dst + kWgBoxBytes, &p.tmDy, full_bar(s), co0 + 64, tw * 8, th * 8, tn);
 #pragma unroll
@@ -1470,36 +1503,42 @@ __global__ void __launch_bounds__(192) wgrad3_kernel(const __grid_constant__ Wgr
             tma_load_4d(a_dst + kW3DyBytes + j * kW3XBlk, &p.tmX, full_bar(s), p.c0 + ci0 + j * 64, tw * 8 - 1,
                         th * 8 + krow - 1, tn);
         }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     } else if (warp == 1) {
-      int bias_started = 0;
+      // the whole warp walks the loop on warp-uniform values; one elected lane issues (see elect_one)
+      int bias_started = 0, s = 0;
+      uint32_t ph = 0;
+      const uint64_t odesc = smem_desc_mnmajor_sw128(smem_u32(ones), 0, 1024);
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_base + s * kStageBytes;
-          // A = dY^T: 64-channel blocks kWgBoxBytes apart (LBO), 8-pixel K groups 1024 B apart (SBO)
-          const uint64_t adesc = smem_desc_mnmajor_sw128(a_addr, kWgBoxBytes, 1024);
+        const uint32_t a_addr = smem_base + s * kStageBytes;
+        // A = dY^T: 64-channel blocks kWgBoxBytes apart (LBO), 8-pixel K groups 1024 B apart (SBO)
+        const uint64_t adesc = smem_desc_mnmajor_sw128(a_addr, kWgBoxBytes, 1024);
+        // B = shifted source window: pixel (h, w) of the tile sits at halo row h*10 + w + tap
+        uint64_t bdesc[3];
+#pragma unroll
+        for (int tap = 0; tap < 3; ++tap) bdesc[tap] = smem_desc_mnmajor_sw128(a_addr + kW3DyBytes + tap * 128, kW3XBlk, 1280);
+        const bool with_bias = p.dbias && (t_begin + kb) % bcols == bcol;
+        if (elect_one()) {
 #pragma unroll
           for (int tap = 0; tap < 3; ++tap) {
-            // B = shifted source window: pixel (h, w) of the tile sits at halo row h*10 + w + tap
-            const uint64_t bdesc = smem_desc_mnmajor_sw128(a_addr + kW3DyBytes + tap * 128, kW3XBlk, 1280);
 #pragma unroll
             for (int k = 0; k < 4; ++k)   // K = 16 pixels = two image rows of the tile: +2 SBO steps per MMA
-              umma_f16(tmem_base + tap * BN, adesc + 128 * k, bdesc + 160 * k, kIdesc, (kb | k) != 0);
+              umma_f16(tmem_base + tap * BN, adesc + 128 * k, bdesc[tap] + 160 * k, kIdesc, (kb | k) != 0);
           }
-          if (p.dbias && (t_begin + kb) % bcols == bcol) {
-            const uint64_t odesc = smem_desc_mnmajor_sw128(smem_u32(ones), 0, 1024);
+          if (with_bias) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_f16(tmem_base + 3 * BN, adesc + 128 * k, odesc, kIdescOnes, (bias_started | k) != 0);
-            bias_started = 1;
           }
           umma_commit(empty_bar(s));
           if (kb == nkb - 1) umma_commit(tmem_full_bar);
         }
+        if (with_bias) bias_started = 1;
         __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     } else {
       const int q = warp & 3;

@@ -95,6 +95,17 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate, one CTA.
+// One thread of a converged warp.  tcgen05.mma / tcgen05.commit / TMA are issued from the uniform datapath: under an
+// `if (lane == 0)` branch ptxas wraps EVERY such instruction in an ELECT / BRA.U.ANY loop over the active lanes (5 of them
+// around the 4 MMAs + commit of a K step: ~90 dependent uniform instructions, ~770 cycles per K step in the r2 ncu capture of
+// the 8x8 layers - more than the MMAs themselves).  With the loop run by the whole warp on warp-uniform values and the issue
+// predicated on elect.sync, the 4 UTCHMMA + UTCBAR come out back to back behind ONE ELECT.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n.reg .pred p;\n"

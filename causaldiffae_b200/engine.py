@@ -40,6 +40,8 @@ FUSED_GN_BWD = os.environ.get("CDAE_FUSED_GN_BWD", "0") != "0"
 # reads a weight gradient, so every wgrad launch only has to wait for the kernel that produced its dY and has to be done by
 # the end of the backward.  In the captured graph this becomes a side branch: its CTAs fill the tail waves and launch gaps of
 # the chain (both kinds of kernel occupy a whole SM per CTA, so this is interleaving, not co-residency).
+# stride-2 data gradients as four parity-class launches (0: one full-resolution conv over a zero-inserted dy)
+S2_DGRAD_CLASSES = os.environ.get("CDAE_S2_DGRAD_CLASSES", "1") != "0"
 WGRAD_SIDE_STREAM = os.environ.get("CDAE_WGRAD_SIDE_STREAM", "1") != "0"
 
 
@@ -500,7 +502,29 @@ class Engine:
                                      dw_ld=cw.cin, dbias=gb if (fused_bias and si == 0) else None)
             fns.append(_side(lambda wd=wd: ops.wgrad(wd)))
             off += c
-        if need_dgrad:
+        if need_dgrad and stride == 2 and S2_DGRAD_CLASSES:
+            # conv_transpose by output parity: dx[2m+a, 2q+b] only sees the taps kh = a+1 (mod 2), kw = b+1 (mod 2) - 1, 2, 2
+            # and 4 of the 9 - at dy[m + (a+1-kh)/2, q + (b+1-kw)/2].  Four launches over the LOW-resolution dy that store
+            # with pixel stride 2 (cdae_igemm_desc.sps / ooh / oow), instead of one full-resolution 9-tap conv over a
+            # zero-inserted copy of dy (4x the MMA work, one more pass over HBM).  ref unet.py:97-105 backward.
+            nco = dy.shape[-1]
+            if nco != cw.cout_tr_pad:
+                raise _lib.CdaeError("internal: dy pitch does not match the transposed weight packing")
+            off = 0
+            for s in srcs:
+                c = s.shape[3]
+                acc, g = s.grad_acc(), s.grad()
+                s.gnb = None                         # a plain gradient: the norm's backward must reduce itself
+                for a in range(2):
+                    for b in range(2):
+                        khs = [(1, 0)] if a == 0 else [(0, 1), (2, 0)]          # (tap, shift in dy)
+                        kws = [(1, 0)] if b == 0 else [(0, 1), (2, 0)]
+                        segs = [(0, dh, dw, 0, nco // 64, (kh * 3 + kw) * nco) for kh, dh in khs for kw, dw in kws]
+                        d = ops.make_igemm_desc([dy], segs, cw.tr[off:off + c], g, c, resid=g if acc else None,
+                                                sps=2, ooh=a, oow=b)
+                        fns.append(lambda d=d: ops.igemm(d))
+                off += c
+        elif need_dgrad:
             dyz = dy
             if stride == 2:
                 dyz = pl.alloc((dy.shape[0], dy.shape[1] * 2, dy.shape[2] * 2, dy.shape[3]))

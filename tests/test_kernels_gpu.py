@@ -296,6 +296,30 @@ def test_igemm_dgrad_matches_autograd():
     assert relerr(nchw(dx), x.grad) < 5e-3
 
 
+@pytest.mark.parametrize("N,H,cin,cout,acc", [(2, 32, 128, 128, False), (3, 16, 256, 192, True), (2, 8, 384, 384, False)])
+def test_stride2_dgrad_parity_classes_match_autograd(N, H, cin, cout, acc):
+    """data gradient of a 3x3 stride-2 pad-1 conv (Downsample, ref unet.py:97-105) as four launches over the low-resolution
+    dy, one per output parity, stored with pixel stride 2 (cdae_igemm_desc.sps / ooh / oow); acc: added to what dx holds"""
+    from causaldiffae_b200 import ops
+    g = torch.Generator().manual_seed(H + cin)
+    x = torch.randn(N, cin, H, H, generator=g).to(dev()).requires_grad_(True)
+    w = (torch.randn(cout, cin, 3, 3, generator=g) * 0.03).to(dev()).to(bf16).float()
+    dy = torch.randn(N, cout, H // 2, H // 2, generator=g).to(dev()).to(bf16).float()
+    F.conv2d(x, w, stride=2, padding=1).backward(dy)
+    wt = w.permute(1, 2, 3, 0).reshape(cin, 9 * cout).contiguous().to(bf16)     # [Cin][tap][Cout]
+    base = torch.randn(N, H, H, cin, generator=g).to(dev()).to(bf16)
+    dx = base.clone() if acc else torch.full((N, H, H, cin), float("nan"), device=dev(), dtype=bf16)
+    for a in range(2):
+        for b in range(2):
+            khs = [(1, 0)] if a == 0 else [(0, 1), (2, 0)]
+            kws = [(1, 0)] if b == 0 else [(0, 1), (2, 0)]
+            segs = [(0, dh, dw, 0, cout // 64, (kh * 3 + kw) * cout) for kh, dh in khs for kw, dw in kws]
+            ops.igemm(ops.make_igemm_desc([nhwc(dy)], segs, wt, dx, cin, resid=dx if acc else None, sps=2, ooh=a, oow=b))
+    ref = x.grad + (nchw(base) if acc else 0)
+    assert torch.isfinite(dx.float()).all()
+    assert relerr(nchw(dx), ref) < 5e-3
+
+
 @pytest.mark.parametrize("N,H,cin,cout,ksize,stride", [(2, 32, 128, 128, 3, 1), (4, 8, 256, 128, 3, 1), (2, 16, 64, 64, 3, 1),
                                                        (3, 16, 192, 256, 1, 1), (2, 32, 128, 128, 3, 2), (8, 4, 128, 128, 3, 1),
                                                        (2, 64, 64, 128, 3, 1), (3, 12, 128, 192, 3, 1), (2, 16, 256, 256, 3, 1), (5, 8, 512, 64, 1, 1)])
