@@ -198,16 +198,19 @@ def test_cfg2_masking_500_step_loss_parity_then_guided_ddim_psnr():
     print("cfg2 masking: smoothed loss (ours)", np.round(sm_m, 4))
     print("cfg2 masking: smoothed loss (ref) ", np.round(sm_t, 4))
     print("cfg2 masking: max rel diff (50-step windows)", rel.max())
-    # the Bernoulli keep-mask halves the effective batch of the conditional branch: 50-step windows of 16 samples carry
-    # ~2 % sampling noise of their own between two bf16/fp32 trajectories (measured 1.98 %), so the gate is taken on
-    # 100-step windows and the 50-step figure is bounded more loosely
+    # What the gate can resolve: two runs of THIS implementation on identical draws already differ by up to 4.3 % in a 100-step
+    # window, 5.5 % in a 50-step window and 0.2 - 0.4 % in the whole-run mean (tools/r2_traj_noise.py: the weight gradients are
+    # accumulated with fp32 atomics, Adam amplifies the last-bit differences, and the Bernoulli keep-mask halves the effective
+    # batch of 16).  Against the fp32 oracle the measured figures are 0.1 - 2.1 % per 100-step window and 0.6 - 1.3 % for their
+    # mean.  The north-star tolerance is "training loss within 2 % over 500 steps": the gate is that figure on the whole run (and
+    # on the run without its first 100 steps, where both losses are still near 1), plus a 6 % bound on single 100-step windows.
     rel100 = np.abs(mine.reshape(-1, 100).mean(1) - theirs.reshape(-1, 100).mean(1)) / theirs.reshape(-1, 100).mean(1)
-    print("cfg2 masking: max rel diff (100-step windows)", rel100.max())
-    # (measured over repeated runs: 100-step windows 0.1 - 2.1 %, their mean 0.3 - 0.7 %; the trajectories are not bit-stable
-    # from run to run either - fp32 atomics in the weight gradients - so single windows are gated at 3 %, the mean at 1 %)
-    assert rel100.max() < 0.03, rel100
-    assert rel100.mean() < 0.01, rel100
-    assert rel.max() < 0.04, rel
+    whole = abs(mine.mean() - theirs.mean()) / theirs.mean()
+    late = abs(mine[100:].mean() - theirs[100:].mean()) / theirs[100:].mean()
+    print("cfg2 masking: rel diff per 100-step window", np.round(rel100, 4), "whole run:", round(float(whole), 4),
+          "after step 100:", round(float(late), 4))
+    assert whole < 0.02 and late < 0.02, (whole, late)
+    assert rel100.max() < 0.06, rel100
 
     # ---- guided (w) DDIM-50 and DDIM-100 counterfactual PSNR on the trained weights
     trained = {k: v.detach().float().clone().contiguous() for k, v in model.state_dict().items()}
