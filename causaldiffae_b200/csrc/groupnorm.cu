@@ -1212,7 +1212,9 @@ extern "C" int cdae_gn_apply_fwd(const void* x0, int C0, const float* stats0, co
                                  int B, int HW, const float* gamma, const float* beta, const float* film, int film_ld,
                                  int film_off, int silu, void* y, float* mean, float* rstd, float* ab, cdae_stream s) {
   if (B == 0 || HW == 0) return CDAE_OK;
-  CDAE_CHECK_ARG(x0 && stats0 && gamma && beta && y && mean && rstd && (C1 == 0 || (x1 && stats1)), "gn_apply_fwd: null pointer");
+  // y == nullptr: constants only - the {a, b} table (and mean / rstd) for a consumer that applies the norm while it loads its
+  // operand (cdae_igemm_desc.gn_ab); one CTA per image, nothing is streamed
+  CDAE_CHECK_ARG(x0 && stats0 && gamma && beta && (y || ab) && mean && rstd && (C1 == 0 || (x1 && stats1)), "gn_apply_fwd: null pointer");
   CDAE_CHECK_ARG((reinterpret_cast<uintptr_t>(ab) & 7) == 0, "gn_apply_fwd: misaligned constant table");
   GnApplyParams p;
   memset(&p, 0, sizeof(p));
@@ -1235,6 +1237,7 @@ extern "C" int cdae_gn_apply_fwd(const void* x0, int C0, const float* stats0, co
   if (ppc > HW) ppc = HW;
   p.ppc = ppc;
   dim3 grid((unsigned)((HW + ppc - 1) / ppc), (unsigned)B);
+  if (!y) { p.ppc = 0; grid.x = 1; }
   const size_t smem = sizeof(float) * (2 * (size_t)p.C + 2 * kGroups);
   if (silu) gn_apply_fwd_kernel<true><<<grid, kApplyThreads, smem, (cudaStream_t)s>>>(p);
   else gn_apply_fwd_kernel<false><<<grid, kApplyThreads, smem, (cudaStream_t)s>>>(p);

@@ -90,6 +90,8 @@ struct alignas(64) IgemmKParams {
   // halo kernel (3x3 stride 1): K is walked source-chunk-major; each 64-channel chunk brings ONE halo tile per box
   struct { int src, c0, nchunk, ntap, wk0; } hs[8];
   int nhs, tap_stride, flip;
+  // GroupNorm+SiLU on load (cdae_igemm_desc.gn_*): per halo segment the first table column of its channels, or -1
+  const float* gn_ab; int gn_c; int gn_col[8];
 };
 
 constexpr int kATileBytes = 128 * 128;  // 128 pixels x 64 bf16
@@ -775,8 +777,11 @@ __device__ __forceinline__ uint32_t bf16_bits(float f) {
   return (uint32_t)(*reinterpret_cast<const uint16_t*>(&h));
 }
 
-template <int AST, int BST, int NS>
-__global__ void __launch_bounds__(256, 1) igemm3t_kernel(const __grid_constant__ IgemmKParams p) {
+// GN: kGnWarps more warps (8..) normalise + activate every halo tile in place between the TMA load and the MMAs
+// (cdae_igemm_desc.gn_*): thread = one 16-byte chunk column (8 channels, constants in registers) x every (4 kGnWarps)-th row.
+constexpr int kGnWarps = 8;
+template <int AST, int BST, int NS, bool GN>
+__global__ void __launch_bounds__(GN ? 256 + 32 * kGnWarps : 256, 1) igemm3t_kernel(const __grid_constant__ IgemmKParams p) {
   constexpr int kWTileBytes = 128 * 128;                 // 128 output channels x 64 k
   constexpr int kSlabStride = 128 * 128;
   constexpr uint32_t kAccCols = 256;
@@ -787,8 +792,8 @@ __global__ void __launch_bounds__(256, 1) igemm3t_kernel(const __grid_constant__
   uint8_t* wsm = smem + AST * kHaloTStride;
   uint8_t* stg = wsm + BST * kWTileBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stg + NS * kSlabStride);
-  // bars: hfull[AST] hempty[AST] wfull[BST] wempty[BST] tfull[2] tempty[2] sready[NS] sfree[NS]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * AST + 2 * BST + 4 + 2 * NS);
+  // bars: hfull[AST] hempty[AST] wfull[BST] wempty[BST] tfull[2] tempty[2] sready[NS] sfree[NS] hready[AST]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * AST + 2 * BST + 4 + 2 * NS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t h_base = smem_u32(smem), w_base = smem_u32(wsm), stg_base = smem_u32(stg);
   const uint32_t bar_base = smem_u32(bars);
@@ -800,9 +805,10 @@ __global__ void __launch_bounds__(256, 1) igemm3t_kernel(const __grid_constant__
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * AST + 2 * BST + 2 + a); };
   auto sready_bar = [&](int b) { return bar_base + 8u * (2 * AST + 2 * BST + 4 + b); };
   auto sfree_bar = [&](int b) { return bar_base + 8u * (2 * AST + 2 * BST + 4 + NS + b); };
+  auto hready = [&](int s) { return bar_base + 8u * (2 * AST + 2 * BST + 4 + 2 * NS + s); };   // GN: tile transformed
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < AST; ++s) { mbar_init(hfull(s), 1); mbar_init(hempty(s), 1); }
+    for (int s = 0; s < AST; ++s) { mbar_init(hfull(s), 1); mbar_init(hempty(s), 1); mbar_init(hready(s), kGnWarps); }
     for (int s = 0; s < BST; ++s) { mbar_init(wfull(s), 1); mbar_init(wempty(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
     for (int b = 0; b < NS; ++b) { mbar_init(sready_bar(b), 1); mbar_init(sfree_bar(b), 1); }
@@ -874,7 +880,7 @@ __global__ void __launch_bounds__(256, 1) igemm3t_kernel(const __grid_constant__
       for (int h = 0; h < p.nhs; ++h) {
         const int nch = p.hs[h].nchunk, ntap = p.hs[h].ntap;
         for (int j = 0; j < nch; ++j) {
-          mbar_wait(hfull(sa), pha);
+          mbar_wait(GN ? hready(sa) : hfull(sa), pha);
           for (int t = 0; t < ntap; ++t) {
             const int ti = ntap == 9 ? (p.flip ? 8 - t : t) : 4;
             const uint32_t row0 = (uint32_t)((ti / 3) * 10 + (ti % 3));
@@ -1017,24 +1023,71 @@ __global__ void __launch_bounds__(256, 1) igemm3t_kernel(const __grid_constant__
         }
       }
     }
+  } else if (GN && warp >= 8) {
+    // ---------------------------------------------------------------- GroupNorm + SiLU on the halo tile, in place
+    // walks the halo stages in the producer's order; segments without a table (the 1x1-skip sources) pass through
+    const int tt = (int)threadIdx.x - 256;                   // 0 .. 32 kGnWarps - 1
+    const uint32_t ck = (uint32_t)(tt & 7);                  // logical 16-byte chunk: channels ck*8 .. +7 of the 64
+    const int r0 = tt >> 3;                                  // rows r0, r0 + 4 kGnWarps, ...
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int box = tile / p.ntn;
+      const int cw = (box % p.tilesW) * 8 - 1, chh = ((box / p.tilesW) % tilesH) * 32 - 1, cn = box / boxes_per_img;
+      for (int h = 0; h < p.nhs; ++h) {
+        const int nch = p.hs[h].nchunk, col0 = p.gn_col[h];
+        for (int j = 0; j < nch; ++j) {
+          float2 ab[8];
+          if (col0 >= 0) {                                   // constants first: they do not depend on the tile
+            const float4* q = reinterpret_cast<const float4*>(p.gn_ab + ((size_t)cn * p.gn_c + col0 + j * 64 + ck * 8) * 2);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float4 v = __ldg(q + e);
+              ab[2 * e] = make_float2(v.x, v.y); ab[2 * e + 1] = make_float2(v.z, v.w);
+            }
+          }
+          mbar_wait(hfull(s), ph);
+          if (col0 >= 0) {
+            const uint32_t tb = h_base + s * kHaloTStride;
+            for (int r = r0; r < kHaloTRows; r += 4 * kGnWarps) {
+              const int hh = r / 10, ww = r - hh * 10;
+              if ((unsigned)(chh + hh) >= (unsigned)p.OHt || (unsigned)(cw + ww) >= (unsigned)p.OWt) continue;   // padding stays 0
+              const uint32_t a = tb + (uint32_t)r * 128u + ((ck ^ (uint32_t)(r & 7)) << 4);
+              float f[8];
+              unpack8(lds8(a), f);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float hv = fmaf(f[e], ab[e].x, ab[e].y);
+                f[e] = fmaf(hv, tanh_fast(hv), hv);
+              }
+              sts8(a, pack8(f));
+            }
+            fence_proxy_async();                             // generic-proxy stores -> visible to the MMA's async-proxy reads
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(hready(s));
+          if (++s == AST) { s = 0; ph ^= 1; }
+        }
+      }
+    }
   }
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-template <int AST, int BST, int NS>
+template <int AST, int BST, int NS, bool GN = false>
 static int launch_igemm3t(const IgemmKParams& kp, cudaStream_t st) {
   constexpr int smem = AST * kHaloTStride + BST * 128 * 128 + NS * 128 * 128 + 1024 + 512;
   static_assert(smem <= 227 * 1024, "igemm3t: shared memory budget");
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(igemm3t_kernel<AST, BST, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_err = cudaFuncSetAttribute(igemm3t_kernel<AST, BST, NS, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   });
   if (attr_err != cudaSuccess) { set_error("igemm3t smem attribute: %s", cudaGetErrorString(attr_err)); return CDAE_ERR_CUDA; }
   const int total = kp.tilesW * (kp.OHt / 32) * kp.Nimg * kp.ntn;
   const int grid = total < kNumSMs ? total : kNumSMs;
-  igemm3t_kernel<AST, BST, NS><<<grid, 256, smem, st>>>(kp);
+  igemm3t_kernel<AST, BST, NS, GN><<<grid, GN ? 256 + 32 * kGnWarps : 256, smem, st>>>(kp);
   CDAE_CHECK_LAUNCH("igemm3t_kernel");
   return CDAE_OK;
 }
@@ -1228,6 +1281,22 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
   }
   kp.nseg = d->nseg; kp.nkb = nkb; kp.nboxes = nboxes; kp.ntn = ntn;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
+  if (d->gn_ab) {
+    CDAE_CHECK_SHAPE(use_t && !d->gnb_ws && d->gn_c > 0 && (reinterpret_cast<uintptr_t>(d->gn_ab) & 15) == 0 && d->gn_c % 4 == 0,
+                     "igemm: GroupNorm on load needs a 3x3 stride-1 layer with cout %% 128 == 0 on an image that tiles into 8x32 "
+                     "boxes, a 16-byte aligned table and gn_c %% 4 == 0");
+    kp.gn_ab = d->gn_ab; kp.gn_c = d->gn_c;
+    for (int h = 0; h < kp.nhs; ++h) {
+      const int off = d->gn_off[kp.hs[h].src];
+      CDAE_CHECK_SHAPE(off < 0 || (kp.hs[h].ntap == 9 && (off + kp.hs[h].c0) % 8 == 0 &&
+                                   off + kp.hs[h].c0 + kp.hs[h].nchunk * 64 <= d->gn_c),
+                       "igemm: GroupNorm on load: source %d (columns %d..) does not fit the table of %d channels", kp.hs[h].src, off,
+                       d->gn_c);
+      kp.gn_col[h] = off < 0 ? -1 : off + kp.hs[h].c0;
+    }
+    // three halo stages: load -> transform -> MMA are all in flight (2/5/3 and 2/4/4 measured 1-3 % slower, r2_gnload_bench)
+    return launch_igemm3t<3, 3, 3, true>(kp, st);
+  }
   if (use_t) {
     static const char* tcfg = getenv("CDAE_T_CFG");           // staging experiments: halo stages / weight stages / slabs
     if (tcfg && tcfg[0] == '3') return launch_igemm3t<3, 3, 3>(kp, st);

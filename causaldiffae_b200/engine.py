@@ -42,6 +42,8 @@ FUSED_GN_BWD = os.environ.get("CDAE_FUSED_GN_BWD", "0") != "0"
 # the chain (both kinds of kernel occupy a whole SM per CTA, so this is interleaving, not co-residency).
 # stride-2 data gradients as four parity-class launches (0: one full-resolution conv over a zero-inserted dy)
 S2_DGRAD_CLASSES = os.environ.get("CDAE_S2_DGRAD_CLASSES", "1") != "0"
+# inference: GroupNorm(+FiLM)+SiLU applied by the consuming 3x3 conv while it loads its operand (no activated tensor)
+GN_ON_LOAD = os.environ.get("CDAE_GN_ON_LOAD", "1") != "0"
 WGRAD_SIDE_STREAM = os.environ.get("CDAE_WGRAD_SIDE_STREAM", "1") != "0"
 
 
@@ -455,9 +457,11 @@ class Engine:
         return self.grad_of(p)
 
     def plan_conv(self, pl, cw, srcs, out, ksize, stride=1, resid=None, skip=None, skip_srcs=None, out_mode=0,
-                  need_dgrad=True, stats=False, bias_img=None):
+                  need_dgrad=True, stats=False, bias_img=None, gn_ab=None):
         """out = conv_ksize(concat(srcs)) + bias [+ resid] [+ conv1x1_skip(concat(skip_srcs)) + bias_skip]
-        stats: `out` feeds a GroupNorm - let the epilogue accumulate its per-(image, channel) sums (out.stats)."""
+        stats: `out` feeds a GroupNorm - let the epilogue accumulate its per-(image, channel) sums (out.stats).
+        gn_ab: `srcs` are the RAW inputs of a GroupNorm(+FiLM)+SiLU whose constants are in gn_ab [B, C, 2]: the conv applies
+        it while loading (inference, see gn_on_load_ok)."""
         chans = [s.shape[3] for s in srcs]
         segs, K = ops.conv_segments(chans, ksize)
         all_srcs = list(srcs)
@@ -471,9 +475,15 @@ class Engine:
         if stats and FUSED_GN_STATS and out_mode == 0 and cw.cout % 64 == 0 and cw.cout == out.shape[3] and \
                 out.shape[1] * out.shape[2] >= 32:
             st = out.stats = pl.alloc_stats(out.shape[0], cw.cout)
+        gn = None
+        if gn_ab is not None:
+            offs, o = [], 0
+            for c in chans:
+                offs.append(o); o += c
+            gn = (gn_ab, offs + [-1] * (len(all_srcs) - len(srcs)))
         d = ops.make_igemm_desc([s.t for s in all_srcs], segs, cw.fwd, out if out_mode == 1 else out.t, cw.cout,
                                 in_stride=stride, bias=cw.bias, bias2=bias2, resid=resid.t if resid is not None else None,
-                                out_mode=out_mode, stats=st, bias_img=bias_img)
+                                out_mode=out_mode, stats=st, bias_img=bias_img, gn=gn)
         pl.add_fwd(lambda: ops.igemm(d))
         return chans
 
@@ -563,6 +573,27 @@ class Engine:
             pl.add_fwd(lambda: ops.gn_fwd(x0.t, gn.weight, gn.bias, x1=x1t, film=film, film_off=film_off, silu=silu,
                                           out=out.t, mean=st[0], rstd=st[1]))
 
+    def gn_on_load_ok(self, pl, cw, x0, x1):
+        """inference only: can the 3x3 conv `cw` over [SiLU](FiLM(GroupNorm(concat(x0, x1)))) apply the norm while it loads?
+        (the transposed halo kernel: cout % 128 == 0, image tiles into 8 x 32 boxes; statistics from the producers)"""
+        if pl.train or not GN_ON_LOAD:
+            return False
+        B, H, W = x0.shape[:3]
+        if x0.stats is None or (x1 is not None and x1.stats is None):
+            return False
+        chans_ok = x0.shape[3] % 64 == 0 and (x1 is None or x1.shape[3] % 64 == 0)
+        return chans_ok and cw.cout % 128 == 0 and H % 32 == 0 and W % 8 == 0
+
+    def plan_gn_constants(self, pl, x0, x1, gn, st, film=None, film_off=0):
+        """the {a, b} table of [SiLU](FiLM(GroupNorm32(concat(x0, x1)))) for a conv that applies it on load"""
+        Ct = x0.shape[3] + (x1.shape[3] if x1 is not None else 0)
+        ab = pl.alloc((x0.shape[0], Ct, 2), th.float32)
+        x1t = x1.t if x1 is not None else None
+        s1 = x1.stats if x1 is not None else None
+        pl.add_fwd(lambda: ops.gn_apply_fwd(x0.t, x0.stats, gn.weight, gn.bias, x1=x1t, stats1=s1, film=film, film_off=film_off,
+                                            silu=True, mean=st[0], rstd=st[1], ab=ab, constants_only=True))
+        return ab
+
     def plan_gn_bwd(self, a, x0, x1, gn, st, dx0, dx1=None, accmask=0, film=None, film_off=0, silu=True, dfilm=None, dadd=None):
         """backward of a = [SiLU](FiLM(GroupNorm32(concat(x0, x1)))): one streaming pass when the conv that produced d(a) left
         du and the statistics behind (a.gnb, see plan_conv_bwd), else the resident reduce-and-apply kernel."""
@@ -586,29 +617,43 @@ class Engine:
         has_skip = not isinstance(rb.skip_connection, nn.Identity)
         sk = self.convs[id(rb.skip_connection)] if has_skip else None
         foff = self.film_off[id(rb)]
-        a1, h1, a2, out = T(pl, (B, H, W, cin)), T(pl, (B, H, W, cout)), T(pl, (B, H, W, cout)), T(pl, (B, H, W, cout))
+        h1, out = T(pl, (B, H, W, cout)), T(pl, (B, H, W, cout))
+        a1 = a2 = None                  # the activated tensors exist only where a norm is not applied on load
         st1 = (pl.alloc((B, 32), th.float32), pl.alloc((B, 32), th.float32))
         st2 = (pl.alloc((B, 32), th.float32), pl.alloc((B, 32), th.float32))
         x1t = x1.t if x1 is not None else None
         ssn = rb.use_scale_shift_norm
-        self.plan_gn_fwd(pl, x0, x1, gn1, a1, st1)
-        if ssn:      # h = GN(conv1(.)) * (1 + scale) + shift  (ref unet.py:190-194)
-            self.plan_conv(pl, cw1, [a1], h1, 3, stats=True)
-            self.plan_gn_fwd(pl, h1, None, gn2, a2, st2, film=film, film_off=foff)
-        else:        # h = GN(conv1(.) + emb_out[..., None, None])  (ref unet.py:195-197): the addend rides in conv1's epilogue
-            self.plan_conv(pl, cw1, [a1], h1, 3, stats=True, bias_img=film[:, foff:foff + cout])
-            self.plan_gn_fwd(pl, h1, None, gn2, a2, st2)
+        # inference at the 64x64 / 32x32 levels: the norms are applied by the consuming conv while it loads its operand -
+        # no activated tensor, no extra pass over HBM (ops.make_igemm_desc(gn=...)); elsewhere one streaming pass each
+        srcs_x = [x0] + ([x1] if x1 is not None else [])
+        bimg = None if ssn else film[:, foff:foff + cout]      # additive conditioning rides in conv1's epilogue (unet.py:195-197)
+        if self.gn_on_load_ok(pl, cw1, x0, x1):
+            ab1 = self.plan_gn_constants(pl, x0, x1, gn1, st1)
+            self.plan_conv(pl, cw1, srcs_x, h1, 3, stats=True, bias_img=bimg, gn_ab=ab1)
+        else:
+            a1 = T(pl, (B, H, W, cin))
+            self.plan_gn_fwd(pl, x0, x1, gn1, a1, st1)
+            self.plan_conv(pl, cw1, [a1], h1, 3, stats=True, bias_img=bimg)
+        fuse2 = self.gn_on_load_ok(pl, cw2, h1, None)
+        if fuse2:    # h = GN(conv1(.)) * (1 + scale) + shift  (ref unet.py:190-194), or plain GN after the additive form
+            ab2 = self.plan_gn_constants(pl, h1, None, gn2, st2, film=film if ssn else None, film_off=foff if ssn else 0)
+        else:
+            a2 = T(pl, (B, H, W, cout))
+            if ssn:
+                self.plan_gn_fwd(pl, h1, None, gn2, a2, st2, film=film, film_off=foff)
+            else:
+                self.plan_gn_fwd(pl, h1, None, gn2, a2, st2)
         drop_off = None
         if rb.dropout and pl.train:     # nn.Dropout between SiLU and conv2 (ref unet.py:157): in place on a2, masks regenerated in bwd
             drop_off = pl.drop_groups
             pl.drop_groups += a2.t.numel() // 8
             a2.gnb = None               # d(a2) has to be masked before the norm's backward sees it
             pl.add_fwd(lambda: ops.dropout_(a2.t, pl.drop_state, drop_off, pl.drop_p))
-        srcs_x = [x0] + ([x1] if x1 is not None else [])
+        c2_src, c2_gn = ([h1], ab2) if fuse2 else ([a2], None)
         if has_skip:
-            self.plan_conv(pl, cw2, [a2], out, 3, skip=sk, skip_srcs=srcs_x, stats=True)
+            self.plan_conv(pl, cw2, c2_src, out, 3, skip=sk, skip_srcs=srcs_x, stats=True, gn_ab=c2_gn)
         else:
-            self.plan_conv(pl, cw2, [a2], out, 3, resid=x0, stats=True)
+            self.plan_conv(pl, cw2, c2_src, out, 3, resid=x0, stats=True, gn_ab=c2_gn)
         if pl.train:
             def build_bwd():
                 fns = []

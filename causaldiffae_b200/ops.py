@@ -230,9 +230,10 @@ def gn_fwd(x0, gamma, beta, x1=None, film=None, film_off=0, silu=True, out=None,
 
 
 def gn_apply_fwd(x0, stats0, gamma, beta, x1=None, stats1=None, film=None, film_off=0, silu=True, out=None, mean=None,
-                 rstd=None, ab=None):
+                 rstd=None, ab=None, constants_only=False):
     """gn_fwd as ONE streaming pass: the per-(image, channel) sums stats0 [B,C0,2] (stats1 [B,C1,2]) were accumulated by
-    the convolutions that produced x0 (x1) (make_igemm_desc(stats=...))."""
+    the convolutions that produced x0 (x1) (make_igemm_desc(stats=...)).  constants_only: nothing is streamed - only the
+    {a, b} table `ab` [B, C, 2] is written, for a conv that applies the norm while loading (make_igemm_desc(gn=...))."""
     _bf16c(x0); _f32c(stats0)
     B = x0.shape[0]
     C0 = x0.shape[-1]
@@ -243,7 +244,11 @@ def gn_apply_fwd(x0, stats0, gamma, beta, x1=None, stats1=None, film=None, film_
         _bf16c(x1); _f32c(stats1); C1 = x1.shape[-1]
         assert tuple(stats1.shape) == (B, C1, 2)
     Ct = C0 + C1
-    out = torch.empty(*x0.shape[:-1], Ct, device=x0.device, dtype=bf16) if out is None else out
+    if constants_only:
+        assert ab is not None and tuple(ab.shape) == (B, Ct, 2)
+        out = None
+    else:
+        out = torch.empty(*x0.shape[:-1], Ct, device=x0.device, dtype=bf16) if out is None else out
     mean = torch.empty(B, 32, device=x0.device, dtype=torch.float32) if mean is None else mean
     rstd = torch.empty(B, 32, device=x0.device, dtype=torch.float32) if rstd is None else rstd
     check(_lib.lib().cdae_gn_apply_fwd(ptr(x0), C0, ptr(stats0), ptr(x1), C1, ptr(stats1), B, HW, ptr(gamma), ptr(beta),
@@ -317,7 +322,7 @@ def conv_segments(chans, ksize=3, transposed=False, wk0=0, src0=0):
 
 
 def make_igemm_desc(srcs, segs, wgt, out, cout, in_stride=1, bias=None, resid=None, out_mode=0, sps=1, ooh=0, oow=0,
-                    bn=0, out_hw=None, bias2=None, stats=None, gnb=None, bias_img=None):
+                    bn=0, out_hw=None, bias2=None, stats=None, gnb=None, bias_img=None, gn=None):
     """Fill a cdae_igemm_desc.  srcs: bf16 [N,H,W,C]; wgt: bf16 [rows, K]; out: bf16 NHWC or fp32 NCHW (out_mode 1).
     stats: optional fp32 [N, cout, 2] that the epilogue ACCUMULATES per-(image, channel) sum / sum of squares of the
     stored output into (zero it first) - the GroupNorm statistics of the consumer, see gn_apply_fwd."""
@@ -369,7 +374,18 @@ def make_igemm_desc(srcs, segs, wgt, out, cout, in_stride=1, bias=None, resid=No
     if bias_img is not None:       # fp32 [N, >= cout] view (row pitch = stride(0)): + bias_img[n, co] in the epilogue
         assert bias_img.dtype == torch.float32 and bias_img.stride(1) == 1 and bias_img.shape[0] == N
         d.bias_img, d.bias_img_ld = bias_img.data_ptr(), bias_img.stride(0)
-    d._keep = (srcs, wgt, out, bias, bias2, resid, stats, gnb, bias_img)   # keep tensors alive as long as the descriptor
+    for i in range(4):
+        d.gn_off[i] = -1
+    if gn is not None:
+        # GroupNorm(+FiLM)+SiLU applied to sources on load: gn = (ab [N, C, 2] from gn_apply_fwd(constants_only=True),
+        # [table column of source i's channel 0, or -1 for a source that is taken raw])
+        gab, offs = gn
+        _f32c(gab)
+        assert gab.dim() == 3 and gab.shape[0] == N and gab.shape[2] == 2 and len(offs) == len(srcs)
+        d.gn_ab, d.gn_c = gab.data_ptr(), gab.shape[1]
+        for i, o in enumerate(offs):
+            d.gn_off[i] = int(o)
+    d._keep = (srcs, wgt, out, bias, bias2, resid, stats, gnb, bias_img, gn)   # keep tensors alive as long as the descriptor
     return d
 
 

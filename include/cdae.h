@@ -165,6 +165,14 @@ typedef struct {
   /* per-(image, channel) additive term of the epilogue: out += bias_img[n * bias_img_ld + co] - the ResBlock's additive
    * timestep conditioning `h + emb_out[..., None, None]` (unet.py:196, use_scale_shift_norm=False).  NHWC output only. */
   const float* bias_img; int32_t bias_img_ld;
+  /* GroupNorm(+FiLM)+SiLU applied to a SOURCE while it is loaded (inference: nn.py:430-437 + unet.py:185-198 folded into the
+   * operand path of the conv that consumes the activation - no activated tensor is materialised).  gn_ab: fp32
+   * [N][gn_c][2] = the per-(image, channel) constants {a, b} of cdae_gn_apply_fwd (u/2 = a x + b; y = u/2 + u/2 tanh(u/2)).
+   * gn_off[i] >= 0: source i is GroupNorm input, its channel c uses table column gn_off[i] + c; -1: source i is taken as
+   * it is (the 1x1-skip sources).  Zero padding stays zero (the reference pads the ACTIVATED tensor).  3x3 stride-1 layers
+   * with cout % 128 == 0 on images that tile into 8 x 32 boxes (the transposed halo kernel); bit-identical to running
+   * cdae_gn_apply_fwd first. */
+  const float* gn_ab; int32_t gn_c; int32_t gn_off[4];
 } cdae_igemm_desc;
 int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s);
 

@@ -296,6 +296,54 @@ def test_igemm_dgrad_matches_autograd():
     assert relerr(nchw(dx), x.grad) < 5e-3
 
 
+@pytest.mark.parametrize("C0,C1,cout,H,film,skip", [(128, 0, 128, 64, False, 0), (128, 128, 128, 32, True, 0),
+                                                     (256, 0, 256, 32, True, 128), (384, 256, 256, 32, False, 0)])
+def test_conv_with_groupnorm_on_load_equals_the_two_pass_form(C0, C1, cout, H, film, skip):
+    """inference: GroupNorm(+FiLM)+SiLU folded into the operand path of the 3x3 conv that consumes it
+    (make_igemm_desc(gn=...), the transposed halo kernel's transform warps) == gn_apply_fwd followed by the conv, bit for
+    bit; `skip`: a second, RAW source feeding a fused 1x1 skip conv (ResBlock conv2 with a channel change)"""
+    from causaldiffae_b200 import ops
+    g = torch.Generator().manual_seed(C0 + C1 + H)
+    N, Ct = 3, C0 + C1
+    x = (torch.randn(N, H, H, Ct, generator=g) * 1.3 + 0.2).to(dev()).to(bf16)
+    x0 = x[..., :C0].contiguous()
+    x1 = x[..., C0:].contiguous() if C1 else None
+    xf = x.float()
+    st = torch.stack([xf.sum(dim=(1, 2)), (xf * xf).sum(dim=(1, 2))], dim=-1)          # what the producing conv's epilogue leaves
+    st0, st1 = st[:, :C0].contiguous(), (st[:, C0:].contiguous() if C1 else None)
+    gamma = (1 + 0.2 * torch.randn(Ct, generator=g)).to(dev())
+    beta = (0.2 * torch.randn(Ct, generator=g)).to(dev())
+    film_t = (0.3 * torch.randn(N, 2 * Ct + 32, generator=g)).to(dev()) if film else None
+    foff = 16
+    xs = torch.randn(N, H, H, skip, generator=g).to(dev()).to(bf16) if skip else None
+    segs, K = ops.conv_segments([C0, C1] if C1 else [C0], 3)
+    Kt = K
+    if skip:
+        ssegs, Kt = ops.conv_segments([skip], 1, wk0=K, src0=2 if C1 else 1)
+        segs = segs + ssegs
+    w = (torch.randn(cout, Kt, generator=g) * Kt ** -0.5).to(dev()).to(bf16)
+    bias = (0.1 * torch.randn(cout, generator=g)).to(dev())
+    # two passes
+    a, _, _ = ops.gn_apply_fwd(x0, st0, gamma, beta, x1=x1, stats1=st1, film=film_t, film_off=foff, silu=True)
+    a0, a1 = a[..., :C0].contiguous(), (a[..., C0:].contiguous() if C1 else None)
+    srcs_a = [a0] + ([a1] if C1 else []) + ([xs] if skip else [])
+    stats_a = torch.zeros(N, cout, 2, device=dev())
+    out_a = torch.empty(N, H, H, cout, device=dev(), dtype=bf16)
+    ops.igemm(ops.make_igemm_desc(srcs_a, segs, w, out_a, cout, bias=bias, stats=stats_a))
+    # fused
+    ab = torch.full((N, Ct, 2), float("nan"), device=dev())
+    ops.gn_apply_fwd(x0, st0, gamma, beta, x1=x1, stats1=st1, film=film_t, film_off=foff, silu=True, ab=ab, constants_only=True)
+    srcs_x = [x0] + ([x1] if C1 else []) + ([xs] if skip else [])
+    offs = [0] + ([C0] if C1 else []) + ([-1] if skip else [])
+    stats_f = torch.zeros(N, cout, 2, device=dev())
+    out_f = torch.full((N, H, H, cout), float("nan"), device=dev(), dtype=bf16)
+    ops.igemm(ops.make_igemm_desc(srcs_x, segs, w, out_f, cout, bias=bias, stats=stats_f, gn=(ab, offs)))
+    assert torch.isfinite(out_f.float()).all()
+    assert torch.equal(out_f, out_a)
+    assert torch.equal(stats_f, stats_a) or relerr(stats_f, stats_a) < 1e-6        # fp32 atomics: order may differ
+    assert torch.equal(x0, x[..., :C0].contiguous())                                # the sources are not modified
+
+
 @pytest.mark.parametrize("N,H,cin,cout,acc", [(2, 32, 128, 128, False), (3, 16, 256, 192, True), (2, 8, 384, 384, False)])
 def test_stride2_dgrad_parity_classes_match_autograd(N, H, cin, cout, acc):
     """data gradient of a 3x3 stride-2 pad-1 conv (Downsample, ref unet.py:97-105) as four launches over the low-resolution

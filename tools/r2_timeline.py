@@ -11,6 +11,7 @@ from causaldiffae_b200.train_util import TrainLoop
 import causaldiffae_b200.nn as cnn
 
 out = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/r2_timeline.csv"
+what = sys.argv[2] if len(sys.argv) > 2 else "train"        # "ddim": two DDIM steps at 512 interventions instead
 torch.cuda.set_device(0)
 dev = torch.device("cuda", 0)
 dist_util.setup_dist()
@@ -20,6 +21,40 @@ torch.manual_seed(0)
 model, diff = su.create_model_and_diffusion(**{**su.model_and_diffusion_defaults(), **bench.FLAGS}, A=bench.PENDULUM)
 bench._dezero(model)
 model.to(dev)
+if what == "ddim":
+    from causaldiffae_b200.sampling import counterfactual
+    from torch.profiler import profile, ProfilerActivity
+    import json, types
+    _, d5 = su.create_model_and_diffusion(**{**su.model_and_diffusion_defaults(), **bench.FLAGS, "timestep_respacing": "ddim5"},
+                                          A=bench.PENDULUM)
+    model.eval()
+    xs = torch.rand(512, 3, 64, 64, device=dev)
+    counterfactual(model, d5, xs, do_var=0, do_value=0.2)
+    counterfactual(model, d5, xs, do_var=0, do_value=0.2)
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        counterfactual(model, d5, xs, do_var=0, do_value=0.1)
+        torch.cuda.synchronize()
+    trace = out.replace(".csv", "_trace.json")
+    prof.export_chrome_trace(trace)
+    ev = sorted(((float(t["ts"]), float(t["dur"]), t["name"]) for t in json.load(open(trace))["traceEvents"]
+                 if t.get("cat") == "kernel" and t.get("ph") == "X"))
+    os.remove(trace)
+    t0 = ev[0][0]
+    wall = max(s + d for s, d, _ in ev) - t0
+    busy = sum(d for _, d, _ in ev)
+    print(f"encode + 5 DDIM steps at 512 interventions: wall {wall:.0f} us, {len(ev)} kernels, sum of kernel durations {busy:.0f} us")
+    agg = collections.defaultdict(lambda: [0.0, 0])
+    for s_, d, n in ev:
+        k = n.split("(")[0].replace("void ", "").replace("cdae::", "")[:44]
+        agg[k][0] += d; agg[k][1] += 1
+    for k, (d, c) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:24]:
+        print(f"{d:9.1f} us {c:4d}  {100 * d / busy:5.1f}%  {k}")
+    with open(out, "w") as f:
+        f.write("start_us,dur_us,name\n")
+        for s_, d, n in ev:
+            f.write(f"{s_ - t0:.1f},{d:.1f},\"{n[:90]}\"\n")
+    sys.exit(0)
 B = 64
 loop = TrainLoop(model=model, diffusion=diff, data=None, batch_size=B, microbatch=-1, lr=1e-4, ema_rate="0.9999",
                  log_interval=10 ** 9, save_interval=10 ** 9, resume_checkpoint="", rep_cond=True, n_vars=4,
