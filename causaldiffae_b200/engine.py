@@ -263,13 +263,27 @@ class Engine:
         for rb in rbs:
             order.append(rb.emb_layers[1].bias)
         seen = {id(p) for p in order}
-        for p in m.parameters():
-            if id(p) not in seen:
-                order.append(p); seen.add(id(p))
+        # the parameters of the representation path (embedding trunk, conv encoder, DAG layer) go LAST: their gradients are the
+        # last ones a backward pass produces, so [0, early_end) - 99 % of the arena - is final as soon as the FiLM projection's
+        # backward has run and its all-reduce can start beside the rest of the backward (TrainLoop._forward_backward_fused)
+        late = set()
+        for name in ("time_embed", "label_emb", "c_emb", "rep_emb", "up_emb", "causal_mask"):
+            mod = getattr(m, name, None)
+            if isinstance(mod, nn.Module):
+                late |= {id(p) for p in mod.parameters()}
+        for want_late in (False, True):
+            for p in m.parameters():
+                if id(p) not in seen and (id(p) in late) == want_late:
+                    order.append(p); seen.add(id(p))
         offs, off = {}, 0
+        self.early_end = None
         for p in order:
+            if id(p) in late and self.early_end is None:
+                self.early_end = off
             offs[id(p)] = off
             off += _round_up(p.numel(), 4)
+        if self.early_end is None:
+            self.early_end = off
         self.n_params = off
         self.arena = th.zeros(off, device=self.device, dtype=th.float32)
         self.grad_arena = th.zeros(off, device=self.device, dtype=th.float32)

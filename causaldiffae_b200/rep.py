@@ -93,9 +93,14 @@ class TrunkRunner:
         eng.film_fwd(st.emb, film_out, st.a_bf)
         return film_out
 
-    def backward(self, st, y, c, z, dfilm, dz_out=None):
+    def backward(self, st, y, c, z, dfilm, dz_out=None, part="all"):
+        """part: "film" = only the FiLM projection's backward (after it every gradient in [0, engine.early_end) is final),
+        "rest" = what follows it, "all" = both"""
         m, eng = self.m, self.m.engine
-        eng.film_bwd(st.emb, st.a_bf, dfilm, st.dfilm_bf, st.demb)
+        if part != "rest":
+            eng.film_bwd(st.emb, st.a_bf, dfilm, st.dfilm_bf, st.demb)
+        if part == "film":
+            return
         if z is not None:
             ops.linear_bwd(z, m.up_emb.weight, st.demb, _g(m.up_emb.weight), _g(m.up_emb.bias), dx=dz_out)
         if m.c_dim is not None:

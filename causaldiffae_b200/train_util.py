@@ -30,6 +30,10 @@ def adam_hyper(lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, ema_rate=
     return [lr, beta1, beta2, eps, weight_decay, ema_rate, grad_scale]
 
 
+# multi-GPU: start the all-reduce of the early gradient range beside the representation path's backward
+OVERLAP_ALLREDUCE = os.environ.get("CDAE_OVERLAP_ALLREDUCE", "1") != "0"
+
+
 class _FlatAdamW:
     """The optimizer object behind `TrainLoop.opt`: torch.optim.AdamW's surface (param_groups / state_dict / step)
     over the flat arena, executed by the fused kernel.  Nothing here synchronises with the host: the step counter, the
@@ -150,12 +154,20 @@ class FusedStep:
         self.sqrt_ac = d._f32_table("sqrt_alphas_cumprod", dev)
         self.sqrt_1mac = d._f32_table("sqrt_one_minus_alphas_cumprod", dev)
         freqs_for(m.model_channels, dev)
-        self.graph, self.runs = None, 0
+        self.graph, self.graph_a, self.graph_b, self.runs = None, None, None, 0
         self.device_rng = False
 
     # ------------------------------------------------------------------ the launch sequence (eager or under capture)
-    def _launch(self):
-        from . import nn as cnn
+    def _launch(self, part="all"):
+        """part "a": everything up to and including the FiLM projection's backward - from there on every gradient in
+        [0, engine.early_end) is final; part "b": the rest of the representation path's backward; "all": both.  The split
+        lets a multi-GPU run start the all-reduce of the early range (99 % of the arena) beside part b."""
+        if part in ("all", "a"):
+            self._launch_a()
+        if part in ("all", "b"):
+            self._launch_b()
+
+    def _launch_a(self):
         m, eng, pl, B = self.m, self.eng, self.pl, self.B
         if self.device_rng:
             ops.randn_(self.noise, self.rng)
@@ -196,8 +208,17 @@ class FusedStep:
         ops.zero_(pl.dfilm)
         pl._run_bwd_eager()
         eng.trunk.backward(self.trunk_st, self.y, self.c if m.c_dim is not None else None, z, pl.dfilm,
-                           self.dz if self.rep else None)
+                           self.dz if self.rep else None, part="film")
+
+    def _launch_b(self):
+        m, eng, pl = self.m, self.eng, self.pl
+        z = self.z if self.rep else None
+        eng.trunk.backward(self.trunk_st, self.y, self.c if m.c_dim is not None else None, z, pl.dfilm,
+                           self.dz if self.rep else None, part="rest")
         if self.rep:
+            enc = m.rep_emb.runner
+            mu, var = self.enc_st.mu, self.enc_st.var
+            zp = self.zp if m.causal_modeling else mu
             ops.latent_bwd(mu, var, zp, self.xi, self.keep, self.c, self.dz, self.dkld, None, None, None, self.dzp, self.dmu,
                            self.dvar, m.n_vars, m.causal_modeling, 0.001)
             if m.causal_modeling:
@@ -211,21 +232,37 @@ class FusedStep:
                           c_mode=1, splits=1)
             enc.backward(self.enc_st, self.x, dmu, self.dvar)
 
-    def run(self):
+    def run(self, after_early=None):
+        """after_early(event): called once both parts are enqueued; `event` marks the end of part "a" on the current stream
+        (the early gradient range is final there).  Without it the step is one graph."""
         from .engine import USE_GRAPHS, _capture
         self.pl.generation += 1            # a pending autograd backward on this plan must fail loudly, not read these buffers
         self.pl.pending = False
         if self.pl.drop_groups:
             self.pl.set_dropout(float(self.m.dropout))
-        if USE_GRAPHS and self.runs >= 2:
-            if self.graph is None:
+        graphs = USE_GRAPHS and self.runs >= 2
+        if after_early is None:
+            if graphs:
+                if self.graph is None:
+                    from . import _lib
+                    k0 = _lib.kernel_count()
+                    self.graph = _capture(self._launch)
+                    self.graph_kernels = _lib.kernel_count() - k0      # kernels one replay of this graph launches (counted)
+                self.graph.replay()
+            else:
+                self._launch()
+        else:
+            if graphs and self.graph_a is None:
                 from . import _lib
                 k0 = _lib.kernel_count()
-                self.graph = _capture(self._launch)
-                self.graph_kernels = _lib.kernel_count() - k0      # kernels one replay of this graph launches (counted)
-            self.graph.replay()
-        else:
-            self._launch()
+                self.graph_a = _capture(self._launch_a)
+                self.graph_b = _capture(self._launch_b)
+                self.graph_kernels = _lib.kernel_count() - k0
+            ev = th.cuda.Event()
+            self.graph_a.replay() if graphs else self._launch_a()
+            ev.record()
+            self.graph_b.replay() if graphs else self._launch_b()
+            after_early(ev)
         self.runs += 1
         self.eng.dirty = False             # the graph packed the current weights; the optimizer marks them dirty again
 
@@ -395,7 +432,7 @@ class TrainLoop:
                 cc = cond["c"][i:i + self.microbatch]
                 if fs.c is None:
                     fs.c = th.zeros(B, cc.shape[1], device=dev)
-                    fs.graph = None
+                    fs.graph = fs.graph_a = fs.graph_b = None
                 fs.c.copy_(cc, non_blocking=True)
             if fs.y is not None:
                 fs.y.copy_(cond["y"][i:i + self.microbatch], non_blocking=True)
@@ -412,7 +449,7 @@ class TrainLoop:
                 fs._klw_host = klw
             device_rng = cnn.RNG_MODE == "device"
             if device_rng != fs.device_rng:
-                fs.device_rng, fs.graph = device_rng, None
+                fs.device_rng, fs.graph, fs.graph_a, fs.graph_b = device_rng, None, None, None
             if not device_rng:      # the reference's draws, in its order: noise (device generator), xi then mask (CPU generator)
                 if self.noise_override is not None:            # parity runs feed the oracle's noise (training_losses(noise=...))
                     fs.noise.copy_(self.noise_override[i:i + self.microbatch], non_blocking=True)
@@ -422,7 +459,9 @@ class TrainLoop:
                     fs.xi.copy_(th.randn(fs.xi.shape))
                     if fs.keep is not None:
                         fs.keep.copy_(th.bernoulli(th.zeros(B) + (1 - self.model.drop_prob)))
-            fs.run()
+            overlap = (OVERLAP_ALLREDUCE and self.use_ddp and self.microbatch >= batch.shape[0])
+            self._early_work = None
+            fs.run(after_early=self._early_exchange if overlap else None)
             if isinstance(self.schedule_sampler, LossAwareSampler):
                 self.schedule_sampler.update_with_local_losses(fs.t, fs.loss.detach().clone())
             self.last_loss = fs.total[0]
@@ -449,16 +488,47 @@ class TrainLoop:
             out["grad_norm"] = v[20] / v[21]
         return out
 
+    def _wire_buffer(self):
+        if getattr(self, "_wire", None) is None:
+            self._wire = th.empty(self.engine.grad_arena.shape, device=self.engine.device, dtype=th.bfloat16)
+        return self._wire
+
+    def _early_exchange(self, ev):
+        """The gradients in [0, engine.early_end) - everything but the representation path, 99 % of the arena - are final at
+        `ev` (end of FusedStep part "a"): their all-reduce starts on a communication stream beside part "b" (the reference
+        overlaps bucket by bucket through DDP hooks, train_util.py:107-126)."""
+        e = self.engine
+        n0 = e.early_end
+        if getattr(self, "_comm", None) is None:
+            self._comm = th.cuda.Stream()
+        self._comm.wait_event(ev)
+        with th.cuda.stream(self._comm):
+            if self.grad_wire_dtype == th.bfloat16:
+                buf = self._wire_buffer()[:n0]
+                ops.cast_bf16(e.grad_arena[:n0], out=buf)
+            else:
+                buf = e.grad_arena[:n0]
+            self._early_work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, async_op=True)
+
     def _exchange_gradients(self):
         """ref train_util.py:107-126 (DDP mean).  bf16 on the wire (default): one cast pass over the arena, ONE NCCL sum
         all-reduce of the 2-byte copy (187 MB instead of 374 MB at cfg2), and the fused optimizer reads that copy
-        directly; fp32 (CDAE_GRAD_WIRE=fp32): the all-reduce runs in place on the arena."""
+        directly; fp32 (CDAE_GRAD_WIRE=fp32): the all-reduce runs in place on the arena.  When the early range is already
+        on its way (_early_exchange) only the tail is exchanged here, then the streams are joined."""
+        e = self.engine
+        lo = e.early_end if getattr(self, "_early_work", None) is not None else 0
         if self.grad_wire_dtype == th.bfloat16:
-            if getattr(self, "_wire", None) is None:
-                self._wire = th.empty(self.engine.grad_arena.shape, device=self.engine.device, dtype=th.bfloat16)
-            ops.cast_bf16(self.engine.grad_arena, out=self._wire)
-            return dp_all_reduce_(self._wire), self._wire
-        return dp_all_reduce_(self.engine.grad_arena), None
+            wire = self._wire_buffer()
+            if lo < e.n_params:
+                ops.cast_bf16(e.grad_arena[lo:], out=wire[lo:])
+            scale, red = dp_all_reduce_(wire[lo:]), wire
+        else:
+            scale, red = dp_all_reduce_(e.grad_arena[lo:]), None
+        if lo:
+            self._early_work.wait()
+            th.cuda.current_stream().wait_stream(self._comm)
+            self._early_work = None
+        return scale, red
 
     def optimize_fp16(self):
         """ref train_util.py:276-290.  The guard is kept, on the device: when any gradient is NaN/Inf the fused kernel

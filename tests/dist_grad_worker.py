@@ -67,10 +67,15 @@ def main():
             mean_ref[n] += osd[n].grad / world
     # this rank's step through the public TrainLoop path (samples t with np.random, draws noise with torch)
     x, c, noise = shard(rank)
-    np.random.seed(50 + rank)
-    torch.manual_seed(900 + rank)
     loop.noise_override = noise.to(dev)            # the shard's noise; everything else is TrainLoop's own (fused) path
-    loop.forward_backward(x, {"c": c})
+    # four times on unchanged weights and identical draws: eager, eager, graph capture + replay, replay - the last one goes
+    # through the two-graph form whose early gradient range is all-reduced beside the rest of the backward
+    for _ in range(4):
+        np.random.seed(50 + rank)
+        torch.manual_seed(900 + rank)
+        loop.forward_backward(x, {"c": c})
+    fs = loop._fused[B]
+    assert fs.runs == 4 and (fs.graph_a is not None) == (os.environ.get("CDAE_OVERLAP_ALLREDUCE", "1") != "0")
     named = dict(model.named_parameters())
     if getattr(loop, "_reduced_grads", None) is not None:
         flat = loop._reduced_grads.float() * loop._grad_scale
@@ -87,7 +92,7 @@ def main():
     gathered = [torch.zeros_like(chk) for _ in range(world)]
     dist.all_gather(gathered, chk)
     same = all(bool(torch.equal(gathered[0], g)) for g in gathered)
-    res = dict(rank=rank, world=world, whole_rel_l2=tot, worst=worst, worst_err=errs[worst], identical_across_ranks=same,
+    res = dict(rank=rank, world=world, overlapped=fs.graph_a is not None, whole_rel_l2=tot, worst=worst, worst_err=errs[worst], identical_across_ranks=same,
                backend=dist.get_backend(), wire="bf16" if bf16_wire else "fp32")
     print("DISTGRAD " + json.dumps(res), flush=True)
     ok = tot < 3e-2 and errs[worst] < 8e-2 and same

@@ -109,3 +109,39 @@ def test_fused_step_vs_autograd_path_and_oracle(name):
         worst = max(worst, relerr(f["grads"][n], sd[n].grad))
     print(name, "fused step vs oracle: worst per-tensor gradient rel L2", worst)
     assert worst < 4e-2, worst
+
+
+def test_two_graph_step_with_early_gradient_exchange_equals_the_single_graph():
+    """multi-GPU form of the fused step on ONE rank (use_ddp forced: the all-reduces are no-ops): part "a" | early-range
+    exchange on the communication stream beside part "b" | tail exchange | optimizer - against the single-graph step"""
+    from oracle import model as om
+    from causaldiffae_b200 import script_util as su
+    flags, A = CFGS["cfg2s-masking"]
+    full = {**su.model_and_diffusion_defaults(), **COMMON, **flags}
+    cfg = om.config_from_flags(**full, A=A)
+    sd = om.seeded_state_dict(cfg, seed=0)
+    B, S, C = 8, flags["image_size"], flags["in_channels"]
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(B, C, S, S, generator=g)
+    cond = {"c": torch.rand(B, flags["n_vars"], generator=g)}
+    res = {}
+    for ddp in (False, True):
+        for wire in ((torch.bfloat16, torch.float32) if ddp else (torch.float32,)):
+            loop, model, diff = make_loop(flags, A, sd, True)
+            loop.use_ddp, loop.grad_wire_dtype = ddp, wire
+            diff.kl_weight = 0.3
+            losses = []
+            for step in range(6):          # eager, eager, capture + replay, replay ...
+                np.random.seed(10 + step); torch.manual_seed(20 + step)
+                loop.run_step(x.cuda(), {k: v.cuda() for k, v in cond.items()})
+                losses.append(float(loop.last_loss))
+            fs = loop._fused[B]
+            assert (fs.graph_a is not None) == ddp and (fs.graph is not None) == (not ddp)
+            assert 0 < loop.engine.early_end < loop.engine.n_params
+            res[(ddp, wire)] = (losses, loop.engine.arena.clone(), loop.ema_params[0][0].clone())
+    base = res[(False, torch.float32)]
+    for key in ((True, torch.float32), (True, torch.bfloat16)):
+        got = res[key]
+        np.testing.assert_allclose(got[0], base[0], rtol=5e-3)
+        tol = 2e-3 if key[1] == torch.bfloat16 else 5e-4      # bf16 wire: the gradient is rounded once more before AdamW
+        assert relerr(got[1], base[1]) < tol and relerr(got[2], base[2]) < tol, (key, relerr(got[1], base[1]))
