@@ -83,12 +83,26 @@ class _FlatAdamW:
         e.dirty = True
 
     def state_dict(self):
-        return dict(step=self.step_count, exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq,
-                    param_groups=self.param_groups)
+        """moments keyed by parameter name with the model's shapes (like the weights and the EMA): the file does not depend on
+        the order of the flat arena"""
+        e = self.engine
+        return dict(step=self.step_count, param_groups=self.param_groups,
+                    exp_avg={k: v.clone() for k, v in e.export_state(self.exp_avg).items()},
+                    exp_avg_sq={k: v.clone() for k, v in e.export_state(self.exp_avg_sq).items()})
 
     def load_state_dict(self, sd):
+        if th.is_tensor(sd["exp_avg"]):
+            raise ValueError("optimizer checkpoint stores flat moment arenas (an older layout of this package): the arena order "
+                             "has changed since, re-save it from the version that wrote it as per-parameter tensors")
         self.step_dev.fill_(int(sd["step"]))
-        self.exp_avg.copy_(sd["exp_avg"]); self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        with th.no_grad():
+            for key, flat in (("exp_avg", self.exp_avg), ("exp_avg_sq", self.exp_avg_sq)):
+                views = self.engine.export_state(flat)
+                missing = set(views) - set(sd[key])
+                if missing:
+                    raise KeyError(f"optimizer checkpoint lacks {key} of {sorted(missing)[:3]} ...")
+                for name, v in views.items():
+                    v.copy_(sd[key][name])
         self.param_groups = sd["param_groups"]
         self._hyper_host = None
 
