@@ -147,3 +147,33 @@ def test_optimize_fp16_skips_the_step_on_non_finite_gradients():
     loop.run_step(x, {"c": c})                                  # and training goes on
     assert loop.opt.step_count == 2 and not torch.equal(snap[0], loop.engine.arena)
     assert bool(torch.isfinite(loop.engine.arena).all())
+
+
+def test_optimizer_state_dict_is_keyed_by_parameter_and_rejects_flat_arenas():
+    """the moments are saved per parameter with the model's shapes (the file does not depend on the arena order, which puts
+    the representation path last); a flat-arena file of an older layout is refused instead of being mis-mapped"""
+    from causaldiffae_b200 import dist_util, logger
+    from causaldiffae_b200.train_util import TrainLoop
+    model, diff, cfg, sd = build()
+    dist_util.setup_dist()
+    logger.configure(dir="/tmp/cdae_optstate", format_strs=[])
+    loop = TrainLoop(model=model, diffusion=diff, data=None, batch_size=4, microbatch=-1, lr=1e-3, ema_rate="0.99",
+                     log_interval=10 ** 9, save_interval=10 ** 9, resume_checkpoint="", rep_cond=True, n_vars=4,
+                     causal_modeling=True, in_channels=3)
+    g = torch.Generator().manual_seed(3)
+    for step in range(3):
+        loop.run_step(torch.rand(4, 3, 32, 32, generator=g).cuda(), {"c": torch.rand(4, 4, generator=g).cuda()})
+    eng = loop.engine
+    assert 0 < eng.early_end < eng.n_params
+    late = [n for n, p in model.named_parameters() if eng.param_offsets[id(p)] >= eng.early_end]
+    assert late and all(n.split(".")[0] in ("time_embed", "rep_emb", "up_emb", "causal_mask") for n in late)
+    osd = loop.opt.state_dict()
+    names = dict(model.named_parameters())
+    assert set(osd["exp_avg"]) == set(names) and all(osd["exp_avg"][n].shape == names[n].shape for n in names)
+    m0, v0, step0 = loop.opt.exp_avg.clone(), loop.opt.exp_avg_sq.clone(), loop.opt.step_count
+    assert float(m0.abs().sum()) > 0
+    loop.opt.exp_avg.zero_(); loop.opt.exp_avg_sq.zero_(); loop.opt.step_dev.zero_()
+    loop.opt.load_state_dict(osd)
+    assert torch.equal(loop.opt.exp_avg, m0) and torch.equal(loop.opt.exp_avg_sq, v0) and loop.opt.step_count == step0
+    with pytest.raises(ValueError):
+        loop.opt.load_state_dict(dict(step=3, param_groups=osd["param_groups"], exp_avg=m0, exp_avg_sq=v0))

@@ -448,6 +448,36 @@ def test_igemm_channel_stats_rejects_unsupported():
         ops.igemm(d)
 
 
+def test_igemm_rejects_unsupported_groupnorm_on_load_and_output_placement():
+    """the new descriptor fields fail loudly where the kernels cannot honour them (no silent fallback)"""
+    from causaldiffae_b200 import ops
+    from causaldiffae_b200._lib import CdaeError
+    segs, _ = ops.conv_segments([64], 3)
+    w = torch.randn(128, 9 * 64, device=dev()).to(bf16)
+    # GroupNorm on load on a 16x16 image: does not tile into 8 x 32 boxes
+    x = torch.randn(2, 16, 16, 64, device=dev()).to(bf16)
+    ab = torch.zeros(2, 64, 2, device=dev())
+    d = ops.make_igemm_desc([x], segs, w, torch.empty(2, 16, 16, 128, device=dev(), dtype=bf16), 128, gn=(ab, [0]))
+    with pytest.raises(CdaeError):
+        ops.igemm(d)
+    # ... and a table that is too narrow for the source
+    x = torch.randn(2, 32, 32, 64, device=dev()).to(bf16)
+    d = ops.make_igemm_desc([x], segs, w, torch.empty(2, 32, 32, 128, device=dev(), dtype=bf16), 128,
+                            gn=(torch.zeros(2, 32, 2, device=dev()), [0]))
+    with pytest.raises(CdaeError):
+        ops.igemm(d)
+    # strided output placement together with channel statistics
+    dy = torch.randn(2, 16, 16, 64, device=dev()).to(bf16)
+    d = ops.make_igemm_desc([dy], segs, w, torch.empty(2, 32, 32, 128, device=dev(), dtype=bf16), 128,
+                            stats=torch.zeros(2, 128, 2, device=dev()), sps=2, ooh=1, oow=0)
+    with pytest.raises(CdaeError):
+        ops.igemm(d)
+    # an offset outside the 2 x 2 parity classes
+    d = ops.make_igemm_desc([dy], segs, w, torch.empty(2, 32, 32, 128, device=dev(), dtype=bf16), 128, sps=2, ooh=2, oow=0)
+    with pytest.raises(CdaeError):
+        ops.igemm(d)
+
+
 @pytest.mark.parametrize("N,H,C0,C1,cin,ksize,film,silu", [
     (2, 64, 128, 0, 128, 3, True, True),        # halo kernel, one image per box, FiLM (ResBlock out_layers norm)
     (3, 32, 256, 128, 256, 3, False, True),     # concat input of the norm: x slab comes from two tensors
