@@ -563,6 +563,7 @@ static int launch_igemm2(const IgemmKParams& kp, cudaStream_t st) {
 // tap-streaming kernel (operand reads + TMA fills > 128 B/clk/SM).  A and B tiles run in separate rings with their own
 // producer warps: an A stage lives for nine B stages.
 //   warp 0 A producer | warp 1 MMA | warps 2-5 epilogue | warp 6 staging manager | warp 7 B producer
+constexpr int kGnWarps = 8;       // transform warps of the GroupNorm-on-load variants (cdae_igemm_desc.gn_*)
 constexpr int kHaloRows = 180;
 constexpr int kHaloBytes = kHaloRows * 128;            // 23040
 constexpr int kHaloStride = 23 * 1024;                 // tiles 1024 B aligned
@@ -571,8 +572,9 @@ __device__ __forceinline__ uint64_t smem_desc_kmajor_sw128_sbo(uint32_t saddr, u
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
-template <int BN, int MT, int AST, int BST, int NS>
-__global__ void __launch_bounds__(256, 1) igemm3_kernel(const __grid_constant__ IgemmKParams p) {
+// GN: kGnWarps more warps normalise + activate every halo tile in place between the TMA load and the MMAs (see igemm3t_kernel)
+template <int BN, int MT, int AST, int BST, int NS, bool GN = false>
+__global__ void __launch_bounds__(GN ? 256 + 32 * kGnWarps : 256, 1) igemm3_kernel(const __grid_constant__ IgemmKParams p) {
   constexpr int kBTileBytes = BN * 128;
   constexpr int kAStage = MT * kHaloStride;
   constexpr int kSlabStride = 128 * 128;
@@ -587,8 +589,8 @@ __global__ void __launch_bounds__(256, 1) igemm3_kernel(const __grid_constant__ 
   uint8_t* bsm = smem + AST * kAStage;
   uint8_t* stg = bsm + BST * kBTileBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stg + NS * kSlabStride);
-  // bars: afull[AST] aempty[AST] bfull[BST] bempty[BST] tfull[2] tempty[2] sready[NS] sfree[NS]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * AST + 2 * BST + 4 + 2 * NS);
+  // bars: afull[AST] aempty[AST] bfull[BST] bempty[BST] tfull[2] tempty[2] sready[NS] sfree[NS] aready[AST]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * AST + 2 * BST + 4 + 2 * NS);
   constexpr int kABI = 1;                                     // the halo box is 8 x 16 pixels of ONE image
   const uint32_t abs_base = (smem_u32(tmem_slot) + 16 + 15) & ~15u;      // [NS][1] x 512 B, GroupNorm-backward fusion
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -602,9 +604,10 @@ __global__ void __launch_bounds__(256, 1) igemm3_kernel(const __grid_constant__ 
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * AST + 2 * BST + 2 + a); };
   auto sready_bar = [&](int b) { return bar_base + 8u * (2 * AST + 2 * BST + 4 + b); };
   auto sfree_bar = [&](int b) { return bar_base + 8u * (2 * AST + 2 * BST + 4 + NS + b); };
+  auto aready = [&](int s) { return bar_base + 8u * (2 * AST + 2 * BST + 4 + 2 * NS + s); };   // GN: tile transformed
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < AST; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
+    for (int s = 0; s < AST; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); mbar_init(aready(s), kGnWarps); }
     for (int s = 0; s < BST; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
     for (int b = 0; b < NS; ++b) { mbar_init(sready_bar(b), 1); mbar_init(sfree_bar(b), 1); }
@@ -686,7 +689,7 @@ __global__ void __launch_bounds__(256, 1) igemm3_kernel(const __grid_constant__ 
       for (int h = 0; h < p.nhs; ++h) {
         const int nch = p.hs[h].nchunk, ntap = p.hs[h].ntap;
         for (int j = 0; j < nch; ++j) {
-          mbar_wait(afull(sa), pha);
+          mbar_wait(GN ? aready(sa) : afull(sa), pha);
           for (int t = 0; t < ntap; ++t) {
             // tap index -> window origin inside the halo tile (flip: data-gradient taps are negated)
             const int ti = ntap == 9 ? (p.flip ? 8 - t : t) : 4;
@@ -721,26 +724,87 @@ __global__ void __launch_bounds__(256, 1) igemm3_kernel(const __grid_constant__ 
     }
   } else if (warp < 6) {
     igemm_epilogue<BN, MT, NS>(p, cx, warp, lane);
-  } else {
+  } else if (warp == 6) {
     igemm_stage_manager<BN, MT, NS>(p, cx, lane);
+  } else if (GN && warp >= 8) {
+    // ---------------------------------------------------------------- GroupNorm + SiLU on the halo tiles, in place
+    const int tt = (int)threadIdx.x - 256;
+    const uint32_t ck = (uint32_t)(tt & 7);                  // logical 16-byte chunk: channels ck*8 .. +7 of the 64
+    const int r0 = tt >> 3;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int tm = tile / p.ntn;
+      int cw[MT], chh[MT], cn[MT];
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const int box = tm * MT + m;
+        cw[m] = (box % p.tilesW) * 8 - 1;
+        chh[m] = ((box / p.tilesW) % p.tilesH) * 16 - 1;
+        cn[m] = box / boxes_per_img;
+      }
+      for (int h = 0; h < p.nhs; ++h) {
+        const int nch = p.hs[h].nchunk, col0 = p.gn_col[h];
+        for (int j = 0; j < nch; ++j) {
+          float2 ab[MT][8];
+          if (col0 >= 0) {
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+              if (cn[m] >= p.Nimg) continue;
+              const float4* q = reinterpret_cast<const float4*>(p.gn_ab + ((size_t)cn[m] * p.gn_c + col0 + j * 64 + ck * 8) * 2);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float4 v = __ldg(q + e);
+                ab[m][2 * e] = make_float2(v.x, v.y); ab[m][2 * e + 1] = make_float2(v.z, v.w);
+              }
+            }
+          }
+          mbar_wait(afull(s), ph);
+          if (col0 >= 0) {
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+              if (cn[m] >= p.Nimg) continue;                 // a box past the end: all zeros, stays so
+              const uint32_t tb = a_base + s * kAStage + m * kHaloStride;
+              for (int r = r0; r < kHaloRows; r += 4 * kGnWarps) {
+                const int hh = r / 10, ww = r - hh * 10;
+                if ((unsigned)(chh[m] + hh) >= (unsigned)p.OHt || (unsigned)(cw[m] + ww) >= (unsigned)p.OWt) continue;
+                const uint32_t a = tb + (uint32_t)r * 128u + ((ck ^ (uint32_t)(r & 7)) << 4);
+                float f[8];
+                unpack8(lds8(a), f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const float hv = fmaf(f[e], ab[m][e].x, ab[m][e].y);
+                  f[e] = fmaf(hv, tanh_fast(hv), hv);
+                }
+                sts8(a, pack8(f));
+              }
+            }
+            fence_proxy_async();
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(aready(s));
+          if (++s == AST) { s = 0; ph ^= 1; }
+        }
+      }
+    }
   }
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
 }
 
-template <int BN, int MT, int AST, int BST, int NS>
+template <int BN, int MT, int AST, int BST, int NS, bool GN = false>
 static int launch_igemm3(const IgemmKParams& kp, cudaStream_t st) {
-  constexpr int smem = AST * MT * kHaloStride + BST * BN * 128 + NS * 128 * 128 + 1024 + 512 + NS * 512 + 32;
+  constexpr int smem = AST * MT * kHaloStride + BST * BN * 128 + NS * 128 * 128 + 1024 + 512 + NS * 512 + 32 + 64;
   static_assert(smem <= 227 * 1024, "igemm3: shared memory budget");
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(igemm3_kernel<BN, MT, AST, BST, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_err = cudaFuncSetAttribute(igemm3_kernel<BN, MT, AST, BST, NS, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   });
   if (attr_err != cudaSuccess) { set_error("igemm3 smem attribute: %s", cudaGetErrorString(attr_err)); return CDAE_ERR_CUDA; }
   const int total = ((kp.nboxes + MT - 1) / MT) * kp.ntn;
   const int grid = total < kNumSMs ? total : kNumSMs;
-  igemm3_kernel<BN, MT, AST, BST, NS><<<grid, 256, smem, st>>>(kp);
+  igemm3_kernel<BN, MT, AST, BST, NS, GN><<<grid, GN ? 256 + 32 * kGnWarps : 256, smem, st>>>(kp);
   CDAE_CHECK_LAUNCH("igemm3_kernel");
   return CDAE_OK;
 }
@@ -779,7 +843,6 @@ __device__ __forceinline__ uint32_t bf16_bits(float f) {
 
 // GN: kGnWarps more warps (8..) normalise + activate every halo tile in place between the TMA load and the MMAs
 // (cdae_igemm_desc.gn_*): thread = one 16-byte chunk column (8 channels, constants in registers) x every (4 kGnWarps)-th row.
-constexpr int kGnWarps = 8;
 template <int AST, int BST, int NS, bool GN>
 __global__ void __launch_bounds__(GN ? 256 + 32 * kGnWarps : 256, 1) igemm3t_kernel(const __grid_constant__ IgemmKParams p) {
   constexpr int kWTileBytes = 128 * 128;                 // 128 output channels x 64 k
@@ -1282,9 +1345,9 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
   kp.nseg = d->nseg; kp.nkb = nkb; kp.nboxes = nboxes; kp.ntn = ntn;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
   if (d->gn_ab) {
-    CDAE_CHECK_SHAPE(use_t && !d->gnb_ws && d->gn_c > 0 && (reinterpret_cast<uintptr_t>(d->gn_ab) & 15) == 0 && d->gn_c % 4 == 0,
-                     "igemm: GroupNorm on load needs a 3x3 stride-1 layer with cout %% 128 == 0 on an image that tiles into 8x32 "
-                     "boxes, a 16-byte aligned table and gn_c %% 4 == 0");
+    CDAE_CHECK_SHAPE(halo && !d->gnb_ws && d->gn_c > 0 && (reinterpret_cast<uintptr_t>(d->gn_ab) & 15) == 0 && d->gn_c % 4 == 0,
+                     "igemm: GroupNorm on load needs a 3x3 stride-1 layer on an image that tiles into 8x16 boxes (the halo "
+                     "kernels), a 16-byte aligned table and gn_c %% 4 == 0");
     kp.gn_ab = d->gn_ab; kp.gn_c = d->gn_c;
     for (int h = 0; h < kp.nhs; ++h) {
       const int off = d->gn_off[kp.hs[h].src];
@@ -1295,7 +1358,16 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
       kp.gn_col[h] = off < 0 ? -1 : off + kp.hs[h].c0;
     }
     // three halo stages: load -> transform -> MMA are all in flight (2/5/3 and 2/4/4 measured 1-3 % slower, r2_gnload_bench)
-    return launch_igemm3t<3, 3, 3, true>(kp, st);
+    if (use_t) return launch_igemm3t<3, 3, 3, true>(kp, st);
+    switch (bn) {          // the pixel-major halo kernel (16x16 levels, narrow heads): one more halo stage where it fits
+      case 16: return launch_igemm3<16, 2, 3, 8, 3, true>(kp, st);
+      case 32: return launch_igemm3<32, 2, 3, 8, 3, true>(kp, st);
+      case 64: return mt == 2 ? launch_igemm3<64, 2, 3, 4, 3, true>(kp, st) : launch_igemm3<64, 1, 3, 8, 3, true>(kp, st);
+      case 128: return mt == 2 ? launch_igemm3<128, 2, 2, 5, 3, true>(kp, st) : launch_igemm3<128, 1, 3, 6, 3, true>(kp, st);
+      case 192: return launch_igemm3<192, 1, 3, 4, 3, true>(kp, st);
+      case 256: return launch_igemm3<256, 1, 3, 3, 3, true>(kp, st);
+      default: set_error("igemm: unsupported bn %d", bn); return CDAE_ERR_SHAPE;
+    }
   }
   if (use_t) {
     static const char* tcfg = getenv("CDAE_T_CFG");           // staging experiments: halo stages / weight stages / slabs

@@ -589,14 +589,14 @@ class Engine:
 
     def gn_on_load_ok(self, pl, cw, x0, x1):
         """inference only: can the 3x3 conv `cw` over [SiLU](FiLM(GroupNorm(concat(x0, x1)))) apply the norm while it loads?
-        (the transposed halo kernel: cout % 128 == 0, image tiles into 8 x 32 boxes; statistics from the producers)"""
+        (the halo kernels: the image tiles into 8 x 16 boxes - the 64x64 ... 16x16 levels; statistics from the producers)"""
         if pl.train or not GN_ON_LOAD:
             return False
         B, H, W = x0.shape[:3]
         if x0.stats is None or (x1 is not None and x1.stats is None):
             return False
         chans_ok = x0.shape[3] % 64 == 0 and (x1 is None or x1.shape[3] % 64 == 0)
-        return chans_ok and cw.cout % 128 == 0 and H % 32 == 0 and W % 8 == 0
+        return chans_ok and H % 16 == 0 and W % 8 == 0
 
     def plan_gn_constants(self, pl, x0, x1, gn, st, film=None, film_off=0):
         """the {a, b} table of [SiLU](FiLM(GroupNorm32(concat(x0, x1)))) for a conv that applies it on load"""
@@ -816,10 +816,13 @@ class Engine:
             h = run_block(blk, h, skip=hs.pop())
         gno, co = m.out[0], m.out[2]
         cwo = self.convs[id(co)]
-        a = T(pl, h.shape)
         sto = (pl.alloc((B, 32), th.float32), pl.alloc((B, 32), th.float32))
-        self.plan_gn_fwd(pl, h, None, gno, a, sto)
-        self.plan_conv(pl, cwo, [a], pl.eps, 3, out_mode=1)
+        if self.gn_on_load_ok(pl, cwo, h, None):
+            self.plan_conv(pl, cwo, [h], pl.eps, 3, out_mode=1, gn_ab=self.plan_gn_constants(pl, h, None, gno, sto))
+        else:
+            a = T(pl, h.shape)
+            self.plan_gn_fwd(pl, h, None, gno, a, sto)
+            self.plan_conv(pl, cwo, [a], pl.eps, 3, out_mode=1)
         if train:
             pl.deps_in = pl.alloc((B, m.out_channels, S, S), th.float32)
             dyo = pl.alloc((B, S, S, 64))

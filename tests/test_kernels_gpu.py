@@ -297,7 +297,10 @@ def test_igemm_dgrad_matches_autograd():
 
 
 @pytest.mark.parametrize("C0,C1,cout,H,film,skip", [(128, 0, 128, 64, False, 0), (128, 128, 128, 32, True, 0),
-                                                     (256, 0, 256, 32, True, 128), (384, 256, 256, 32, False, 0)])
+                                                     (256, 0, 256, 32, True, 128), (384, 256, 256, 32, False, 0),
+                                                     # the pixel-major halo kernel: 16x16 level, N tiles 192 / 128 / 64
+                                                     (384, 0, 384, 16, True, 0), (384, 384, 384, 16, False, 0),
+                                                     (256, 0, 384, 16, True, 256), (128, 0, 128, 16, False, 0), (64, 64, 64, 48, True, 0)])
 def test_conv_with_groupnorm_on_load_equals_the_two_pass_form(C0, C1, cout, H, film, skip):
     """inference: GroupNorm(+FiLM)+SiLU folded into the operand path of the 3x3 conv that consumes it
     (make_igemm_desc(gn=...), the transposed halo kernel's transform warps) == gn_apply_fwd followed by the conv, bit for
@@ -448,16 +451,39 @@ def test_igemm_channel_stats_rejects_unsupported():
         ops.igemm(d)
 
 
+def test_head_conv_with_groupnorm_on_load_fp32_nchw_output():
+    """the UNet head (GroupNorm -> SiLU -> conv 128 -> 3, fp32 NCHW output, ref unet.py:498) with the norm applied on load"""
+    from causaldiffae_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    N, H, C = 3, 32, 128
+    x = (torch.randn(N, H, H, C, generator=g) * 1.2 - 0.1).to(dev()).to(bf16)
+    xf = x.float()
+    st = torch.stack([xf.sum(dim=(1, 2)), (xf * xf).sum(dim=(1, 2))], dim=-1).contiguous()
+    gamma, beta = (1 + 0.2 * torch.randn(C, generator=g)).to(dev()), (0.2 * torch.randn(C, generator=g)).to(dev())
+    wp = torch.zeros(16, 9 * C, device=dev(), dtype=bf16)
+    wp[:3] = (torch.randn(3, 9 * C, generator=g) * 0.03).to(dev()).to(bf16)
+    b3 = torch.randn(3, generator=g).to(dev())
+    segs, _ = ops.conv_segments([C], 3)
+    a, _, _ = ops.gn_apply_fwd(x, st, gamma, beta, silu=True)
+    out_a = torch.empty(N, 3, H, H, device=dev())
+    ops.igemm(ops.make_igemm_desc([a], segs, wp, out_a, 3, bias=b3, out_mode=1))
+    ab = torch.empty(N, C, 2, device=dev())
+    ops.gn_apply_fwd(x, st, gamma, beta, silu=True, ab=ab, constants_only=True)
+    out_f = torch.full((N, 3, H, H), float("nan"), device=dev())
+    ops.igemm(ops.make_igemm_desc([x], segs, wp, out_f, 3, bias=b3, out_mode=1, gn=(ab, [0])))
+    assert torch.equal(out_f, out_a)
+
+
 def test_igemm_rejects_unsupported_groupnorm_on_load_and_output_placement():
     """the new descriptor fields fail loudly where the kernels cannot honour them (no silent fallback)"""
     from causaldiffae_b200 import ops
     from causaldiffae_b200._lib import CdaeError
     segs, _ = ops.conv_segments([64], 3)
     w = torch.randn(128, 9 * 64, device=dev()).to(bf16)
-    # GroupNorm on load on a 16x16 image: does not tile into 8 x 32 boxes
-    x = torch.randn(2, 16, 16, 64, device=dev()).to(bf16)
+    # GroupNorm on load on an 8x8 image: does not tile into 8 x 16 boxes (no halo kernel)
+    x = torch.randn(2, 8, 8, 64, device=dev()).to(bf16)
     ab = torch.zeros(2, 64, 2, device=dev())
-    d = ops.make_igemm_desc([x], segs, w, torch.empty(2, 16, 16, 128, device=dev(), dtype=bf16), 128, gn=(ab, [0]))
+    d = ops.make_igemm_desc([x], segs, w, torch.empty(2, 8, 8, 128, device=dev(), dtype=bf16), 128, gn=(ab, [0]))
     with pytest.raises(CdaeError):
         ops.igemm(d)
     # ... and a table that is too narrow for the source
