@@ -36,7 +36,7 @@ class IgemmDesc(C.Structure):
                 ("gnb_ws", C.c_void_p), ("gnb_ab", C.c_void_p), ("gnb_x0", C.c_void_p), ("gnb_x1", C.c_void_p),
                 ("gnb_c0", C.c_int32), ("gnb_ld0", C.c_int32), ("gnb_ld1", C.c_int32), ("gnb_silu", C.c_int32),
                 ("bias_img", C.c_void_p), ("bias_img_ld", C.c_int32),
-                ("gn_ab", C.c_void_p), ("gn_c", C.c_int32), ("gn_off", C.c_int32 * 4)]
+                ("gn_ab", C.c_void_p), ("gn_c", C.c_int32), ("gn_off", C.c_int32 * 4), ("up2x", C.c_int32)]
 
 
 class WgradDesc(C.Structure):

@@ -843,8 +843,15 @@ __device__ __forceinline__ uint32_t bf16_bits(float f) {
 
 // GN: kGnWarps more warps (8..) normalise + activate every halo tile in place between the TMA load and the MMAs
 // (cdae_igemm_desc.gn_*): thread = one 16-byte chunk column (8 channels, constants in registers) x every (4 kGnWarps)-th row.
-template <int AST, int BST, int NS, bool GN>
-__global__ void __launch_bounds__(GN ? 256 + 32 * kGnWarps : 256, 1) igemm3t_kernel(const __grid_constant__ IgemmKParams p) {
+// XF = 2 (cdae_igemm_desc.up2x): the sources are at HALF the output resolution; the halo producer loads the 6 x 18 low-resolution
+// pixels under a 10 x 34 halo tile and the transform warps expand them (nearest neighbour: row (r + 1) >> 1, column
+// (c + 1) >> 1) - F.interpolate(scale_factor=2) of unet.py:69-79 without the 4x tensor in HBM.
+constexpr int kLoTRows = 108;                          // 6 x 18 low-resolution pixels
+constexpr int kLoTBytes = kLoTRows * 128;              // 13824
+constexpr int kLoTStride = 14 * 1024;
+template <int AST, int BST, int NS, int XF>
+__global__ void __launch_bounds__(XF ? 256 + 32 * kGnWarps : 256, 1) igemm3t_kernel(const __grid_constant__ IgemmKParams p) {
+  constexpr bool GN = XF == 1, UP = XF == 2;
   constexpr int kWTileBytes = 128 * 128;                 // 128 output channels x 64 k
   constexpr int kSlabStride = 128 * 128;
   constexpr uint32_t kAccCols = 256;
@@ -854,9 +861,10 @@ __global__ void __launch_bounds__(GN ? 256 + 32 * kGnWarps : 256, 1) igemm3t_ker
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* wsm = smem + AST * kHaloTStride;
   uint8_t* stg = wsm + BST * kWTileBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + NS * kSlabStride);
-  // bars: hfull[AST] hempty[AST] wfull[BST] wempty[BST] tfull[2] tempty[2] sready[NS] sfree[NS] hready[AST]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * AST + 2 * BST + 4 + 2 * NS);
+  uint8_t* losm = stg + NS * kSlabStride;                 // UP: low-resolution tiles [AST]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(losm + (UP ? AST * kLoTStride : 0));
+  // bars: hfull[AST] hempty[AST] wfull[BST] wempty[BST] tfull[2] tempty[2] sready[NS] sfree[NS] hready[AST] lempty[AST]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * AST + 2 * BST + 4 + 2 * NS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t h_base = smem_u32(smem), w_base = smem_u32(wsm), stg_base = smem_u32(stg);
   const uint32_t bar_base = smem_u32(bars);
@@ -868,10 +876,14 @@ __global__ void __launch_bounds__(GN ? 256 + 32 * kGnWarps : 256, 1) igemm3t_ker
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * AST + 2 * BST + 2 + a); };
   auto sready_bar = [&](int b) { return bar_base + 8u * (2 * AST + 2 * BST + 4 + b); };
   auto sfree_bar = [&](int b) { return bar_base + 8u * (2 * AST + 2 * BST + 4 + NS + b); };
-  auto hready = [&](int s) { return bar_base + 8u * (2 * AST + 2 * BST + 4 + 2 * NS + s); };   // GN: tile transformed
+  auto hready = [&](int s) { return bar_base + 8u * (2 * AST + 2 * BST + 4 + 2 * NS + s); };   // XF: tile transformed
+  auto lempty = [&](int s) { return bar_base + 8u * (3 * AST + 2 * BST + 4 + 2 * NS + s); };   // UP: low-res tile consumed
+  const uint32_t lo_base = smem_u32(losm);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < AST; ++s) { mbar_init(hfull(s), 1); mbar_init(hempty(s), 1); mbar_init(hready(s), kGnWarps); }
+    for (int s = 0; s < AST; ++s) {
+      mbar_init(hfull(s), 1); mbar_init(hempty(s), 1); mbar_init(hready(s), kGnWarps); mbar_init(lempty(s), kGnWarps);
+    }
     for (int s = 0; s < BST; ++s) { mbar_init(wfull(s), 1); mbar_init(wempty(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
     for (int b = 0; b < NS; ++b) { mbar_init(sready_bar(b), 1); mbar_init(sfree_bar(b), 1); }
@@ -900,10 +912,15 @@ __global__ void __launch_bounds__(GN ? 256 + 32 * kGnWarps : 256, 1) igemm3t_ker
         const CUtensorMap* tma = &p.tmA[p.hs[h].src];
         const int c0 = p.hs[h].c0, nch = p.hs[h].nchunk;
         for (int j = 0; j < nch; ++j) {
-          mbar_wait(hempty(s), ph ^ 1);
+          mbar_wait(UP ? lempty(s) : hempty(s), ph ^ 1);
           if (elect_one()) {
-            mbar_expect_tx(hfull(s), kHaloTBytes);
-            tma_load_4d(h_base + s * kHaloTStride, tma, hfull(s), c0 + j * 64, cw, chh, cn);
+            if (UP) {      // (cw, chh) = high-resolution halo origin (odd): the low-resolution origin is its arithmetic half
+              mbar_expect_tx(hfull(s), kLoTBytes);
+              tma_load_4d(lo_base + s * kLoTStride, tma, hfull(s), c0 + j * 64, (cw - 1) / 2, (chh - 1) / 2, cn);
+            } else {
+              mbar_expect_tx(hfull(s), kHaloTBytes);
+              tma_load_4d(h_base + s * kHaloTStride, tma, hfull(s), c0 + j * 64, cw, chh, cn);
+            }
           }
           __syncwarp();
           if (++s == AST) { s = 0; ph ^= 1; }
@@ -943,7 +960,7 @@ __global__ void __launch_bounds__(GN ? 256 + 32 * kGnWarps : 256, 1) igemm3t_ker
       for (int h = 0; h < p.nhs; ++h) {
         const int nch = p.hs[h].nchunk, ntap = p.hs[h].ntap;
         for (int j = 0; j < nch; ++j) {
-          mbar_wait(GN ? hready(sa) : hfull(sa), pha);
+          mbar_wait(XF ? hready(sa) : hfull(sa), pha);
           for (int t = 0; t < ntap; ++t) {
             const int ti = ntap == 9 ? (p.flip ? 8 - t : t) : 4;
             const uint32_t row0 = (uint32_t)((ti / 3) * 10 + (ti % 3));
@@ -1086,6 +1103,33 @@ __global__ void __launch_bounds__(GN ? 256 + 32 * kGnWarps : 256, 1) igemm3t_ker
         }
       }
     }
+  } else if (UP && warp >= 8) {
+    // ---------------------------------------------------------------- nearest x2 expansion of the low-resolution tile
+    const int tt = (int)threadIdx.x - 256;
+    const uint32_t ck = (uint32_t)(tt & 7);
+    const int r0 = tt >> 3;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int h = 0; h < p.nhs; ++h) {
+        const int nch = p.hs[h].nchunk;
+        for (int j = 0; j < nch; ++j) {
+          mbar_wait(hfull(s), ph);                           // low-resolution tile landed
+          mbar_wait(hempty(s), ph ^ 1);                      // the MMAs are done with the previous contents of the halo tile
+          const uint32_t src = lo_base + s * kLoTStride, dst = h_base + s * kHaloTStride;
+          for (int r = r0; r < kHaloTRows; r += 4 * kGnWarps) {
+            const int hh = r / 10, ww = r - hh * 10;
+            const int lr = ((hh + 1) >> 1) * 6 + ((ww + 1) >> 1);
+            sts8(dst + (uint32_t)r * 128u + ((ck ^ (uint32_t)(r & 7)) << 4),
+                 lds8(src + (uint32_t)lr * 128u + ((ck ^ (uint32_t)(lr & 7)) << 4)));
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) { mbar_arrive(hready(s)); mbar_arrive(lempty(s)); }
+          if (++s == AST) { s = 0; ph ^= 1; }
+        }
+      }
+    }
   } else if (GN && warp >= 8) {
     // ---------------------------------------------------------------- GroupNorm + SiLU on the halo tile, in place
     // walks the halo stages in the producer's order; segments without a table (the 1x1-skip sources) pass through
@@ -1138,19 +1182,19 @@ __global__ void __launch_bounds__(GN ? 256 + 32 * kGnWarps : 256, 1) igemm3t_ker
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-template <int AST, int BST, int NS, bool GN = false>
+template <int AST, int BST, int NS, int XF = 0>
 static int launch_igemm3t(const IgemmKParams& kp, cudaStream_t st) {
-  constexpr int smem = AST * kHaloTStride + BST * 128 * 128 + NS * 128 * 128 + 1024 + 512;
+  constexpr int smem = AST * kHaloTStride + BST * 128 * 128 + NS * 128 * 128 + (XF == 2 ? AST * kLoTStride : 0) + 1024 + 512;
   static_assert(smem <= 227 * 1024, "igemm3t: shared memory budget");
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(igemm3t_kernel<AST, BST, NS, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_err = cudaFuncSetAttribute(igemm3t_kernel<AST, BST, NS, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   });
   if (attr_err != cudaSuccess) { set_error("igemm3t smem attribute: %s", cudaGetErrorString(attr_err)); return CDAE_ERR_CUDA; }
   const int total = kp.tilesW * (kp.OHt / 32) * kp.Nimg * kp.ntn;
   const int grid = total < kNumSMs ? total : kNumSMs;
-  igemm3t_kernel<AST, BST, NS, GN><<<grid, GN ? 256 + 32 * kGnWarps : 256, smem, st>>>(kp);
+  igemm3t_kernel<AST, BST, NS, XF><<<grid, XF ? 256 + 32 * kGnWarps : 256, smem, st>>>(kp);
   CDAE_CHECK_LAUNCH("igemm3t_kernel");
   return CDAE_OK;
 }
@@ -1227,9 +1271,11 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
   IgemmKParams kp;
   memset(&kp, 0, sizeof(kp));
   const int es = d->in_stride;
-  const int OHt = (d->H + es - 1) / es, OWt = (d->W + es - 1) / es;
+  const int up = d->up2x ? 2 : 1;                  // sources at half the output resolution (nearest x2 on load)
+  CDAE_CHECK_SHAPE(up == 1 || es == 1, "igemm: up2x needs a stride-1 conv");
+  const int OHt = up == 2 ? 2 * d->H : (d->H + es - 1) / es, OWt = up == 2 ? 2 * d->W : (d->W + es - 1) / es;
   static const bool no_halo = getenv("CDAE_NO_HALO") != nullptr;
-  const bool halo = !no_halo && halo_plan(d, kp);
+  const bool halo = !no_halo && halo_plan(d, kp) && OHt % 16 == 0 && OWt % 8 == 0;
   if (halo) { kp.BW = 8; kp.BH = 16; kp.BNI = 1; }
   else tile_geometry(128, OHt, OWt, &kp.BW, &kp.BH, &kp.BNI);
   kp.tilesW = (OWt + kp.BW - 1) / kp.BW;
@@ -1290,6 +1336,7 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
     uint64_t str[3] = {C * 2, C * 2 * d->W, C * 2 * (uint64_t)d->W * d->H};
     uint32_t box[4] = {64, (uint32_t)(kp.BW * es), (uint32_t)(kp.BH * es), (uint32_t)kp.BNI};
     if (halo) { box[1] = 10; box[2] = use_t ? 34 : 18; box[3] = 1; }     // output box + one pixel of halo on every side
+    if (up == 2) { box[1] = 6; box[2] = 18; }                           // the low-resolution pixels under a 10 x 34 halo tile
     uint32_t est[4] = {1, (uint32_t)es, (uint32_t)es, 1};
     int rc = make_tmap_bf16(&kp.tmA[i], d->src[i], 4, dims, str, box, est);
     if (rc) return rc;
@@ -1344,6 +1391,11 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
   }
   kp.nseg = d->nseg; kp.nkb = nkb; kp.nboxes = nboxes; kp.ntn = ntn;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
+  if (up == 2) {
+    CDAE_CHECK_SHAPE(use_t && !d->gn_ab && !d->gnb_ws && !d->resid,
+                     "igemm: up2x needs a plain 3x3 stride-1 layer with cout %% 128 == 0 whose output tiles into 8x32 boxes");
+    return launch_igemm3t<2, 3, 3, 2>(kp, st);
+  }
   if (d->gn_ab) {
     CDAE_CHECK_SHAPE(halo && !d->gnb_ws && d->gn_c > 0 && (reinterpret_cast<uintptr_t>(d->gn_ab) & 15) == 0 && d->gn_c % 4 == 0,
                      "igemm: GroupNorm on load needs a 3x3 stride-1 layer on an image that tiles into 8x16 boxes (the halo "
@@ -1358,7 +1410,7 @@ extern "C" int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s) {
       kp.gn_col[h] = off < 0 ? -1 : off + kp.hs[h].c0;
     }
     // three halo stages: load -> transform -> MMA are all in flight (2/5/3 and 2/4/4 measured 1-3 % slower, r2_gnload_bench)
-    if (use_t) return launch_igemm3t<3, 3, 3, true>(kp, st);
+    if (use_t) return launch_igemm3t<3, 3, 3, 1>(kp, st);
     switch (bn) {          // the pixel-major halo kernel (16x16 levels, narrow heads): one more halo stage where it fits
       case 16: return launch_igemm3<16, 2, 3, 8, 3, true>(kp, st);
       case 32: return launch_igemm3<32, 2, 3, 8, 3, true>(kp, st);

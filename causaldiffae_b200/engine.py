@@ -44,6 +44,8 @@ FUSED_GN_BWD = os.environ.get("CDAE_FUSED_GN_BWD", "0") != "0"
 S2_DGRAD_CLASSES = os.environ.get("CDAE_S2_DGRAD_CLASSES", "1") != "0"
 # inference: GroupNorm(+FiLM)+SiLU applied by the consuming 3x3 conv while it loads its operand (no activated tensor)
 GN_ON_LOAD = os.environ.get("CDAE_GN_ON_LOAD", "1") != "0"
+# inference: nearest x2 upsampling expanded by the consuming conv from a low-resolution halo tile (no 4x tensor)
+UP_ON_LOAD = os.environ.get("CDAE_UP_ON_LOAD", "1") != "0"
 WGRAD_SIDE_STREAM = os.environ.get("CDAE_WGRAD_SIDE_STREAM", "1") != "0"
 
 
@@ -757,7 +759,16 @@ class Engine:
     def plan_upsample(self, pl, up, x):
         B, H, W, Cc = x.shape
         cw = self.convs[id(up.conv)]
-        u, out = T(pl, (B, 2 * H, 2 * W, Cc)), T(pl, (B, 2 * H, 2 * W, Cc))
+        out = T(pl, (B, 2 * H, 2 * W, Cc))
+        if not pl.train and UP_ON_LOAD and cw.cout % 128 == 0 and (2 * H) % 32 == 0 and (2 * W) % 8 == 0 and Cc % 64 == 0:
+            # inference: the conv expands the low-resolution halo tile itself (make_igemm_desc(up2x=True)): no 4x tensor
+            chans = [Cc]
+            segs, _ = ops.conv_segments(chans, 3)
+            st = out.stats = pl.alloc_stats(B, cw.cout) if FUSED_GN_STATS else None
+            d = ops.make_igemm_desc([x.t], segs, cw.fwd, out.t, cw.cout, bias=cw.bias, stats=st, up2x=True)
+            pl.add_fwd(lambda: ops.igemm(d))
+            return out
+        u = T(pl, (B, 2 * H, 2 * W, Cc))
         pl.add_fwd(lambda: ops.upsample2x(x.t, out=u.t))
         self.plan_conv(pl, cw, [u], out, 3, stats=True)
         if pl.train:

@@ -322,7 +322,7 @@ def conv_segments(chans, ksize=3, transposed=False, wk0=0, src0=0):
 
 
 def make_igemm_desc(srcs, segs, wgt, out, cout, in_stride=1, bias=None, resid=None, out_mode=0, sps=1, ooh=0, oow=0,
-                    bn=0, out_hw=None, bias2=None, stats=None, gnb=None, bias_img=None, gn=None):
+                    bn=0, out_hw=None, bias2=None, stats=None, gnb=None, bias_img=None, gn=None, up2x=False):
     """Fill a cdae_igemm_desc.  srcs: bf16 [N,H,W,C]; wgt: bf16 [rows, K]; out: bf16 NHWC or fp32 NCHW (out_mode 1).
     stats: optional fp32 [N, cout, 2] that the epilogue ACCUMULATES per-(image, channel) sum / sum of squares of the
     stored output into (zero it first) - the GroupNorm statistics of the consumer, see gn_apply_fwd."""
@@ -374,6 +374,7 @@ def make_igemm_desc(srcs, segs, wgt, out, cout, in_stride=1, bias=None, resid=No
     if bias_img is not None:       # fp32 [N, >= cout] view (row pitch = stride(0)): + bias_img[n, co] in the epilogue
         assert bias_img.dtype == torch.float32 and bias_img.stride(1) == 1 and bias_img.shape[0] == N
         d.bias_img, d.bias_img_ld = bias_img.data_ptr(), bias_img.stride(0)
+    d.up2x = int(bool(up2x))          # sources at half the output resolution, nearest x2 upsampling applied on load
     for i in range(4):
         d.gn_off[i] = -1
     if gn is not None:

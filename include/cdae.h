@@ -173,6 +173,11 @@ typedef struct {
    * with cout % 128 == 0 on images that tile into 8 x 32 boxes (the transposed halo kernel); bit-identical to running
    * cdae_gn_apply_fwd first. */
   const float* gn_ab; int32_t gn_c; int32_t gn_off[4];
+  /* up2x != 0: the sources are [N, H, W, C] at HALF the output resolution and the conv runs over their nearest-neighbour x2
+   * upsampling (Upsample: F.interpolate(scale_factor=2, mode="nearest") + conv3x3, unet.py:69-79) - expanded from a
+   * low-resolution halo tile in shared memory, the 4x tensor is never written.  Output [N, 2H, 2W, cout]; 3x3 stride-1
+   * layers with cout % 128 == 0 whose OUTPUT tiles into 8 x 32 boxes (the transposed halo kernel). */
+  int32_t up2x;
 } cdae_igemm_desc;
 int cdae_igemm(const cdae_igemm_desc* d, cdae_stream s);
 

@@ -451,6 +451,31 @@ def test_igemm_channel_stats_rejects_unsupported():
         ops.igemm(d)
 
 
+@pytest.mark.parametrize("N,H,C,cout", [(3, 16, 128, 128), (2, 32, 256, 256), (5, 16, 384, 384), (2, 16, 64, 128)])
+def test_conv_over_nearest_upsampling_on_load_equals_materialised(N, H, C, cout):
+    """Upsample (ref unet.py:69-79): conv3x3(F.interpolate(x, scale_factor=2, mode="nearest")) with the expansion done by the
+    conv's transform warps from a low-resolution halo tile (make_igemm_desc(up2x=True)) == upsample2x + conv, bit for bit,
+    and both against torch"""
+    from causaldiffae_b200 import ops
+    g = torch.Generator().manual_seed(N + H + C)
+    x = torch.randn(N, H, H, C, generator=g).to(dev()).to(bf16)
+    segs, K = ops.conv_segments([C], 3)
+    wt = (torch.randn(cout, C, 3, 3, generator=g) * (9 * C) ** -0.5).to(dev()).to(bf16).float()
+    w = pack_ohwi(wt)
+    bias = (0.1 * torch.randn(cout, generator=g)).to(dev())
+    u = ops.upsample2x(x)
+    out_a = torch.empty(N, 2 * H, 2 * H, cout, device=dev(), dtype=bf16)
+    st_a = torch.zeros(N, cout, 2, device=dev())
+    ops.igemm(ops.make_igemm_desc([u], segs, w, out_a, cout, bias=bias, stats=st_a))
+    out_f = torch.full((N, 2 * H, 2 * H, cout), float("nan"), device=dev(), dtype=bf16)
+    st_f = torch.zeros(N, cout, 2, device=dev())
+    ops.igemm(ops.make_igemm_desc([x], segs, w, out_f, cout, bias=bias, stats=st_f, up2x=True))
+    assert torch.equal(out_f, out_a)
+    assert relerr(st_f, st_a) < 1e-6
+    ref = F.conv2d(F.interpolate(nchw(x), scale_factor=2, mode="nearest"), wt, bias, padding=1)
+    assert relerr(nchw(out_f), ref) < 5e-3
+
+
 def test_head_conv_with_groupnorm_on_load_fp32_nchw_output():
     """the UNet head (GroupNorm -> SiLU -> conv 128 -> 3, fp32 NCHW output, ref unet.py:498) with the norm applied on load"""
     from causaldiffae_b200 import ops
