@@ -12,8 +12,9 @@ import causaldiffae_b200.nn as cnn
 
 out = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/r2_timeline.csv"
 what = sys.argv[2] if len(sys.argv) > 2 else "train"        # "ddim": two DDIM steps at 512 interventions instead
-torch.cuda.set_device(0)
-dev = torch.device("cuda", 0)
+_lr = int(os.environ.get("LOCAL_RANK", "0"))          # under torchrun: every rank runs, rank 0 reports
+torch.cuda.set_device(_lr)
+dev = torch.device("cuda", _lr)
 dist_util.setup_dist()
 logger.configure(dir="/tmp/cdae_prof", format_strs=[])
 cnn.RNG_MODE = "device"
@@ -70,6 +71,10 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         loop.run_step(x, dict(cond))
     torch.cuda.synchronize()
 import json, types
+if int(os.environ.get("RANK", "0")) != 0:          # under torchrun the other ranks only take part in the collectives
+    import torch.distributed as _d
+    _d.barrier()
+    sys.exit(0)
 trace = out.replace(".csv", "_trace.json")
 prof.export_chrome_trace(trace)
 tj = json.load(open(trace))
@@ -121,4 +126,12 @@ for k, (d, c) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:32]:
     print(f"{d:9.1f} us {c:4d}  {100 * d / busy:5.1f}%  {k}")
 gaps.sort(reverse=True)
 print("largest gaps (us, at):", [(round(g, 1), round(a)) for g, a in gaps[:12]])
+nccl = [(round(s_), round(d_)) for s_, d_, _, n_ in rows if "nccl" in n_.lower()]
+if nccl:
+    print("NCCL kernels (start_us, dur_us):", nccl)
+    tail = [(round(s_), round(d_), n_.split("(")[0][-40:]) for s_, d_, _, n_ in rows if s_ > rows[-1][0] - 1500]
+    print("last 1.5 ms:", tail[-40:])
 print("gap total by size: >5us", round(sum(g for g, _ in gaps if g > 5)), " 2-5us", round(sum(g for g, _ in gaps if 2 < g <= 5)), " <=2us", round(sum(g for g, _ in gaps if g <= 2)))
+import torch.distributed as _d
+if _d.is_initialized() and _d.get_world_size() > 1:
+    _d.barrier()
